@@ -154,3 +154,120 @@ class RefLib:
             raise RuntimeError("reference transcribe failed")
         return ids[:n].copy(), dict(mel_ms=tm[0], enc_ms=tm[1], prefill_ms=tm[2], decode_ms=tm[3],
                                     enc_tokens=T.value)
+
+
+class OracleLib:
+    """The plain-C restatement oracle/qasr_oracle.c (kind = "port"). Same surface as RefLib."""
+
+    def __init__(self, path=None):
+        path = path or os.path.join(HERE, "libqasr_oracle.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError("oracle/libqasr_oracle.so not built (run `make -C oracle oracle`)")
+        self.path = path
+        L = self.lib = C.CDLL(path)
+        L.qo_load.restype = C.c_void_p
+        L.qo_load.argtypes = [C.c_char_p]
+        L.qo_free.argtypes = [C.c_void_p]
+        L.qo_config.argtypes = [C.c_void_p, i32p]
+        L.qo_mel_spectrogram.restype = C.POINTER(C.c_float)
+        L.qo_mel_spectrogram.argtypes = [f32p, C.c_int, C.POINTER(C.c_int)]
+        L.qo_encoder_forward.restype = C.POINTER(C.c_float)
+        L.qo_encoder_forward.argtypes = [C.c_void_p, f32p, C.c_int, C.POINTER(C.c_int)]
+        L.qo_free_buf.argtypes = [C.c_void_p]
+        L.qo_set_kv_len.argtypes = [C.c_void_p, C.c_int]
+        L.qo_get_kv_len.restype = C.c_int
+        L.qo_get_kv_len.argtypes = [C.c_void_p]
+        L.qo_decoder_prefill.argtypes = [C.c_void_p, f32p, C.c_int]
+        L.qo_decoder_forward.restype = C.c_int
+        L.qo_decoder_forward.argtypes = [C.c_void_p, f32p]
+        L.qo_decoder_forward_logits.argtypes = [C.c_void_p, f32p, f32p]
+        L.qo_embed_token.argtypes = [C.c_void_p, C.c_int, f32p]
+        L.qo_read_kv.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, f32p]
+        L.qo_transcribe_ids.restype = C.c_int
+        L.qo_transcribe_ids.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int, i32p, f64p, C.POINTER(C.c_int)]
+        self.ctx = None
+        self.cfg = None
+
+    def threads_used(self, threads=0):
+        return os.cpu_count() or 1
+
+    def load(self, model_dir, threads=0):
+        self.ctx = self.lib.qo_load(model_dir.encode())
+        if not self.ctx:
+            raise RuntimeError(f"oracle failed to load {model_dir}")
+        cfg = np.zeros(12, np.int32)
+        self.lib.qo_config(self.ctx, cfg)
+        keys = ["enc_d_model", "enc_layers", "enc_heads", "enc_ffn_dim", "enc_output_dim", "dec_hidden",
+                "dec_layers", "dec_heads", "dec_kv_heads", "dec_head_dim", "dec_intermediate", "vocab_size"]
+        self.cfg = dict(zip(keys, (int(v) for v in cfg)))
+        return self
+
+    def close(self):
+        if self.ctx:
+            self.lib.qo_free(self.ctx)
+            self.ctx = None
+
+    def _take(self, ptr, n):
+        out = np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+        self.lib.qo_free_buf(ptr)
+        return out
+
+    def mel(self, samples):
+        samples = np.ascontiguousarray(samples, np.float32)
+        fr = C.c_int(0)
+        p = self.lib.qo_mel_spectrogram(samples, len(samples), C.byref(fr))
+        if not p:
+            return None
+        return self._take(p, 128 * fr.value).reshape(128, fr.value)
+
+    def encode(self, mel):
+        mel = np.ascontiguousarray(mel, np.float32)
+        T = C.c_int(0)
+        p = self.lib.qo_encoder_forward(self.ctx, mel, mel.shape[1], C.byref(T))
+        if not p:
+            return None
+        H = self.cfg["enc_output_dim"]
+        return self._take(p, T.value * H).reshape(T.value, H)
+
+    @property
+    def kv_len(self):
+        return self.lib.qo_get_kv_len(self.ctx)
+
+    @kv_len.setter
+    def kv_len(self, n):
+        self.lib.qo_set_kv_len(self.ctx, int(n))
+
+    def prefill(self, embeds):
+        embeds = np.ascontiguousarray(embeds, np.float32)
+        self.lib.qo_decoder_prefill(self.ctx, embeds, embeds.shape[0])
+
+    def step(self, embed):
+        return self.lib.qo_decoder_forward(self.ctx, np.ascontiguousarray(embed, np.float32))
+
+    def step_logits(self, embed):
+        out = np.empty(self.cfg["vocab_size"], np.float32)
+        self.lib.qo_decoder_forward_logits(self.ctx, np.ascontiguousarray(embed, np.float32), out)
+        return out
+
+    def embed(self, tok):
+        out = np.empty(self.cfg["dec_hidden"], np.float32)
+        self.lib.qo_embed_token(self.ctx, int(tok), out)
+        return out
+
+    def read_kv(self, layer, length):
+        kvd = self.cfg["dec_kv_heads"] * self.cfg["dec_head_dim"]
+        k = np.empty((length, kvd), np.float32)
+        v = np.empty((length, kvd), np.float32)
+        self.lib.qo_read_kv(self.ctx, layer, length, k, v)
+        return k, v
+
+    def transcribe_ids(self, samples, max_new):
+        samples = np.ascontiguousarray(samples, np.float32)
+        ids = np.zeros(max_new, np.int32)
+        tm = np.zeros(4, np.float64)
+        T = C.c_int(0)
+        n = self.lib.qo_transcribe_ids(self.ctx, samples, len(samples), max_new, ids, tm, C.byref(T))
+        if n < 0:
+            raise RuntimeError("oracle transcribe failed")
+        return ids[:n].copy(), dict(mel_ms=tm[0], enc_ms=tm[1], prefill_ms=tm[2], decode_ms=tm[3],
+                                    enc_tokens=T.value)
