@@ -1,0 +1,1005 @@
+// qasr_api.cu - C ABI of libqasr_cuda.so (see include/qasr_cuda.h): context, one-time HBM
+// upload of the safetensors checkpoint, the level-1 entry points (mel / encoder / prefill /
+// decode step / greedy loop) and their CUDA-graph plumbing.  No CPU fallback anywhere: every
+// path either launches sm_100a kernels or fails with an error code.
+#include "../../include/qasr_cuda.h"
+#include "qasr_internal.h"
+#include "qasr_safetensors.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <string>
+#include <vector>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+const char *qasr_cuda_last_error(void) { return g_err; }
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return set_err(QASR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define CKR(expr)              \
+    do {                       \
+        int r__ = (expr);      \
+        if (r__ != 0) return r__; \
+    } while (0)
+
+// ------------------------------------------------------------------ context
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4;
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct EncLayerW {
+    bf16_t *wqkv, *wo, *fc1, *fc2;
+    float *bqkv, *bo, *fc1b, *fc2b, *ln1w, *ln1b, *ln2w, *ln2b;
+};
+struct DecLayerW {
+    bf16_t *wqkv, *wo, *wgu, *wdown;
+    float *qn, *kn, *in_norm, *post_norm;
+};
+
+struct qasr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool loaded = false;
+    int nsplit = 2;
+    // config (reference qwen_config_t)
+    int d = 0, enc_layers = 0, enc_heads = 0, F = 0, H = 0, dec_layers = 0, heads = 16, kv_heads = 8, hd = 128, I = 0,
+        V = 151936;
+    // weights
+    std::vector<void *> owned; // every cudaMalloc'd weight block
+    float *c1w = nullptr, *c1b = nullptr, *c2b = nullptr, *c3b = nullptr;
+    bf16_t *c2w = nullptr, *c3w = nullptr, *conv_out = nullptr, *p1w = nullptr, *p2w = nullptr;
+    float *lnpw = nullptr, *lnpb = nullptr, *p1b = nullptr, *p2b = nullptr;
+    EncLayerW enc[32];
+    DecLayerW dec[48];
+    bf16_t *emb = nullptr;
+    float *final_norm = nullptr;
+    size_t weight_bytes = 0;
+    // constant tables
+    float *mel_cos = nullptr, *mel_sin = nullptr, *mel_win = nullptr, *mel_fb = nullptr, *pe = nullptr;
+    float *rope_cos = nullptr, *rope_sin = nullptr;
+    int rope_cap = 0;
+    // KV cache f32 [layers][kv_max][kv_heads*hd]
+    float *kv_k = nullptr, *kv_v = nullptr;
+    int kv_max = 0;
+    // decode-step state
+    float *x = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *attn_part = nullptr, *logits = nullptr,
+          *pending = nullptr, *part_val = nullptr;
+    int *part_idx = nullptr, *d_pos = nullptr, *d_done = nullptr, *d_step = nullptr, *d_tokens = nullptr;
+    unsigned *counters = nullptr;
+    int *h_tokens = nullptr, *dh_tokens = nullptr; // mapped pinned ring
+    int max_steps = 64;
+    int n_parts = 0;
+    bool has_pending = false;
+    int x_token = -1; // token whose embedding currently sits in x (or -1)
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    int graph_nodes = 0;
+    bool use_graph = true;
+    // scratch
+    DevBuf ws_samples, ws_meltmp, ws_mel, ws_enc, ws_encout, ws_pre, ws_ids, ws_geom;
+    int *d_gmax = nullptr;
+    int mel_frames = 0, enc_T = 0;
+    cudaEvent_t ev[5] = {};
+    double last_decode_ms = 0.0;
+    long long launches = 0;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ lifecycle
+int qasr_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+qasr_ctx_t *qasr_cuda_init(int device) {
+    int n = qasr_cuda_device_count();
+    if (n <= 0) { set_err(QASR_ERR_CUDA, "no CUDA device visible: libqasr_cuda has no CPU fallback"); return nullptr; }
+    if (device < 0 || device >= n) { set_err(QASR_ERR_ARG, "device %d out of range (%d visible)", device, n); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) { set_err(QASR_ERR_CUDA, "cudaSetDevice(%d) failed", device); return nullptr; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        set_err(QASR_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+        return nullptr;
+    }
+    qasr_ctx_t *c = new qasr_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_err(QASR_ERR_CUDA, "cudaStreamCreate failed");
+        delete c;
+        return nullptr;
+    }
+    for (int i = 0; i < 5; i++) cudaEventCreate(&c->ev[i]);
+    const char *ng = getenv("QASR_NO_GRAPH");
+    c->use_graph = !(ng && ng[0] == '1');
+    if (gemm_tc_init() != 0) {
+        set_err(QASR_ERR_CUDA, "%s", gemm_tc_error());
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+void qasr_cuda_free(qasr_ctx_t *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+    for (void *p : c->owned) cudaFree(p);
+    cudaFree(c->kv_k); cudaFree(c->kv_v); cudaFree(c->rope_cos); cudaFree(c->rope_sin);
+    if (c->h_tokens) cudaFreeHost(c->h_tokens);
+    c->ws_samples.release(); c->ws_meltmp.release(); c->ws_mel.release(); c->ws_enc.release();
+    c->ws_encout.release(); c->ws_pre.release(); c->ws_ids.release(); c->ws_geom.release();
+    for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int qasr_cuda_set_gemm_split(qasr_ctx_t *c, int nsplit) {
+    if (!c || (nsplit != 1 && nsplit != 2)) return set_err(QASR_ERR_ARG, "nsplit must be 1 or 2");
+    c->nsplit = nsplit;
+    return 0;
+}
+
+int qasr_cuda_config(const qasr_ctx_t *c, int *o) {
+    if (!c || !o) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
+    o[0] = c->d; o[1] = c->enc_layers; o[2] = c->enc_heads; o[3] = c->F; o[4] = c->H; o[5] = c->H;
+    o[6] = c->dec_layers; o[7] = c->heads; o[8] = c->kv_heads; o[9] = c->hd; o[10] = c->I; o[11] = c->V;
+    return 0;
+}
+
+double qasr_cuda_last_decode_ms(const qasr_ctx_t *c) { return c ? c->last_decode_ms : 0.0; }
+long long qasr_cuda_launch_count(const qasr_ctx_t *c) { return c ? c->launches : 0; }
+void qasr_set_threads(int n) { (void)n; }
+int qasr_get_num_cpus(void) { long n = sysconf(_SC_NPROCESSORS_ONLN); return n > 0 ? (int)n : 1; }
+
+// ------------------------------------------------------------------ weight upload
+static inline float bf16_to_f32(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+
+static void *dev_alloc(qasr_ctx_t *c, size_t bytes) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, align_up(bytes, 256)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    c->owned.push_back(p);
+    c->weight_bytes += bytes;
+    return p;
+}
+
+static const qst_tensor_t *need(qst_dir_t *st, const char *name, int *rc) {
+    const qst_tensor_t *t = qst_find(st, name);
+    if (!t) *rc = set_err(QASR_ERR_MODEL, "tensor not found: %s", name);
+    return t;
+}
+
+// f32-class tensor (norm weights, biases, conv1): BF16 upcast exactly, or F32 verbatim
+// (reference safetensors_get_f32, qwen_asr_safetensors.c:255-278)
+static float *up_f32(qasr_ctx_t *c, qst_dir_t *st, const char *name, int *rc) {
+    const qst_tensor_t *t = need(st, name, rc);
+    if (!t) return nullptr;
+    std::vector<float> h(t->numel);
+    if (t->dtype == QST_BF16) {
+        const uint16_t *s = (const uint16_t *)t->data;
+        for (size_t i = 0; i < t->numel; i++) h[i] = bf16_to_f32(s[i]);
+    } else if (t->dtype == QST_F32) {
+        memcpy(h.data(), t->data, t->numel * 4);
+    } else { *rc = set_err(QASR_ERR_MODEL, "unsupported dtype for %s", name); return nullptr; }
+    float *d = (float *)dev_alloc(c, t->numel * 4);
+    if (!d || cudaMemcpy(d, h.data(), t->numel * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+        *rc = set_err(QASR_ERR_CUDA, "upload failed: %s", name);
+        return nullptr;
+    }
+    return d;
+}
+
+static const uint16_t *host_bf16(qst_dir_t *st, const char *name, size_t expect_numel, int *rc) {
+    const qst_tensor_t *t = need(st, name, rc);
+    if (!t) return nullptr;
+    if (t->dtype != QST_BF16) { *rc = set_err(QASR_ERR_MODEL, "%s must be BF16 (matrix weights are uploaded verbatim)", name); return nullptr; }
+    if (expect_numel && t->numel != expect_numel) { *rc = set_err(QASR_ERR_MODEL, "%s has %zu elements, expected %zu", name, t->numel, expect_numel); return nullptr; }
+    return (const uint16_t *)t->data;
+}
+
+// bf16 matrix uploaded verbatim from the mmap (north_star item 5)
+static bf16_t *up_bf16(qasr_ctx_t *c, qst_dir_t *st, const char *name, size_t numel, int *rc) {
+    const uint16_t *h = host_bf16(st, name, numel, rc);
+    if (!h) return nullptr;
+    bf16_t *d = (bf16_t *)dev_alloc(c, numel * 2);
+    if (!d || cudaMemcpy(d, h, numel * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *rc = set_err(QASR_ERR_CUDA, "upload failed: %s", name); return nullptr; }
+    return d;
+}
+
+// several bf16 matrices stacked along rows into one device matrix (fused QKV)
+static bf16_t *up_bf16_cat(qasr_ctx_t *c, qst_dir_t *st, const char *const *names, const size_t *numels, int n, int *rc) {
+    size_t total = 0;
+    for (int i = 0; i < n; i++) total += numels[i];
+    bf16_t *d = (bf16_t *)dev_alloc(c, total * 2);
+    if (!d) { *rc = set_err(QASR_ERR_NOMEM, "cudaMalloc failed"); return nullptr; }
+    size_t off = 0;
+    for (int i = 0; i < n; i++) {
+        const uint16_t *h = host_bf16(st, names[i], numels[i], rc);
+        if (!h) return nullptr;
+        if (cudaMemcpy(d + off, h, numels[i] * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *rc = set_err(QASR_ERR_CUDA, "upload failed: %s", names[i]); return nullptr; }
+        off += numels[i];
+    }
+    return d;
+}
+
+static float *up_f32_cat(qasr_ctx_t *c, qst_dir_t *st, const char *const *names, int n, int each, int *rc) {
+    std::vector<float> h((size_t)n * each);
+    for (int i = 0; i < n; i++) {
+        const qst_tensor_t *t = need(st, names[i], rc);
+        if (!t) return nullptr;
+        if ((int)t->numel != each) { *rc = set_err(QASR_ERR_MODEL, "%s: bad size", names[i]); return nullptr; }
+        if (t->dtype == QST_BF16) for (int k = 0; k < each; k++) h[(size_t)i * each + k] = bf16_to_f32(((const uint16_t *)t->data)[k]);
+        else if (t->dtype == QST_F32) memcpy(&h[(size_t)i * each], t->data, (size_t)each * 4);
+        else { *rc = set_err(QASR_ERR_MODEL, "unsupported dtype for %s", names[i]); return nullptr; }
+    }
+    float *d = (float *)dev_alloc(c, h.size() * 4);
+    if (!d || cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { *rc = set_err(QASR_ERR_CUDA, "upload failed"); return nullptr; }
+    return d;
+}
+
+static bf16_t *up_host_vec(qasr_ctx_t *c, const std::vector<uint16_t> &h, int *rc) {
+    bf16_t *d = (bf16_t *)dev_alloc(c, h.size() * 2);
+    if (!d || cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) { *rc = set_err(QASR_ERR_CUDA, "upload failed"); return nullptr; }
+    return d;
+}
+static float *up_host_f32(qasr_ctx_t *c, const std::vector<float> &h, int *rc) {
+    float *d = (float *)dev_alloc(c, h.size() * 4);
+    if (!d || cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { *rc = set_err(QASR_ERR_CUDA, "upload failed"); return nullptr; }
+    return d;
+}
+
+// Slaney mel filterbank, reference qwen_asr_audio.c:236-287.  Stored [201][128] (bin-major).
+static float hz_to_mel(float f) { return f >= 1000.0f ? 15.0f + logf(f / 1000.0f) * (27.0f / logf(6.4f)) : 3.0f * f / 200.0f; }
+static float mel_to_hz(float m) { return m >= 15.0f ? 1000.0f * expf((logf(6.4f) / 27.0f) * (m - 15.0f)) : 200.0f * m / 3.0f; }
+
+static int build_tables(qasr_ctx_t *c) {
+    int rc = 0;
+    std::vector<float> ct(400 * 208, 0.0f), st(400 * 208, 0.0f), win(400), fb(201 * 128, 0.0f);
+    for (int k = 0; k < 201; k++)
+        for (int j = 0; j < 400; j++) { // f32 angle exactly as the reference forms it (:330-335)
+            float ang = 2.0f * (float)M_PI * (float)k * (float)j / (float)400;
+            ct[j * 208 + k] = cosf(ang);
+            st[j * 208 + k] = sinf(ang);
+        }
+    for (int i = 0; i < 400; i++) win[i] = 0.5f * (1.0f - cosf(2.0f * (float)M_PI * (float)i / (float)400));
+    float pts[130];
+    const float mmin = hz_to_mel(0.0f), mmax = hz_to_mel(8000.0f);
+    for (int i = 0; i < 130; i++) pts[i] = mel_to_hz(mmin + (mmax - mmin) * (float)i / 129.0f);
+    for (int m = 0; m < 128; m++) {
+        float dl = pts[m + 1] - pts[m], dr = pts[m + 2] - pts[m + 1];
+        if (dl == 0.0f) dl = 1e-6f;
+        if (dr == 0.0f) dr = 1e-6f;
+        const float en = 2.0f / (pts[m + 2] - pts[m]);
+        for (int f = 0; f < 201; f++) {
+            const float hz = (float)f * 8000.0f / 200.0f;
+            float v = fminf((hz - pts[m]) / dl, (pts[m + 2] - hz) / dr);
+            fb[f * 128 + m] = (v < 0.0f ? 0.0f : v) * en;
+        }
+    }
+    c->mel_cos = up_host_f32(c, ct, &rc); c->mel_sin = up_host_f32(c, st, &rc);
+    c->mel_win = up_host_f32(c, win, &rc); c->mel_fb = up_host_f32(c, fb, &rc);
+    // per-chunk sinusoidal PE table [13][d], reference qwen_asr_kernels.c:1198-1211
+    std::vector<float> pe((size_t)13 * c->d);
+    const int half = c->d / 2;
+    const float lt = logf(10000.0f) / (float)(half - 1);
+    for (int p = 0; p < 13; p++)
+        for (int i = 0; i < half; i++) {
+            const float ang = (float)p * expf(-(float)i * lt);
+            pe[(size_t)p * c->d + i] = sinf(ang);
+            pe[(size_t)p * c->d + half + i] = cosf(ang);
+        }
+    c->pe = up_host_f32(c, pe, &rc);
+    return rc;
+}
+
+// RoPE cos/sin [pos][64] with the reference's f32 formula (qwen_asr_decoder.c:253-302)
+static int ensure_rope(qasr_ctx_t *c, int need_pos) {
+    if (need_pos <= c->rope_cap) return 0;
+    int cap = c->rope_cap ? c->rope_cap : 4096;
+    while (cap < need_pos) cap *= 2;
+    std::vector<float> hc((size_t)cap * 64), hs((size_t)cap * 64);
+    float inv[64];
+    for (int d = 0; d < 64; d++) inv[d] = 1.0f / powf(1e6f, (float)(2 * d) / 128.0f);
+    for (int p = 0; p < cap; p++)
+        for (int d = 0; d < 64; d++) {
+            const float ang = (float)p * inv[d];
+            hc[(size_t)p * 64 + d] = cosf(ang);
+            hs[(size_t)p * 64 + d] = sinf(ang);
+        }
+    CK(cudaStreamSynchronize(c->stream));
+    float *nc = nullptr, *ns = nullptr;
+    CK(cudaMalloc(&nc, hc.size() * 4));
+    CK(cudaMalloc(&ns, hs.size() * 4));
+    CK(cudaMemcpy(nc, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ns, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice));
+    cudaFree(c->rope_cos); cudaFree(c->rope_sin);
+    c->rope_cos = nc; c->rope_sin = ns; c->rope_cap = cap;
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; } // pointers changed
+    return 0;
+}
+
+// KV cache growth keeps rows [0,keep) of every layer (reference kv_cache_grow, qwen_asr_decoder.c:179-206)
+static int ensure_kv(qasr_ctx_t *c, int need_pos, int keep) {
+    if (need_pos <= c->kv_max) return 0;
+    int cap = c->kv_max ? c->kv_max : 2048;
+    while (cap < need_pos) cap *= 2;
+    const size_t kvd = (size_t)c->kv_heads * c->hd;
+    const size_t bytes = (size_t)c->dec_layers * cap * kvd * 4;
+    float *nk = nullptr, *nv = nullptr;
+    CK(cudaStreamSynchronize(c->stream));
+    if (cudaMalloc(&nk, bytes) != cudaSuccess || cudaMalloc(&nv, bytes) != cudaSuccess) {
+        cudaGetLastError(); cudaFree(nk);
+        return set_err(QASR_ERR_NOMEM, "KV cache allocation of %zu bytes failed", 2 * bytes);
+    }
+    if (c->kv_k && keep > 0)
+        for (int l = 0; l < c->dec_layers; l++) {
+            CK(cudaMemcpy(nk + (size_t)l * cap * kvd, c->kv_k + (size_t)l * c->kv_max * kvd, (size_t)keep * kvd * 4, cudaMemcpyDeviceToDevice));
+            CK(cudaMemcpy(nv + (size_t)l * cap * kvd, c->kv_v + (size_t)l * c->kv_max * kvd, (size_t)keep * kvd * 4, cudaMemcpyDeviceToDevice));
+        }
+    cudaFree(c->kv_k); cudaFree(c->kv_v);
+    c->kv_k = nk; c->kv_v = nv; c->kv_max = cap;
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    return 0;
+}
+
+int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
+    if (!c || !model_dir) return set_err(QASR_ERR_ARG, "null argument");
+    if (c->loaded) return set_err(QASR_ERR_STATE, "context already holds a model");
+    CK(cudaSetDevice(c->device));
+    qst_dir_t *st = qst_open_dir(model_dir);
+    if (!st) return set_err(QASR_ERR_MODEL, "cannot open safetensors in %s", model_dir);
+    int rc = 0;
+    // variant probe, reference qwen_asr.c:146-203 (dims are hard-coded there; config.json is not read)
+    if (qst_find(st, "thinker.audio_tower.layers.31.self_attn.q_proj.weight")) {
+        qst_close(st);
+        return set_err(QASR_ERR_MODEL, "Qwen3-Omni-30B-MoE checkpoints are out of scope for this path");
+    }
+    const bool big = qst_find(st, "thinker.audio_tower.layers.18.self_attn.q_proj.weight") != nullptr;
+    c->d = big ? 1024 : 896; c->enc_layers = big ? 24 : 18; c->enc_heads = big ? 16 : 14; c->F = big ? 4096 : 3584;
+    c->H = big ? 2048 : 1024; c->dec_layers = 28; c->heads = 16; c->kv_heads = 8; c->hd = 128; c->I = big ? 6144 : 3072;
+    c->V = 151936;
+    const int d = c->d, F = c->F, H = c->H, I = c->I;
+    char n0[256], n1[256], n2[256];
+#define E "thinker.audio_tower."
+    c->c1w = up_f32(c, st, E "conv2d1.weight", &rc); c->c1b = up_f32(c, st, E "conv2d1.bias", &rc);
+    c->c2b = up_f32(c, st, E "conv2d2.bias", &rc); c->c3b = up_f32(c, st, E "conv2d3.bias", &rc);
+    for (int cv = 2; cv <= 3 && rc == 0; cv++) { // [oc][ic][ki][kj] -> [oc][(ki*3+kj)*480 + ic]
+        snprintf(n0, sizeof n0, E "conv2d%d.weight", cv);
+        const uint16_t *h = host_bf16(st, n0, (size_t)480 * 480 * 9, &rc);
+        if (!h) break;
+        std::vector<uint16_t> perm((size_t)480 * 4320);
+        for (int oc = 0; oc < 480; oc++)
+            for (int ic = 0; ic < 480; ic++)
+                for (int t = 0; t < 9; t++) perm[(size_t)oc * 4320 + t * 480 + ic] = h[((size_t)oc * 480 + ic) * 9 + t];
+        (cv == 2 ? c->c2w : c->c3w) = up_host_vec(c, perm, &rc);
+    }
+    if (rc == 0) { // conv_out [d][ch*16+f] -> [d][f*480+ch]
+        const uint16_t *h = host_bf16(st, E "conv_out.weight", (size_t)d * 7680, &rc);
+        if (h) {
+            std::vector<uint16_t> perm((size_t)d * 7680);
+            for (int n = 0; n < d; n++)
+                for (int ch = 0; ch < 480; ch++)
+                    for (int f = 0; f < 16; f++) perm[(size_t)n * 7680 + f * 480 + ch] = h[(size_t)n * 7680 + ch * 16 + f];
+            c->conv_out = up_host_vec(c, perm, &rc);
+        }
+    }
+    for (int l = 0; l < c->enc_layers && rc == 0; l++) {
+        EncLayerW &L = c->enc[l];
+        snprintf(n0, sizeof n0, E "layers.%d.self_attn.q_proj.weight", l);
+        snprintf(n1, sizeof n1, E "layers.%d.self_attn.k_proj.weight", l);
+        snprintf(n2, sizeof n2, E "layers.%d.self_attn.v_proj.weight", l);
+        const char *wn[3] = {n0, n1, n2};
+        const size_t ne[3] = {(size_t)d * d, (size_t)d * d, (size_t)d * d};
+        L.wqkv = up_bf16_cat(c, st, wn, ne, 3, &rc);
+        snprintf(n0, sizeof n0, E "layers.%d.self_attn.q_proj.bias", l);
+        snprintf(n1, sizeof n1, E "layers.%d.self_attn.k_proj.bias", l);
+        snprintf(n2, sizeof n2, E "layers.%d.self_attn.v_proj.bias", l);
+        L.bqkv = up_f32_cat(c, st, wn, 3, d, &rc);
+#define LN(field, suffix) snprintf(n0, sizeof n0, E "layers.%d." suffix, l); L.field = up_f32(c, st, n0, &rc)
+        snprintf(n0, sizeof n0, E "layers.%d.self_attn.out_proj.weight", l); L.wo = up_bf16(c, st, n0, (size_t)d * d, &rc);
+        LN(bo, "self_attn.out_proj.bias");
+        LN(ln1w, "self_attn_layer_norm.weight"); LN(ln1b, "self_attn_layer_norm.bias");
+        snprintf(n0, sizeof n0, E "layers.%d.fc1.weight", l); L.fc1 = up_bf16(c, st, n0, (size_t)F * d, &rc);
+        LN(fc1b, "fc1.bias");
+        snprintf(n0, sizeof n0, E "layers.%d.fc2.weight", l); L.fc2 = up_bf16(c, st, n0, (size_t)d * F, &rc);
+        LN(fc2b, "fc2.bias");
+        LN(ln2w, "final_layer_norm.weight"); LN(ln2b, "final_layer_norm.bias");
+#undef LN
+    }
+    if (rc == 0) {
+        c->lnpw = up_f32(c, st, E "ln_post.weight", &rc); c->lnpb = up_f32(c, st, E "ln_post.bias", &rc);
+        c->p1w = up_bf16(c, st, E "proj1.weight", (size_t)d * d, &rc); c->p1b = up_f32(c, st, E "proj1.bias", &rc);
+        c->p2w = up_bf16(c, st, E "proj2.weight", (size_t)H * d, &rc); c->p2b = up_f32(c, st, E "proj2.bias", &rc);
+    }
+#undef E
+    if (rc == 0) c->emb = up_bf16(c, st, "thinker.model.embed_tokens.weight", (size_t)c->V * H, &rc);
+    for (int l = 0; l < c->dec_layers && rc == 0; l++) {
+        DecLayerW &L = c->dec[l];
+#define P "thinker.model.layers.%d."
+        snprintf(n0, sizeof n0, P "self_attn.q_proj.weight", l);
+        snprintf(n1, sizeof n1, P "self_attn.k_proj.weight", l);
+        snprintf(n2, sizeof n2, P "self_attn.v_proj.weight", l);
+        const char *wn[3] = {n0, n1, n2};
+        const size_t ne[3] = {(size_t)2048 * H, (size_t)1024 * H, (size_t)1024 * H};
+        L.wqkv = up_bf16_cat(c, st, wn, ne, 3, &rc);
+        snprintf(n0, sizeof n0, P "self_attn.o_proj.weight", l); L.wo = up_bf16(c, st, n0, (size_t)H * 2048, &rc);
+        snprintf(n0, sizeof n0, P "mlp.down_proj.weight", l); L.wdown = up_bf16(c, st, n0, (size_t)H * I, &rc);
+        snprintf(n0, sizeof n0, P "self_attn.q_norm.weight", l); L.qn = up_f32(c, st, n0, &rc);
+        snprintf(n0, sizeof n0, P "self_attn.k_norm.weight", l); L.kn = up_f32(c, st, n0, &rc);
+        snprintf(n0, sizeof n0, P "input_layernorm.weight", l); L.in_norm = up_f32(c, st, n0, &rc);
+        snprintf(n0, sizeof n0, P "post_attention_layernorm.weight", l); L.post_norm = up_f32(c, st, n0, &rc);
+        // gate/up rows interleaved [g0,u0,g1,u1,...] (reference qwen_asr_decoder.c:140-152) so SwiGLU
+        // pairs are adjacent GEMV rows / GEMM columns and fuse into the epilogue
+        snprintf(n0, sizeof n0, P "mlp.gate_proj.weight", l);
+        snprintf(n1, sizeof n1, P "mlp.up_proj.weight", l);
+#undef P
+        if (rc) break;
+        const uint16_t *g = host_bf16(st, n0, (size_t)I * H, &rc), *u = host_bf16(st, n1, (size_t)I * H, &rc);
+        if (!g || !u) break;
+        std::vector<uint16_t> gu((size_t)2 * I * H);
+        for (int r = 0; r < I; r++) {
+            memcpy(&gu[(size_t)(2 * r) * H], g + (size_t)r * H, (size_t)H * 2);
+            memcpy(&gu[(size_t)(2 * r + 1) * H], u + (size_t)r * H, (size_t)H * 2);
+        }
+        L.wgu = up_host_vec(c, gu, &rc);
+    }
+    if (rc == 0) c->final_norm = up_f32(c, st, "thinker.model.norm.weight", &rc);
+    qst_close(st);
+    if (rc) return rc;
+    CKR(build_tables(c));
+
+    // decode-step state
+    auto dalloc = [&](size_t bytes) -> void * { void *p = dev_alloc(c, bytes); if (p) cudaMemset(p, 0, bytes); return p; };
+    c->n_parts = argmax_num_parts(c->V);
+    c->x = (float *)dalloc((size_t)H * 4); c->pending = (float *)dalloc((size_t)H * 4);
+    c->qkv = (float *)dalloc(4096 * 4); c->attn = (float *)dalloc(2048 * 4); c->act = (float *)dalloc((size_t)I * 4);
+    c->attn_part = (float *)dalloc((size_t)8 * QASR_ATTN_SPLITS * 2 * QASR_ATTN_PART_STRIDE * 4);
+    c->logits = (float *)dalloc((size_t)c->V * 4);
+    c->part_val = (float *)dalloc((size_t)c->n_parts * 4); c->part_idx = (int *)dalloc((size_t)c->n_parts * 4);
+    c->counters = (unsigned *)dalloc(8 * 4);
+    c->d_pos = (int *)dalloc(4); c->d_done = (int *)dalloc(4); c->d_step = (int *)dalloc(4);
+    c->d_tokens = (int *)dalloc((size_t)c->max_steps * 4);
+    c->d_gmax = (int *)dalloc(4);
+    if (!c->x || !c->logits || !c->d_gmax) return set_err(QASR_ERR_NOMEM, "state allocation failed");
+    CK(cudaHostAlloc((void **)&c->h_tokens, (size_t)c->max_steps * 4, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void **)&c->dh_tokens, c->h_tokens, 0));
+    CKR(ensure_kv(c, 2048, 0));
+    CKR(ensure_rope(c, 4096));
+    c->loaded = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------ mel
+int qasr_cuda_mel_frames(int n_samples) { return n_samples / 160; }
+
+int qasr_cuda_encoder_tokens(int frames) {
+    int T = 0;
+    for (int s = 0; s < frames; s += 100) {
+        int w = frames - s < 100 ? frames - s : 100;
+        w = (w - 1) / 2 + 1; w = (w - 1) / 2 + 1; w = (w - 1) / 2 + 1;
+        T += w;
+    }
+    return T;
+}
+
+static int mel_device(qasr_ctx_t *c, const float *samples, int n, int *frames_out) {
+    const int frames = n / 160; // (n + 400 - 400)/160 + 1 - 1, reference :311-312
+    if (frames <= 0) return set_err(QASR_ERR_ARG, "audio too short (%d samples)", n); // reference returns NULL (:313-317)
+    if (c->ws_samples.reserve((size_t)n * 4) || c->ws_meltmp.reserve((size_t)frames * 128 * 4) || c->ws_mel.reserve((size_t)frames * 128 * 4))
+        return set_err(QASR_ERR_NOMEM, "mel workspace allocation failed");
+    CK(cudaMemcpyAsync(c->ws_samples.p, samples, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_mel(c->stream, c->ws_samples.as<float>(), n, frames, c->mel_cos, c->mel_sin, c->mel_win, c->mel_fb,
+               c->ws_meltmp.as<float>(), c->d_gmax, c->ws_mel.as<float>());
+    c->launches += 3;
+    CK(cudaGetLastError());
+    c->mel_frames = frames;
+    *frames_out = frames;
+    return 0;
+}
+
+int qasr_cuda_mel(qasr_ctx_t *c, const float *samples, int n_samples, float *mel_out, int *out_frames) {
+    if (!c || !samples || !out_frames) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
+    CK(cudaSetDevice(c->device));
+    int frames = 0;
+    CKR(mel_device(c, samples, n_samples, &frames));
+    if (mel_out) CK(cudaMemcpyAsync(mel_out, c->ws_mel.p, (size_t)frames * 128 * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *out_frames = frames;
+    return 0;
+}
+
+// ------------------------------------------------------------------ encoder
+static int gemm(qasr_ctx_t *c, const bf16_t *a_hi, const bf16_t *a_lo, int M, int K, const bf16_t *W, int N, int mode,
+                float *of, bf16_t *ohi, bf16_t *olo, const float *bias, int ldo) {
+    GemmEpilogue e;
+    e.mode = mode; e.out_f32 = of; e.out_hi = ohi; e.out_lo = (c->nsplit == 2) ? olo : nullptr; e.bias = bias; e.ldo = ldo;
+    if (launch_gemm_tc(c->stream, a_hi, c->nsplit == 2 ? a_lo : nullptr, M, K, W, N, e) != 0)
+        return set_err(QASR_ERR_CUDA, "%s", gemm_tc_error());
+    c->launches += 1;
+    return 0;
+}
+
+// mel (device, [128, frames]) -> encoder output rows in c->ws_encout ([T, H] f32)
+static int encode_device(qasr_ctx_t *c, const float *d_mel, int frames, int *T_out) {
+    const int d = c->d, F = c->F, H = c->H;
+    const int nc = (frames + 99) / 100;
+    std::vector<int> geom((size_t)nc * 2 + 3 * (nc + 1));
+    int *w0 = geom.data(), *m0 = w0 + nc, *o1 = m0 + nc, *o2 = o1 + nc + 1, *o3 = o2 + nc + 1;
+    o1[0] = o2[0] = o3[0] = 0;
+    for (int i = 0; i < nc; i++) {
+        const int w = frames - i * 100 < 100 ? frames - i * 100 : 100;
+        const int w1 = (w - 1) / 2 + 1, w2 = (w1 - 1) / 2 + 1, w3 = (w2 - 1) / 2 + 1;
+        w0[i] = w; m0[i] = i * 100;
+        o1[i + 1] = o1[i] + w1 * 64; o2[i + 1] = o2[i] + w2 * 32; o3[i + 1] = o3[i] + w3 * 16;
+    }
+    const int tot1 = o1[nc], tot2 = o2[nc], tot3 = o3[nc], T = tot3 / 16;
+    const int nwin = (T + 103) / 104; // 13 * (800/100) tokens per window, reference qwen_asr_encoder.c:291-297
+    std::vector<int> aux((size_t)T + nwin + 1);
+    { // per-token PE row (position restarts in every chunk) and window starts
+        int t = 0;
+        for (int i = 0; i < nc; i++) { const int w3 = (o3[i + 1] - o3[i]) / 16; for (int k = 0; k < w3; k++) aux[t++] = k; }
+        for (int w = 0; w < nwin; w++) aux[T + w] = w * 104;
+        aux[T + nwin] = T;
+    }
+    if (c->ws_geom.reserve((geom.size() + aux.size()) * 4)) return set_err(QASR_ERR_NOMEM, "geom alloc");
+    int *dg = c->ws_geom.as<int>();
+    CK(cudaMemcpyAsync(dg, geom.data(), geom.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(dg + geom.size(), aux.data(), aux.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream)); // host vectors go out of scope below
+    ConvGeom g;
+    g.n_chunks = nc; g.d_w0 = dg; g.d_mel0 = dg + nc; g.d_off1 = dg + 2 * nc; g.d_off2 = g.d_off1 + nc + 1; g.d_off3 = g.d_off2 + nc + 1;
+    g.total1 = tot1; g.total2 = tot2; g.total3 = tot3;
+    const int *d_rowpos = dg + geom.size(), *d_win = d_rowpos + T;
+
+    // workspace carve (all offsets 256-byte aligned)
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_act1 = carve((size_t)tot1 * 480 * 2 * 2), o_col2 = carve((size_t)tot2 * 4320 * 2 * 2),
+                 o_act2 = carve((size_t)tot2 * 480 * 2 * 2), o_col3 = carve((size_t)tot3 * 4320 * 2 * 2),
+                 o_act3 = carve((size_t)tot3 * 480 * 2 * 2), o_x = carve((size_t)T * d * 4),
+                 o_xn = carve((size_t)T * d * 2 * 2), o_qkv = carve((size_t)T * 3 * d * 4),
+                 o_att = carve((size_t)T * d * 2 * 2), o_mid = carve((size_t)T * F * 2 * 2);
+    if (c->ws_enc.reserve(off) || c->ws_encout.reserve((size_t)T * H * 4)) return set_err(QASR_ERR_NOMEM, "encoder workspace (%zu bytes)", off);
+    uint8_t *B = c->ws_enc.as<uint8_t>();
+#define HI(o) reinterpret_cast<bf16_t *>(B + (o))
+#define LO(o, n) (reinterpret_cast<bf16_t *>(B + (o)) + (size_t)(n))
+    cudaStream_t s = c->stream;
+    const bool two = c->nsplit == 2;
+    // conv stem, reference qwen_asr_encoder.c:221-276
+    launch_conv1(s, d_mel, frames, c->c1w, c->c1b, g, HI(o_act1), two ? LO(o_act1, (size_t)tot1 * 480) : nullptr);
+    launch_im2col_stage(s, HI(o_act1), HI(o_col2), g, 2);
+    if (two) launch_im2col_stage(s, LO(o_act1, (size_t)tot1 * 480), LO(o_col2, (size_t)tot2 * 4320), g, 2);
+    c->launches += two ? 3 : 2;
+    CKR(gemm(c, HI(o_col2), LO(o_col2, (size_t)tot2 * 4320), tot2, 4320, c->c2w, 480, QASR_GEMM_GELU_SPLIT, nullptr,
+             HI(o_act2), LO(o_act2, (size_t)tot2 * 480), c->c2b, 480));
+    launch_im2col_stage(s, HI(o_act2), HI(o_col3), g, 3);
+    if (two) launch_im2col_stage(s, LO(o_act2, (size_t)tot2 * 480), LO(o_col3, (size_t)tot3 * 4320), g, 3);
+    c->launches += two ? 2 : 1;
+    CKR(gemm(c, HI(o_col3), LO(o_col3, (size_t)tot3 * 4320), tot3, 4320, c->c3w, 480, QASR_GEMM_GELU_SPLIT, nullptr,
+             HI(o_act3), LO(o_act3, (size_t)tot3 * 480), c->c3b, 480));
+    float *x = reinterpret_cast<float *>(B + o_x);
+    CKR(gemm(c, HI(o_act3), LO(o_act3, (size_t)tot3 * 480), T, 7680, c->conv_out, d, QASR_GEMM_F32, x, nullptr, nullptr, nullptr, d));
+    launch_add_rows(s, x, c->pe, d_rowpos, T, d);
+    c->launches += 1;
+    // transformer, reference qwen_asr_encoder.c:312-347
+    float *qkv = reinterpret_cast<float *>(B + o_qkv);
+    bf16_t *xn_hi = HI(o_xn), *xn_lo = LO(o_xn, (size_t)T * d), *at_hi = HI(o_att), *at_lo = LO(o_att, (size_t)T * d),
+           *mid_hi = HI(o_mid), *mid_lo = LO(o_mid, (size_t)T * F);
+    for (int l = 0; l < c->enc_layers; l++) {
+        const EncLayerW &L = c->enc[l];
+        launch_layernorm(s, x, L.ln1w, L.ln1b, 1e-5f, T, d, nullptr, xn_hi, two ? xn_lo : nullptr);
+        CKR(gemm(c, xn_hi, xn_lo, T, d, L.wqkv, 3 * d, QASR_GEMM_F32, qkv, nullptr, nullptr, L.bqkv, 3 * d));
+        launch_attn_windowed(s, qkv, qkv + d, qkv + 2 * d, 3 * d, c->enc_heads, d_win, nwin, 104, 0.125f, d, nullptr, at_hi, two ? at_lo : nullptr);
+        CKR(gemm(c, at_hi, at_lo, T, d, L.wo, d, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, L.bo, d));
+        launch_layernorm(s, x, L.ln2w, L.ln2b, 1e-5f, T, d, nullptr, xn_hi, two ? xn_lo : nullptr);
+        CKR(gemm(c, xn_hi, xn_lo, T, d, L.fc1, F, QASR_GEMM_GELU_SPLIT, nullptr, mid_hi, mid_lo, L.fc1b, F));
+        CKR(gemm(c, mid_hi, mid_lo, T, F, L.fc2, d, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, L.fc2b, d));
+        c->launches += 3;
+    }
+    // tail, reference qwen_asr_encoder.c:350-361
+    launch_layernorm(s, x, c->lnpw, c->lnpb, 1e-5f, T, d, nullptr, xn_hi, two ? xn_lo : nullptr);
+    CKR(gemm(c, xn_hi, xn_lo, T, d, c->p1w, d, QASR_GEMM_GELU_SPLIT, nullptr, at_hi, at_lo, c->p1b, d));
+    CKR(gemm(c, at_hi, at_lo, T, d, c->p2w, H, QASR_GEMM_F32, c->ws_encout.as<float>(), nullptr, nullptr, c->p2b, H));
+    c->launches += 1;
+#undef HI
+#undef LO
+    CK(cudaGetLastError());
+    c->enc_T = T;
+    *T_out = T;
+    return 0;
+}
+
+int qasr_cuda_encode(qasr_ctx_t *c, const float *mel, int mel_frames, float *enc_out, int *out_tokens) {
+    if (!c || !out_tokens) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
+    CK(cudaSetDevice(c->device));
+    const float *d_mel;
+    if (mel) {
+        if (mel_frames <= 0) return set_err(QASR_ERR_ARG, "mel_frames must be positive");
+        if (c->ws_mel.reserve((size_t)mel_frames * 128 * 4)) return set_err(QASR_ERR_NOMEM, "mel alloc");
+        CK(cudaMemcpyAsync(c->ws_mel.p, mel, (size_t)mel_frames * 128 * 4, cudaMemcpyHostToDevice, c->stream));
+        c->mel_frames = mel_frames;
+    } else {
+        if (c->mel_frames <= 0) return set_err(QASR_ERR_STATE, "no device-resident mel: call qasr_cuda_mel first");
+        mel_frames = c->mel_frames;
+    }
+    d_mel = c->ws_mel.as<float>();
+    int T = 0;
+    CKR(encode_device(c, d_mel, mel_frames, &T));
+    if (enc_out) CK(cudaMemcpyAsync(enc_out, c->ws_encout.p, (size_t)T * c->H * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *out_tokens = T;
+    return 0;
+}
+
+// ------------------------------------------------------------------ decoder prefill
+// x: device [P, H] f32 rows inside ws_pre (offset 0).  reference qwen_asr_decoder.c:457-563
+static int prefill_device(qasr_ctx_t *c, int P, int kv_len) {
+    const int H = c->H, I = c->I;
+    CKR(ensure_kv(c, kv_len + P + 1, kv_len));
+    CKR(ensure_rope(c, kv_len + P + 1));
+    uint8_t *B = c->ws_pre.as<uint8_t>();
+    size_t off = align_up((size_t)P * H * 4, 256);
+    auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
+    const size_t o_xn = carve((size_t)P * H * 4), o_qkv = carve((size_t)P * 4096 * 4), o_q = carve((size_t)P * 2048 * 4),
+                 o_att = carve((size_t)P * 2048 * 4), o_act = carve((size_t)P * I * 4);
+    if (off > c->ws_pre.cap) return set_err(QASR_ERR_STATE, "prefill workspace not reserved");
+    float *x = reinterpret_cast<float *>(B);
+    bf16_t *xn_hi = reinterpret_cast<bf16_t *>(B + o_xn), *xn_lo = xn_hi + (size_t)P * H;
+    float *qkv = reinterpret_cast<float *>(B + o_qkv), *q = reinterpret_cast<float *>(B + o_q);
+    bf16_t *at_hi = reinterpret_cast<bf16_t *>(B + o_att), *at_lo = at_hi + (size_t)P * 2048;
+    bf16_t *ac_hi = reinterpret_cast<bf16_t *>(B + o_act), *ac_lo = ac_hi + (size_t)P * I;
+    cudaStream_t s = c->stream;
+    const bool two = c->nsplit == 2;
+    const size_t kvd = (size_t)c->kv_heads * c->hd;
+    const float scale = 1.0f / sqrtf((float)c->hd);
+    for (int l = 0; l < c->dec_layers; l++) {
+        const DecLayerW &L = c->dec[l];
+        float *kc = c->kv_k + (size_t)l * c->kv_max * kvd, *vc = c->kv_v + (size_t)l * c->kv_max * kvd;
+        launch_rmsnorm(s, x, L.in_norm, 1e-6f, P, H, nullptr, xn_hi, two ? xn_lo : nullptr);
+        CKR(gemm(c, xn_hi, xn_lo, P, H, L.wqkv, 4096, QASR_GEMM_F32, qkv, nullptr, nullptr, nullptr, 4096));
+        launch_qk_norm_rope_store(s, qkv, L.qn, L.kn, c->rope_cos, c->rope_sin, kv_len, P, 1e-6f, q, kc, vc);
+        launch_attn_prefill(s, q, kc, vc, kv_len, P, kv_len + P, c->heads, c->kv_heads, scale, nullptr, at_hi, two ? at_lo : nullptr);
+        CKR(gemm(c, at_hi, at_lo, P, 2048, L.wo, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H));
+        launch_rmsnorm(s, x, L.post_norm, 1e-6f, P, H, nullptr, xn_hi, two ? xn_lo : nullptr);
+        CKR(gemm(c, xn_hi, xn_lo, P, H, L.wgu, 2 * I, QASR_GEMM_SWIGLU_SPLIT, nullptr, ac_hi, ac_lo, nullptr, I));
+        CKR(gemm(c, ac_hi, ac_lo, P, I, L.wdown, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H));
+        c->launches += 4;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int reserve_prefill(qasr_ctx_t *c, int P) {
+    const size_t H = c->H, I = c->I, p = P;
+    size_t bytes = align_up(p * H * 4, 256) * 2 + align_up(p * 4096 * 4, 256) + align_up(p * 2048 * 4, 256) * 2 + align_up(p * I * 4, 256);
+    if (c->ws_pre.reserve(bytes)) return set_err(QASR_ERR_NOMEM, "prefill workspace (%zu bytes)", bytes);
+    return 0;
+}
+
+int qasr_cuda_prefill_embeds(qasr_ctx_t *c, const float *embeds, int seq_len, int kv_len) {
+    if (!c || !embeds) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
+    if (seq_len <= 0) return 0;
+    if (kv_len < 0) return set_err(QASR_ERR_ARG, "negative kv_len");
+    CK(cudaSetDevice(c->device));
+    CKR(reserve_prefill(c, seq_len));
+    CK(cudaMemcpyAsync(c->ws_pre.p, embeds, (size_t)seq_len * c->H * 4, cudaMemcpyHostToDevice, c->stream));
+    CKR(prefill_device(c, seq_len, kv_len));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// rows = embed(pre) | encoder rows | embed(suf); prefill all but the last row, keep it pending.
+static int prefill_prompt_device(qasr_ctx_t *c, const int *pre, int n_pre, int n_audio, const int *suf, int n_suf, int kv_len) {
+    if (n_audio > c->enc_T) return set_err(QASR_ERR_STATE, "n_audio=%d exceeds the %d encoder rows on the device", n_audio, c->enc_T);
+    const int total = n_pre + n_audio + n_suf, H = c->H;
+    if (total < 1) return set_err(QASR_ERR_ARG, "empty prompt");
+    CKR(reserve_prefill(c, total));
+    if (c->ws_ids.reserve((size_t)(n_pre + n_suf + 1) * 4)) return set_err(QASR_ERR_NOMEM, "ids alloc");
+    int *d_ids = c->ws_ids.as<int>();
+    float *x = c->ws_pre.as<float>();
+    if (n_pre) CK(cudaMemcpyAsync(d_ids, pre, (size_t)n_pre * 4, cudaMemcpyHostToDevice, c->stream));
+    if (n_suf) CK(cudaMemcpyAsync(d_ids + n_pre, suf, (size_t)n_suf * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_embed_gather(c->stream, c->emb, d_ids, n_pre, H, x);
+    if (n_audio) CK(cudaMemcpyAsync(x + (size_t)n_pre * H, c->ws_encout.p, (size_t)n_audio * H * 4, cudaMemcpyDeviceToDevice, c->stream));
+    launch_embed_gather(c->stream, c->emb, d_ids + n_pre, n_suf, H, x + (size_t)(n_pre + n_audio) * H);
+    c->launches += 2;
+    CK(cudaMemcpyAsync(c->pending, x + (size_t)(total - 1) * H, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
+    c->has_pending = true;
+    if (total > 1) CKR(prefill_device(c, total - 1, kv_len));
+    return 0;
+}
+
+int qasr_cuda_prefill_prompt(qasr_ctx_t *c, const int *pre_ids, int n_pre, int n_audio, const int *suf_ids, int n_suf, int kv_len) {
+    if (!c || (n_pre > 0 && !pre_ids) || (n_suf > 0 && !suf_ids)) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
+    if (n_pre < 0 || n_audio < 0 || n_suf < 0 || kv_len < 0) return set_err(QASR_ERR_ARG, "negative count");
+    for (int i = 0; i < n_pre; i++) if (pre_ids[i] < 0 || pre_ids[i] >= c->V) return set_err(QASR_ERR_ARG, "token id out of range");
+    for (int i = 0; i < n_suf; i++) if (suf_ids[i] < 0 || suf_ids[i] >= c->V) return set_err(QASR_ERR_ARG, "token id out of range");
+    CK(cudaSetDevice(c->device));
+    CKR(prefill_prompt_device(c, pre_ids, n_pre, n_audio, suf_ids, n_suf, kv_len));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ decode step
+// One token through the 28 blocks, input row in c->x, position in *d_pos.
+// reference qwen_asr_decoder.c:632-678.  5 launches per layer.
+static void enqueue_layers(qasr_ctx_t *c, cudaStream_t s) {
+    const int H = c->H, I = c->I;
+    const size_t kvd = (size_t)c->kv_heads * c->hd;
+    for (int l = 0; l < c->dec_layers; l++) {
+        const DecLayerW &L = c->dec[l];
+        float *kc = c->kv_k + (size_t)l * c->kv_max * kvd, *vc = c->kv_v + (size_t)l * c->kv_max * kvd;
+        launch_gemv_bf16(s, L.wqkv, c->x, L.in_norm, 1e-6f, c->qkv, nullptr, nullptr, 4096, H, QASR_EPI_STORE, c->d_done);
+        launch_attn_decode(s, c->qkv, L.qn, L.kn, c->rope_cos, c->rope_sin, kc, vc, c->d_pos, c->attn_part, c->counters, c->attn, 1e-6f);
+        launch_gemv_bf16(s, L.wo, c->attn, nullptr, 0.f, c->x, c->x, nullptr, H, 2048, QASR_EPI_RESIDUAL, c->d_done);
+        launch_gemv_bf16(s, L.wgu, c->x, L.post_norm, 1e-6f, c->act, nullptr, nullptr, 2 * I, H, QASR_EPI_SWIGLU, c->d_done);
+        launch_gemv_bf16(s, L.wdown, c->act, nullptr, 0.f, c->x, c->x, nullptr, H, I, QASR_EPI_RESIDUAL, c->d_done);
+    }
+}
+static void enqueue_greedy_head(qasr_ctx_t *c, cudaStream_t s) {
+    launch_argmax_gemv(s, c->emb, c->x, c->final_norm, 1e-6f, c->V, c->H, c->part_val, c->part_idx, c->d_done);
+    launch_argmax_finalize(s, c->part_val, c->part_idx, c->n_parts, c->emb, c->H, c->x, c->d_tokens, c->d_step, c->d_pos,
+                           c->d_done, c->dh_tokens, c->max_steps);
+}
+static const int kStepKernels = 28 * 5 + 2;
+
+static int ensure_graph(qasr_ctx_t *c) {
+    if (!c->use_graph || c->graph_exec) return 0;
+    if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    enqueue_layers(c, c->stream);
+    enqueue_greedy_head(c, c->stream);
+    CK(cudaStreamEndCapture(c->stream, &c->graph));
+    CK(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
+    return 0;
+}
+
+// Enqueue n greedy steps (each consumes c->x, leaves the next embedding in c->x).
+static int enqueue_steps(qasr_ctx_t *c, int n) {
+    if (c->use_graph) {
+        CKR(ensure_graph(c));
+        for (int i = 0; i < n; i++) CK(cudaGraphLaunch(c->graph_exec, c->stream));
+    } else {
+        for (int i = 0; i < n; i++) { enqueue_layers(c, c->stream); enqueue_greedy_head(c, c->stream); }
+        CK(cudaGetLastError());
+    }
+    c->launches += (long long)n * kStepKernels;
+    return 0;
+}
+
+static int step_common(qasr_ctx_t *c, int kv_len, int *out_token) {
+    CKR(ensure_kv(c, kv_len + 2, kv_len));
+    CKR(ensure_rope(c, kv_len + 2));
+    launch_set_state(c->stream, c->d_pos, kv_len, c->d_done, 0, c->d_step, 0);
+    c->launches += 1;
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    CKR(enqueue_steps(c, 1));
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->last_decode_ms = ms;
+    const int tok = c->h_tokens[0];
+    c->x_token = tok;
+    if (out_token) *out_token = tok;
+    return 0;
+}
+
+int qasr_cuda_step_embed(qasr_ctx_t *c, const float *embed, int kv_len, int *out_token) {
+    if (!c || !embed || !out_token) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
+    if (kv_len < 0) return set_err(QASR_ERR_ARG, "negative kv_len");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->x, embed, (size_t)c->H * 4, cudaMemcpyHostToDevice, c->stream));
+    return step_common(c, kv_len, out_token);
+}
+
+static int load_token_embedding(qasr_ctx_t *c, int token_id) {
+    if (token_id < 0 || token_id >= c->V) return set_err(QASR_ERR_ARG, "token id %d out of range", token_id);
+    if (c->x_token == token_id) return 0; // already gathered by the previous step's finalize
+    if (c->ws_ids.reserve(64)) return set_err(QASR_ERR_NOMEM, "ids alloc");
+    CK(cudaMemcpyAsync(c->ws_ids.p, &token_id, 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream)); // token_id is a stack variable
+    launch_embed_gather(c->stream, c->emb, c->ws_ids.as<int>(), 1, c->H, c->x);
+    c->launches += 1;
+    c->x_token = token_id;
+    return 0;
+}
+
+int qasr_cuda_step_token(qasr_ctx_t *c, int token_id, int kv_len, int *out_token) {
+    if (!c || !out_token) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
+    if (kv_len < 0) return set_err(QASR_ERR_ARG, "negative kv_len");
+    CK(cudaSetDevice(c->device));
+    CKR(load_token_embedding(c, token_id));
+    return step_common(c, kv_len, out_token);
+}
+
+int qasr_cuda_step_pending(qasr_ctx_t *c, int kv_len, int *out_token) {
+    if (!c || !out_token) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded || !c->has_pending) return set_err(QASR_ERR_STATE, "no pending row: call qasr_cuda_prefill_prompt first");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->x, c->pending, (size_t)c->H * 4, cudaMemcpyDeviceToDevice, c->stream));
+    c->has_pending = false;
+    return step_common(c, kv_len, out_token);
+}
+
+int qasr_cuda_step_logits(qasr_ctx_t *c, const float *embed, int kv_len, float *logits) {
+    if (!c || !embed || !logits) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
+    if (kv_len < 0) return set_err(QASR_ERR_ARG, "negative kv_len");
+    CK(cudaSetDevice(c->device));
+    CKR(ensure_kv(c, kv_len + 2, kv_len));
+    CKR(ensure_rope(c, kv_len + 2));
+    CK(cudaMemcpyAsync(c->x, embed, (size_t)c->H * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_set_state(c->stream, c->d_pos, kv_len, c->d_done, 0, c->d_step, 0);
+    enqueue_layers(c, c->stream);
+    // final RMSNorm fused into the lm_head GEMV (reference qwen_asr_decoder.c:781-782)
+    launch_gemv_bf16(c->stream, c->emb, c->x, c->final_norm, 1e-6f, c->logits, nullptr, nullptr, c->V, c->H, QASR_EPI_STORE, nullptr);
+    c->launches += 28 * 5 + 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(logits, c->logits, (size_t)c->V * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->x_token = -1;
+    return 0;
+}
+
+// Greedy loop on the device; only ids cross PCIe.  reference qwen_asr.c:788-818
+static int generate_device(qasr_ctx_t *c, int first_token, int kv_len, int max_new, int *out_ids, int *out_n, int *out_kv) {
+    int n = 0;
+    if (max_new <= 0) { *out_n = 0; if (out_kv) *out_kv = kv_len; return 0; }
+    out_ids[n++] = first_token;
+    int tok = first_token;
+    int pos = kv_len;
+    if (tok != QASR_TOKEN_ENDOFTEXT && tok != QASR_TOKEN_IM_END && n < max_new) {
+        CKR(ensure_kv(c, kv_len + max_new + 1, kv_len));
+        CKR(ensure_rope(c, kv_len + max_new + 1));
+        CKR(load_token_embedding(c, tok));
+        CK(cudaEventRecord(c->ev[0], c->stream));
+        bool done = false;
+        while (!done && n < max_new) {
+            int chunk = max_new - n;
+            if (chunk > 16) chunk = 16;
+            if (chunk > c->max_steps) chunk = c->max_steps;
+            launch_set_state(c->stream, c->d_pos, pos, c->d_done, 0, c->d_step, 0);
+            c->launches += 1;
+            CKR(enqueue_steps(c, chunk));
+            CK(cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < chunk; i++) {
+                tok = c->h_tokens[i];
+                out_ids[n++] = tok;
+                pos++;
+                if (tok == QASR_TOKEN_ENDOFTEXT || tok == QASR_TOKEN_IM_END) { done = true; break; }
+            }
+        }
+        CK(cudaEventRecord(c->ev[1], c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+        c->last_decode_ms = ms;
+        c->x_token = tok;
+    }
+    *out_n = n;
+    if (out_kv) *out_kv = pos;
+    return 0;
+}
+
+int qasr_cuda_generate(qasr_ctx_t *c, int first_token, int kv_len, int max_new, int *out_ids, int *out_n, int *out_kv_len) {
+    if (!c || !out_ids || !out_n) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
+    if (kv_len < 0) return set_err(QASR_ERR_ARG, "negative kv_len");
+    CK(cudaSetDevice(c->device));
+    return generate_device(c, first_token, kv_len, max_new, out_ids, out_n, out_kv_len);
+}
+
+// Whole offline segment. reference transcribe_segment, qwen_asr.c:649-842
+int qasr_cuda_transcribe_ids(qasr_ctx_t *c, const float *samples, int n_samples, int max_new, int *out_ids, int *out_n,
+                             double *timings_ms, int *out_enc_tokens) {
+    static const int PRE[] = {151644, 8948, 198, 151645, 198, 151644, 872, 198, 151669}; // qwen_asr.c:388-393
+    static const int SUF[] = {151670, 151645, 198, 151644, 77091, 198};                  // qwen_asr.c:394-396
+    if (!c || !samples || !out_ids || !out_n) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
+    CK(cudaSetDevice(c->device));
+    int frames = 0, T = 0, first = 0;
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    CKR(mel_device(c, samples, n_samples, &frames));
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    CKR(encode_device(c, c->ws_mel.as<float>(), frames, &T));
+    CK(cudaEventRecord(c->ev[3], c->stream));
+    CKR(prefill_prompt_device(c, PRE, 9, T, SUF, 6, 0));
+    CK(cudaMemcpyAsync(c->x, c->pending, (size_t)c->H * 4, cudaMemcpyDeviceToDevice, c->stream));
+    c->has_pending = false;
+    const int kv0 = 9 + T + 6 - 1;
+    CKR(ensure_kv(c, kv0 + max_new + 2, kv0));
+    CKR(ensure_rope(c, kv0 + max_new + 2));
+    launch_set_state(c->stream, c->d_pos, kv0, c->d_done, 0, c->d_step, 0);
+    c->launches += 1;
+    CKR(enqueue_steps(c, 1));
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    first = c->h_tokens[0];
+    c->x_token = first;
+    float t_mel = 0, t_enc = 0, t_pre = 0;
+    cudaEventElapsedTime(&t_mel, c->ev[0], c->ev[2]);
+    cudaEventElapsedTime(&t_enc, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&t_pre, c->ev[3], c->ev[4]);
+    c->last_decode_ms = 0.0;
+    int kv_out = 0;
+    CKR(generate_device(c, first, kv0 + 1, max_new, out_ids, out_n, &kv_out));
+    if (timings_ms) { timings_ms[0] = t_mel; timings_ms[1] = t_enc; timings_ms[2] = t_pre; timings_ms[3] = c->last_decode_ms; }
+    if (out_enc_tokens) *out_enc_tokens = T;
+    return 0;
+}
+
+// ------------------------------------------------------------------ test hooks
+int qasr_cuda_read_kv(qasr_ctx_t *c, int layer, int len, float *k_out, float *v_out) {
+    if (!c || !k_out || !v_out) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded || layer < 0 || layer >= c->dec_layers || len < 0 || len > c->kv_max) return set_err(QASR_ERR_ARG, "bad layer/len");
+    CK(cudaSetDevice(c->device));
+    const size_t kvd = (size_t)c->kv_heads * c->hd;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(k_out, c->kv_k + (size_t)layer * c->kv_max * kvd, (size_t)len * kvd * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(v_out, c->kv_v + (size_t)layer * c->kv_max * kvd, (size_t)len * kvd * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int qasr_cuda_embed_token(qasr_ctx_t *c, int token_id, float *out) {
+    if (!c || !out) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded || token_id < 0 || token_id >= c->V) return set_err(QASR_ERR_ARG, "bad token id");
+    CK(cudaSetDevice(c->device));
+    std::vector<uint16_t> h(c->H);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(h.data(), c->emb + (size_t)token_id * c->H, (size_t)c->H * 2, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < c->H; i++) out[i] = bf16_to_f32(h[i]);
+    return 0;
+}
+
+// ------------------------------------------------------------------ accessors for qasr_ops.cu
+cudaStream_t qasr_internal_stream(qasr_ctx_t *c) { return c->stream; }
+int qasr_internal_device(qasr_ctx_t *c) { return c->device; }
+int qasr_internal_nsplit(qasr_ctx_t *c) { return c->nsplit; }
+void qasr_internal_count(qasr_ctx_t *c, int n) { c->launches += n; }
+int qasr_internal_err(int code, const char *msg) { return set_err(code, "%s", msg); }

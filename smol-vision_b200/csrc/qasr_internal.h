@@ -1,0 +1,88 @@
+// qasr_internal.h - internal launcher prototypes shared by the .cu files of libqasr_cuda.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef uint16_t bf16_t; // raw bf16 bits on the host side / in signatures
+
+enum { QASR_EPI_STORE = 0, QASR_EPI_RESIDUAL = 1, QASR_EPI_SWIGLU = 2 };
+// tensor-core GEMM epilogues
+enum { QASR_GEMM_F32 = 0, QASR_GEMM_RESIDUAL = 1, QASR_GEMM_GELU_SPLIT = 2, QASR_GEMM_SWIGLU_SPLIT = 3 };
+
+#define QASR_ATTN_SPLITS 16
+#define QASR_ATTN_PART_STRIDE 132 /* 128 acc + m + l + pad */
+#define QASR_ARGMAX_ROWS_PER_CTA 32
+
+struct GemmEpilogue {
+    int mode;          // QASR_GEMM_*
+    float *out_f32;    // F32 / RESIDUAL target [M, ldo]
+    bf16_t *out_hi;    // *_SPLIT targets [M, ldo]
+    bf16_t *out_lo;    // may be NULL (nsplit == 1)
+    const float *bias; // [N] or NULL
+    int ldo;           // leading dimension of the output (N, or N/2 for SWIGLU)
+};
+
+// ---- decode-step kernels (qasr_decode.cu)
+void launch_gemv_bf16(cudaStream_t s, const bf16_t *W, const float *x, const float *gamma, float eps, float *out,
+                      const float *res, const float *bias, int N, int K, int epi, const int *d_done);
+void launch_argmax_gemv(cudaStream_t s, const bf16_t *E, const float *x, const float *gamma, float eps, int V, int K,
+                        float *part_val, int *part_idx, const int *d_done);
+int argmax_num_parts(int V);
+void launch_argmax_finalize(cudaStream_t s, const float *part_val, const int *part_idx, int n_parts, const bf16_t *E,
+                            int H, float *x_next, int *d_tokens, int *d_step, int *d_pos, int *d_done,
+                            volatile int *h_tokens_mapped, int max_steps);
+void launch_attn_decode(cudaStream_t s, const float *qkv, const float *qn, const float *kn, const float *rope_cos,
+                        const float *rope_sin, float *kc, float *vc, const int *d_pos, float *part,
+                        unsigned *counters, float *out, float eps);
+void launch_set_state(cudaStream_t s, int *d_pos, int pos, int *d_done, int done, int *d_step, int step);
+void launch_embed_gather(cudaStream_t s, const bf16_t *E, const int *d_ids, int n, int H, float *out);
+
+// ---- row-wise / prefill / encoder kernels (qasr_rows.cu)
+void launch_rmsnorm(cudaStream_t s, const float *x, const float *gamma, float eps, int M, int H, float *out_f32,
+                    bf16_t *out_hi, bf16_t *out_lo);
+void launch_layernorm(cudaStream_t s, const float *x, const float *w, const float *b, float eps, int M, int H,
+                      float *out_f32, bf16_t *out_hi, bf16_t *out_lo);
+void launch_rmsnorm_per_head(cudaStream_t s, float *x, const float *w, int seq, int n_heads, int head_dim, float eps);
+void launch_qk_norm_rope_store(cudaStream_t s, const float *qkv, const float *qn, const float *kn, const float *rope_cos,
+                               const float *rope_sin, int start_pos, int P, float eps, float *q_out, float *kc, float *vc);
+void launch_attn_prefill(cudaStream_t s, const float *q, const float *kc, const float *vc, int q_offset, int P, int seq_k,
+                         int n_heads, int n_kv_heads, float scale, float *out_f32, bf16_t *out_hi, bf16_t *out_lo);
+void launch_attn_windowed(cudaStream_t s, const float *q, const float *k, const float *v, int ld, int n_heads,
+                          const int *d_window_starts, int n_windows, int max_window, float scale, int out_ld,
+                          float *out_f32, bf16_t *out_hi, bf16_t *out_lo);
+void launch_split_f32(cudaStream_t s, const float *x, size_t n, bf16_t *hi, bf16_t *lo);
+void launch_add_rows(cudaStream_t s, float *x, const float *table, const int *d_row_idx, int M, int d);
+void launch_eltwise(cudaStream_t s, int op, float *a, const float *b, float scalar, size_t n);
+void launch_swiglu(cudaStream_t s, float *out, const float *gate_up, int seq, int inter);
+void launch_softmax(cudaStream_t s, float *x, int rows, int cols);
+void launch_rope_apply(cudaStream_t s, float *x, const float *c, const float *sn, int seq, int n_heads, int head_dim);
+void launch_gemm_f32(cudaStream_t s, const float *A, const float *W, const float *bias, float *C, int M, int N, int K);
+void launch_im2col_f32(cudaStream_t s, const float *in, float *cols, int c_in, int h_in, int w_in, int kh, int kw,
+                       int stride, int padding, int h_out, int w_out);
+void launch_transpose_bias(cudaStream_t s, const float *in, const float *bias, float *out, int S, int C);
+
+// ---- conv stem (qasr_conv.cu)
+struct ConvGeom { // per-chunk geometry tables live on the device
+    int n_chunks;
+    const int *d_w0;   // [n_chunks] mel frames in the chunk
+    const int *d_mel0; // [n_chunks] first mel frame of the chunk
+    const int *d_off1; // [n_chunks+1] position prefix for stage-1 output (w1*64 each)
+    const int *d_off2; // stage-2 output (w2*32)
+    const int *d_off3; // stage-3 output (w3*16)
+    int total1, total2, total3;
+};
+void launch_conv1(cudaStream_t s, const float *mel, int frames, const float *w, const float *b, const ConvGeom &g,
+                  bf16_t *out_hi, bf16_t *out_lo);
+void launch_im2col_stage(cudaStream_t s, const bf16_t *src, bf16_t *dst, const ConvGeom &g, int stage /*2 or 3*/);
+
+// ---- mel (qasr_mel.cu)
+void launch_mel(cudaStream_t s, const float *samples, int n, int frames, const float *d_cos, const float *d_sin,
+                const float *d_win, const float *d_fb, float *mel_tmp, int *d_gmax, float *mel_out);
+
+// ---- tcgen05 GEMM (qasr_gemm_tc.cu)
+// C[M,N] = A[M,K] * W[N,K]^T with A given as bf16 hi (+ optional lo) planes, W bf16, f32 accumulate in TMEM.
+int gemm_tc_init(void); // resolves cuTensorMapEncodeTiled, sets smem attributes; 0 on success
+int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M, int K, const bf16_t *W, int N,
+                   const GemmEpilogue &epi);
+const char *gemm_tc_error(void);

@@ -1,0 +1,112 @@
+// qasr_mel.cu - log-mel front end (reference qwen_mel_spectrogram, qwen_asr_audio.c:293-394).
+//
+// Pass 1 (one CTA per 8 frames): reflect-pad + periodic Hann window into shared memory,
+// direct 201-bin DFT of the 400-sample frame against the f32 cos/sin tables (built on the host
+// with the reference's own f32 angle formula, :328-336, and kept resident), power, 128-bin
+// Slaney filterbank, log10(max(.,1e-10)), running global max (atomicMax on an order-preserving
+// int).  Pass 2: clamp at gmax-8, (v+4)/4, transpose to the reference's [128, frames] layout.
+// FP32 FFMA throughout: the front end is <0.1 % of the flops of a segment.
+#include "qasr_common.cuh"
+#include "qasr_internal.h"
+
+#define MEL_FPB 8     // frames per CTA
+#define MEL_NFFT 400
+#define MEL_NFREQ 201
+#define MEL_TSTRIDE 208 // padded row stride of the [n][k] DFT tables and the [k][m]-major filterbank rows
+
+__device__ __forceinline__ int float_to_ordered(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void __launch_bounds__(256)
+mel_pass1_kernel(const float *__restrict__ samples, int n, int frames, const float *__restrict__ ct,
+                 const float *__restrict__ st, const float *__restrict__ win, const float *__restrict__ fb /*[201][128]*/,
+                 float *__restrict__ mel_tmp /*[frames][128]*/, int *__restrict__ gmax) {
+    __shared__ float fr[MEL_FPB][MEL_NFFT];
+    __shared__ float pw[MEL_FPB][MEL_NFREQ + 3];
+    __shared__ float red[8];
+    const int t0 = blockIdx.x * MEL_FPB, tid = threadIdx.x;
+    // windowed frames; padded[i]: i<200 -> x[200-i]; i<200+n -> x[i-200]; else x[n-2-(i-200-n)]  (:301-309)
+    for (int e = tid; e < MEL_FPB * MEL_NFFT; e += 256) {
+        const int f = e / MEL_NFFT, i = e % MEL_NFFT, t = t0 + f;
+        float v = 0.0f;
+        if (t < frames) {
+            const int p = t * 160 + i;
+            int src;
+            if (p < 200) src = 200 - p;
+            else if (p < 200 + n) src = p - 200;
+            else src = n - 2 - (p - 200 - n);
+            v = (src >= 0 && src < n) ? samples[src] * win[i] : 0.0f;
+        }
+        fr[f][i] = v;
+    }
+    __syncthreads();
+    if (tid < MEL_NFREQ) {
+        float re[MEL_FPB], im[MEL_FPB];
+#pragma unroll
+        for (int f = 0; f < MEL_FPB; f++) re[f] = im[f] = 0.0f;
+        for (int j = 0; j < MEL_NFFT; j++) {
+            const float c = ct[j * MEL_TSTRIDE + tid], s = st[j * MEL_TSTRIDE + tid];
+#pragma unroll
+            for (int f = 0; f < MEL_FPB; f++) {
+                const float x = fr[f][j];
+                re[f] = fmaf(x, c, re[f]);
+                im[f] = fmaf(x, s, im[f]);
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < MEL_FPB; f++) pw[f][tid] = re[f] * re[f] + im[f] * im[f];
+    }
+    __syncthreads();
+    const int m = tid & 127, fg = tid >> 7; // 2 groups x 4 frames
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < MEL_NFREQ; k++) {
+        const float w = fb[k * 128 + m];
+#pragma unroll
+        for (int f = 0; f < 4; f++) acc[f] = fmaf(w, pw[fg * 4 + f][k], acc[f]);
+    }
+    float lmax = -1e30f;
+#pragma unroll
+    for (int f = 0; f < 4; f++) {
+        const int t = t0 + fg * 4 + f;
+        if (t < frames) {
+            const float v = log10f(fmaxf(acc[f], 1e-10f));
+            mel_tmp[(size_t)t * 128 + m] = v;
+            lmax = fmaxf(lmax, v);
+        }
+    }
+    lmax = warp_max(lmax);
+    if ((tid & 31) == 0) red[tid >> 5] = lmax;
+    __syncthreads();
+    if (tid == 0) {
+        float v = red[0];
+        for (int w = 1; w < 8; w++) v = fmaxf(v, red[w]);
+        atomicMax(gmax, float_to_ordered(v));
+    }
+}
+
+__global__ void mel_pass2_kernel(const float *__restrict__ mel_tmp, const int *__restrict__ gmax, int frames,
+                                 float *__restrict__ mel /*[128][frames]*/) {
+    const float lo = ordered_to_float(*gmax) - 8.0f;
+    const size_t total = (size_t)128 * frames;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(e / frames), t = (int)(e % frames);
+        float v = mel_tmp[(size_t)t * 128 + m];
+        if (v < lo) v = lo;
+        mel[e] = (v + 4.0f) / 4.0f;
+    }
+}
+
+__global__ void mel_init_kernel(int *gmax) { *gmax = float_to_ordered(-1e30f); }
+
+void launch_mel(cudaStream_t s, const float *samples, int n, int frames, const float *d_cos, const float *d_sin,
+                const float *d_win, const float *d_fb, float *mel_tmp, int *d_gmax, float *mel_out) {
+    mel_init_kernel<<<1, 1, 0, s>>>(d_gmax);
+    mel_pass1_kernel<<<(frames + MEL_FPB - 1) / MEL_FPB, 256, 0, s>>>(samples, n, frames, d_cos, d_sin, d_win, d_fb,
+                                                                     mel_tmp, d_gmax);
+    const size_t total = (size_t)128 * frames;
+    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    mel_pass2_kernel<<<blocks, 256, 0, s>>>(mel_tmp, d_gmax, frames, mel_out);
+}

@@ -1,0 +1,427 @@
+// qasr_rows.cu - row-wise kernels for the encoder and the decoder prefill: norms that emit the
+// bf16 hi/lo operand planes of the tensor-core GEMMs, q/k-norm + RoPE + KV store, causal and
+// windowed attention, and the small f32 operators behind the level-2 test seam.
+#include "qasr_common.cuh"
+#include "qasr_internal.h"
+
+// Store one value into whichever outputs are requested.
+__device__ __forceinline__ void store_out(float v, size_t idx, float *of, bf16_t *ohi, bf16_t *olo) {
+    if (of) of[idx] = v;
+    if (ohi) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        ohi[idx] = __bfloat16_as_ushort(hi);
+        if (olo) olo[idx] = __bfloat16_as_ushort(lo);
+    }
+}
+
+// ------------------------------------------------------------------ RMSNorm (rows)
+// out = x * rsqrt(mean(x^2)+eps) * w, reference qwen_asr_kernels.c:801-860. One warp per row.
+__global__ void __launch_bounds__(256)
+rmsnorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ gamma, float eps, int M, int H,
+                    float *of, bf16_t *ohi, bf16_t *olo) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float *xr = x + (size_t)row * H;
+    float ss = 0.0f;
+    for (int i = lane; i < H; i += 32) { const float v = xr[i]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / sqrtf(ss / (float)H + eps);
+    for (int i = lane; i < H; i += 32) store_out(xr[i] * inv * gamma[i], (size_t)row * H + i, of, ohi, olo);
+}
+void launch_rmsnorm(cudaStream_t s, const float *x, const float *gamma, float eps, int M, int H, float *out_f32,
+                    bf16_t *out_hi, bf16_t *out_lo) {
+    if (M > 0) rmsnorm_rows_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, gamma, eps, M, H, out_f32, out_hi, out_lo);
+}
+
+// ------------------------------------------------------------------ LayerNorm (rows)
+// (x-mean)*rsqrt(var+eps)*w+b, biased variance, reference qwen_asr_kernels.c:691-799.
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b, float eps,
+                      int M, int H, float *of, bf16_t *ohi, bf16_t *olo) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float *xr = x + (size_t)row * H;
+    float sum = 0.0f;
+    for (int i = lane; i < H; i += 32) sum += xr[i];
+    const float mean = warp_sum(sum) / (float)H;
+    float var = 0.0f;
+    for (int i = lane; i < H; i += 32) { const float d = xr[i] - mean; var = fmaf(d, d, var); }
+    var = warp_sum(var) / (float)H;
+    const float inv = 1.0f / sqrtf(var + eps);
+    for (int i = lane; i < H; i += 32) {
+        const float v = (xr[i] - mean) * inv * w[i] + b[i];
+        store_out(v, (size_t)row * H + i, of, ohi, olo);
+    }
+}
+void launch_layernorm(cudaStream_t s, const float *x, const float *w, const float *b, float eps, int M, int H,
+                      float *out_f32, bf16_t *out_hi, bf16_t *out_lo) {
+    if (M > 0) layernorm_rows_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, w, b, eps, M, H, out_f32, out_hi, out_lo);
+}
+
+// ------------------------------------------------------------------ per-head RMSNorm (in place)
+// reference qwen_asr_kernels.c:862-924. One warp per (row, head).
+__global__ void __launch_bounds__(256)
+rmsnorm_per_head_kernel(float *x, const float *__restrict__ w, int n_vec, int head_dim, float eps) {
+    const int v = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (v >= n_vec) return;
+    float *p = x + (size_t)v * head_dim;
+    float ss = 0.0f;
+    for (int i = lane; i < head_dim; i += 32) ss = fmaf(p[i], p[i], ss);
+    ss = warp_sum(ss);
+    const float inv = 1.0f / sqrtf(ss / (float)head_dim + eps);
+    for (int i = lane; i < head_dim; i += 32) p[i] = p[i] * inv * w[i];
+}
+void launch_rmsnorm_per_head(cudaStream_t s, float *x, const float *w, int seq, int n_heads, int head_dim, float eps) {
+    const int n = seq * n_heads;
+    if (n > 0) rmsnorm_per_head_kernel<<<(n + 7) / 8, 256, 0, s>>>(x, w, n, head_dim, eps);
+}
+
+// ------------------------------------------------------------------ prefill: q/k norm + RoPE + KV store
+// qkv [P, 4096] = q(16x128) | k(8x128) | v(8x128).  grid (P, 32 head slots), 128 threads.
+// reference qwen_asr_decoder.c:510-524.
+__global__ void __launch_bounds__(128)
+qk_norm_rope_store_kernel(const float *__restrict__ qkv, const float *__restrict__ qn, const float *__restrict__ kn,
+                          const float *__restrict__ rope_cos, const float *__restrict__ rope_sin, int start_pos,
+                          float eps, float *__restrict__ q_out, float *__restrict__ kc, float *__restrict__ vc) {
+    __shared__ float tmp[128];
+    __shared__ float red[4];
+    const int p = blockIdx.x, slot = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int pos = start_pos + p;
+    const float v = qkv[(size_t)p * 4096 + slot * 128 + t];
+    if (slot >= 24) { // V: plain copy into the cache
+        vc[(size_t)pos * 1024 + (slot - 24) * 128 + t] = v;
+        return;
+    }
+    float ss = warp_sum(v * v);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    ss = red[0] + red[1] + red[2] + red[3];
+    const float *w = slot < 16 ? qn : kn;
+    tmp[t] = v * (1.0f / sqrtf(ss / 128.0f + eps)) * w[t];
+    __syncthreads();
+    const int d = t & 63;
+    const float c = rope_cos[(size_t)pos * 64 + d], sn = rope_sin[(size_t)pos * 64 + d];
+    const float r = t < 64 ? tmp[t] * c - tmp[t + 64] * sn : tmp[t] * c + tmp[t - 64] * sn;
+    if (slot < 16) q_out[(size_t)p * 2048 + slot * 128 + t] = r;
+    else kc[(size_t)pos * 1024 + (slot - 16) * 128 + t] = r;
+}
+void launch_qk_norm_rope_store(cudaStream_t s, const float *qkv, const float *qn, const float *kn, const float *rope_cos,
+                               const float *rope_sin, int start_pos, int P, float eps, float *q_out, float *kc, float *vc) {
+    if (P > 0) qk_norm_rope_store_kernel<<<dim3(P, 32), 128, 0, s>>>(qkv, qn, kn, rope_cos, rope_sin, start_pos, eps, q_out, kc, vc);
+}
+
+// ------------------------------------------------------------------ online-softmax helpers
+template <int NV>
+__device__ __forceinline__ void soft_update(float sc, float &m, float &l, float (&acc)[NV], const float (&v)[NV]) {
+    if (sc > m) {
+        const float c = expf(m - sc);
+        l = l * c + 1.0f;
+#pragma unroll
+        for (int i = 0; i < NV; i++) acc[i] = acc[i] * c + v[i];
+        m = sc;
+    } else {
+        const float w = expf(sc - m);
+        l += w;
+#pragma unroll
+        for (int i = 0; i < NV; i++) acc[i] = fmaf(w, v[i], acc[i]);
+    }
+}
+
+// ------------------------------------------------------------------ causal GQA attention (prefill)
+// reference qwen_asr_kernels.c:1101-1148.  head_dim = 128.  One warp owns 2 consecutive query
+// positions x the (n_heads/n_kv_heads = 2) query heads of one kv head => 4 queries share each
+// K/V row load; lane owns dims 4l..4l+3.  Query i attends keys [0, q_offset+i].
+__global__ void __launch_bounds__(128)
+attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, const float *__restrict__ vc,
+                    int q_offset, int P, int seq_k, int n_heads, int n_kv_heads, float scale, float *of, bf16_t *ohi,
+                    bf16_t *olo) {
+    const int kvh = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i0 = (blockIdx.y * 4 + warp) * 2;
+    if (i0 >= P) return;
+    const int per = n_heads / n_kv_heads; // 2
+    const int qld = n_heads * 128, kld = n_kv_heads * 128;
+    const bool has2 = (i0 + 1 < P);
+    float qv[4][4], acc[4][4], m[4], l[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int qi = i0 + (a >> 1), hh = kvh * per + (a & 1);
+        const float4 t4 = (a < 2 || has2) ? *reinterpret_cast<const float4 *>(q + (size_t)qi * qld + hh * 128 + lane * 4)
+                                          : make_float4(0, 0, 0, 0);
+        qv[a][0] = t4.x; qv[a][1] = t4.y; qv[a][2] = t4.z; qv[a][3] = t4.w;
+        acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.0f;
+        m[a] = -1e30f; l[a] = 0.0f;
+    }
+    int kend0 = q_offset + i0 + 1, kend1 = q_offset + i0 + 2;
+    if (kend0 > seq_k) kend0 = seq_k;
+    if (kend1 > seq_k) kend1 = seq_k;
+    const int kmax = has2 ? kend1 : kend0;
+    for (int j = 0; j < kmax; j++) {
+        const float4 k4 = *reinterpret_cast<const float4 *>(kc + (size_t)j * kld + kvh * 128 + lane * 4);
+        const float4 v4 = *reinterpret_cast<const float4 *>(vc + (size_t)j * kld + kvh * 128 + lane * 4);
+        const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+        float sc[4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+            sc[a] = warp_sum(qv[a][0] * k4.x + qv[a][1] * k4.y + qv[a][2] * k4.z + qv[a][3] * k4.w) * scale;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int ke = (a < 2) ? kend0 : kend1;
+            if (j < ke && (a < 2 || has2)) soft_update<4>(sc[a], m[a], l[a], acc[a], vv);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        if (a >= 2 && !has2) break;
+        const int qi = i0 + (a >> 1), hh = kvh * per + (a & 1);
+        const float inv = l[a] > 0.0f ? 1.0f / l[a] : 0.0f;
+        const size_t base = (size_t)qi * qld + hh * 128 + lane * 4;
+#pragma unroll
+        for (int c = 0; c < 4; c++) store_out(acc[a][c] * inv, base + c, of, ohi, olo);
+    }
+}
+void launch_attn_prefill(cudaStream_t s, const float *q, const float *kc, const float *vc, int q_offset, int P, int seq_k,
+                         int n_heads, int n_kv_heads, float scale, float *out_f32, bf16_t *out_hi, bf16_t *out_lo) {
+    if (P <= 0) return;
+    dim3 grid(n_kv_heads, (P + 7) / 8);
+    attn_prefill_kernel<<<grid, 128, 0, s>>>(q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, out_f32, out_hi, out_lo);
+}
+
+// ------------------------------------------------------------------ windowed bidirectional attention (encoder)
+// reference qwen_asr_kernels.c:1054-1099.  head_dim = 64: lane owns dims 2l,2l+1; one warp owns
+// 4 consecutive queries of one head inside one window; all keys of the window are visited.
+// q/k/v may be column slices of one [T, ld] buffer (fused QKV GEMM output).
+__global__ void __launch_bounds__(128)
+attn_windowed_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v, int ld,
+                     const int *__restrict__ window_starts, float scale, int out_ld, float *of, bf16_t *ohi,
+                     bf16_t *olo) {
+    const int h = blockIdx.x, w = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ws = window_starts[w], we = window_starts[w + 1];
+    const int i0 = ws + (blockIdx.z * 4 + warp) * 4;
+    if (i0 >= we) return;
+    float qv[4][2], acc[4][2], m[4], l[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int qi = i0 + a;
+        const float2 t2 = qi < we ? *reinterpret_cast<const float2 *>(q + (size_t)qi * ld + h * 64 + lane * 2)
+                                  : make_float2(0, 0);
+        qv[a][0] = t2.x; qv[a][1] = t2.y;
+        acc[a][0] = acc[a][1] = 0.0f;
+        m[a] = -1e30f; l[a] = 0.0f;
+    }
+    for (int j = ws; j < we; j++) {
+        const float2 k2 = *reinterpret_cast<const float2 *>(k + (size_t)j * ld + h * 64 + lane * 2);
+        const float2 v2 = *reinterpret_cast<const float2 *>(v + (size_t)j * ld + h * 64 + lane * 2);
+        const float vv[2] = {v2.x, v2.y};
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const float sc = warp_sum(qv[a][0] * k2.x + qv[a][1] * k2.y) * scale;
+            soft_update<2>(sc, m[a], l[a], acc[a], vv);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int qi = i0 + a;
+        if (qi >= we) break;
+        const float inv = l[a] > 0.0f ? 1.0f / l[a] : 0.0f;
+        const size_t base = (size_t)qi * out_ld + h * 64 + lane * 2;
+        store_out(acc[a][0] * inv, base, of, ohi, olo);
+        store_out(acc[a][1] * inv, base + 1, of, ohi, olo);
+    }
+}
+void launch_attn_windowed(cudaStream_t s, const float *q, const float *k, const float *v, int ld, int n_heads,
+                          const int *d_window_starts, int n_windows, int max_window, float scale, int out_ld,
+                          float *out_f32, bf16_t *out_hi, bf16_t *out_lo) {
+    if (n_windows <= 0) return;
+    dim3 grid(n_heads, n_windows, (max_window + 15) / 16);
+    attn_windowed_kernel<<<grid, 128, 0, s>>>(q, k, v, ld, d_window_starts, scale, out_ld, out_f32, out_hi, out_lo);
+}
+
+// ------------------------------------------------------------------ small element-wise kernels
+__global__ void split_f32_kernel(const float *__restrict__ x, size_t n, bf16_t *hi, bf16_t *lo) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        store_out(x[i], i, nullptr, hi, lo);
+}
+void launch_split_f32(cudaStream_t s, const float *x, size_t n, bf16_t *hi, bf16_t *lo) {
+    if (n == 0) return;
+    const int blocks = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    split_f32_kernel<<<blocks, 256, 0, s>>>(x, n, hi, lo);
+}
+
+// x[m, :] += table[row_idx[m], :]   (per-chunk sinusoidal PE, reference qwen_asr_encoder.c:280-284)
+__global__ void add_rows_kernel(float *x, const float *__restrict__ table, const int *__restrict__ row_idx, int d) {
+    const int m = blockIdx.x;
+    const float *t = table + (size_t)row_idx[m] * d;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) x[(size_t)m * d + i] += t[i];
+}
+void launch_add_rows(cudaStream_t s, float *x, const float *table, const int *d_row_idx, int M, int d) {
+    if (M > 0) add_rows_kernel<<<M, 256, 0, s>>>(x, table, d_row_idx, d);
+}
+
+// op: 0 add (a+=b) 1 mul (a*=b) 2 scale (a*=s) 3 gelu 4 silu
+__global__ void eltwise_kernel(int op, float *a, const float *__restrict__ b, float sc, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = a[i];
+        switch (op) {
+            case 0: v += b[i]; break;
+            case 1: v *= b[i]; break;
+            case 2: v *= sc; break;
+            case 3: v = gelu_tanh(v); break;
+            default: v = silu(v); break;
+        }
+        a[i] = v;
+    }
+}
+void launch_eltwise(cudaStream_t s, int op, float *a, const float *b, float scalar, size_t n) {
+    if (n == 0) return;
+    const int blocks = (int)((n + 255) / 256 < 2368 ? (n + 255) / 256 : 2368);
+    eltwise_kernel<<<blocks, 256, 0, s>>>(op, a, b, scalar, n);
+}
+
+// reference qwen_asr_kernels.c:946-1010 (out may alias gate_up: each thread reads its pair first,
+// and writes index j <= 2j, so a row-serial in-place update is only safe per row; we stage through
+// registers per row chunk and sync).
+__global__ void swiglu_kernel(float *out, const float *gate_up, int inter) {
+    const int srow = blockIdx.x;
+    const float *gu = gate_up + (size_t)srow * 2 * inter;
+    float *o = out + (size_t)srow * inter;
+    for (int j0 = 0; j0 < inter; j0 += blockDim.x) {
+        const int j = j0 + threadIdx.x;
+        float r = 0.0f;
+        if (j < inter) r = silu(gu[2 * j]) * gu[2 * j + 1];
+        __syncthreads(); // all reads of this chunk (indices < 2*(j0+blockDim)) done before writes < j0+blockDim
+        if (j < inter) o[j] = r;
+        __syncthreads();
+    }
+}
+void launch_swiglu(cudaStream_t s, float *out, const float *gate_up, int seq, int inter) {
+    if (seq > 0) swiglu_kernel<<<seq, 256, 0, s>>>(out, gate_up, inter);
+}
+
+// reference qwen_asr_kernels.c:1012-1029. One CTA per row.
+__global__ void softmax_kernel(float *x, int cols) {
+    __shared__ float red[32];
+    float *row = x + (size_t)blockIdx.x * cols;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) mx = fmaxf(mx, row[i]);
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < nw; w++) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sum = 0.0f;
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) { const float e = expf(row[i] - mx); row[i] = e; sum += e; }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.0f;
+    for (int w = 0; w < nw; w++) sum += red[w];
+    const float inv = 1.0f / sum;
+    for (int i = threadIdx.x; i < cols; i += blockDim.x) row[i] *= inv;
+}
+void launch_softmax(cudaStream_t s, float *x, int rows, int cols) {
+    if (rows > 0) softmax_kernel<<<rows, 256, 0, s>>>(x, cols);
+}
+
+// reference qwen_asr_kernels.c:1233-1298; cos/sin given as [seq, head_dim] (duplicated halves)
+__global__ void rope_apply_kernel(float *x, const float *__restrict__ c, const float *__restrict__ sn, int n_heads,
+                                  int head_dim) {
+    const int s = blockIdx.x, half = head_dim / 2;
+    for (int idx = threadIdx.x; idx < n_heads * half; idx += blockDim.x) {
+        const int h = idx / half, d = idx % half;
+        float *v = x + ((size_t)s * n_heads + h) * head_dim;
+        const float x1 = v[d], x2 = v[half + d];
+        v[d] = x1 * c[(size_t)s * head_dim + d] - x2 * sn[(size_t)s * head_dim + d];
+        v[half + d] = x2 * c[(size_t)s * head_dim + half + d] + x1 * sn[(size_t)s * head_dim + half + d];
+    }
+}
+void launch_rope_apply(cudaStream_t s, float *x, const float *c, const float *sn, int seq, int n_heads, int head_dim) {
+    if (seq > 0) rope_apply_kernel<<<seq, 256, 0, s>>>(x, c, sn, n_heads, head_dim);
+}
+
+// ------------------------------------------------------------------ exact f32 SIMT GEMM
+// C[M,N] = A[M,K] W[N,K]^T + bias.  Serves the f32-weight operators of the level-2 seam
+// (qwen_linear / qwen_matmul_t / qwen_conv2d take arbitrary f32 weights, which the bf16
+// tensor-core path cannot represent exactly).  64x64 tile, 4x4 per thread, BK = 16.
+__global__ void __launch_bounds__(256)
+gemm_f32_kernel(const float *__restrict__ A, const float *__restrict__ W, const float *__restrict__ bias,
+                float *__restrict__ C, int M, int N, int K) {
+    __shared__ float As[16][65], Ws[16][65];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+            const int r = e >> 4, kk = e & 15;
+            As[kk][r] = (m0 + r < M && k0 + kk < K) ? A[(size_t)(m0 + r) * K + k0 + kk] : 0.0f;
+            Ws[kk][r] = (n0 + r < N && k0 + kk < K) ? W[(size_t)(n0 + r) * K + k0 + kk] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { a[i] = As[kk][ty * 4 + i]; b[i] = Ws[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) {
+            const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+            if (m < M && n < N) C[(size_t)m * N + n] = acc[i][j] + (bias ? bias[n] : 0.0f);
+        }
+}
+void launch_gemm_f32(cudaStream_t s, const float *A, const float *W, const float *bias, float *C, int M, int N, int K) {
+    if (M <= 0 || N <= 0) return;
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    gemm_f32_kernel<<<grid, 256, 0, s>>>(A, W, bias, C, M, N, K);
+}
+
+// patches[pos][K] with K ordered (ic, ki, kj) as in the reference weight layout [C_out, C_in, kH, kW]
+// (reference im2col, qwen_asr_kernels.c:566-590, transposed so the GEMM reads K-contiguous rows).
+__global__ void im2col_f32_kernel(const float *__restrict__ in, float *__restrict__ cols, int c_in, int h_in, int w_in,
+                                  int kh, int kw, int stride, int padding, int h_out, int w_out) {
+    const int K = c_in * kh * kw;
+    const size_t total = (size_t)h_out * w_out * K;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int p = (int)(e / K), kidx = (int)(e % K);
+        const int ic = kidx / (kh * kw), ki = (kidx / kw) % kh, kj = kidx % kw;
+        const int oh = p / w_out, ow = p % w_out;
+        const int ih = oh * stride - padding + ki, iw = ow * stride - padding + kj;
+        cols[e] = (ih >= 0 && ih < h_in && iw >= 0 && iw < w_in) ? in[((size_t)ic * h_in + ih) * w_in + iw] : 0.0f;
+    }
+}
+void launch_im2col_f32(cudaStream_t s, const float *in, float *cols, int c_in, int h_in, int w_in, int kh, int kw,
+                       int stride, int padding, int h_out, int w_out) {
+    const size_t total = (size_t)h_out * w_out * c_in * kh * kw;
+    if (total == 0) return;
+    const int blocks = (int)((total + 255) / 256 < 4736 ? (total + 255) / 256 : 4736);
+    im2col_f32_kernel<<<blocks, 256, 0, s>>>(in, cols, c_in, h_in, w_in, kh, kw, stride, padding, h_out, w_out);
+}
+
+// out[c][s] = in[s][c] + bias[c]   ([S,C] GEMM result -> reference's [C_out, H_out*W_out] layout)
+__global__ void transpose_bias_kernel(const float *__restrict__ in, const float *__restrict__ bias, float *__restrict__ out,
+                                      int S, int C) {
+    __shared__ float tile[32][33];
+    const int s0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int s = s0 + r, c = c0 + threadIdx.x;
+        tile[r][threadIdx.x] = (s < S && c < C) ? in[(size_t)s * C + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, s = s0 + threadIdx.x;
+        if (c < C && s < S) out[(size_t)c * S + s] = tile[threadIdx.x][r] + (bias ? bias[c] : 0.0f);
+    }
+}
+void launch_transpose_bias(cudaStream_t s, const float *in, const float *bias, float *out, int S, int C) {
+    if (S <= 0 || C <= 0) return;
+    dim3 grid((S + 31) / 32, (C + 31) / 32), block(32, 8);
+    transpose_bias_kernel<<<grid, block, 0, s>>>(in, bias, out, S, C);
+}

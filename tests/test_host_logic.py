@@ -1,0 +1,100 @@
+"""CPU: host-side logic - synthetic inputs, segment splitting (reference qwen_asr.c:617-643,
+941-970) and the multi-GPU shard/gather plumbing (world_size 2 over gloo)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_synth_audio_deterministic(pkg):
+    a = pkg.synth_audio(3.0, seed=5)
+    b = pkg.synth_audio(3.0, seed=5)
+    c = pkg.synth_audio(3.0, seed=6)
+    assert a.dtype == np.float32 and len(a) == 48000
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+    assert np.abs(a).max() < 1.0 and np.abs(a).max() > 0.05
+    assert np.array_equal(a, np.round(a * 32768) / 32768)  # s16-quantised like a WAV sample
+
+
+def test_split_segments_matches_reference_rules(pkg):
+    seg = pkg.segments
+    audio = pkg.synth_audio(95.0, seed=1)
+    ranges = seg.split_segments(audio, 20.0, 3.0)
+    assert ranges[0][0] == 0 and ranges[-1][1] == len(audio)
+    assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))  # contiguous, no overlap
+    for (a, b) in ranges[:-1]:
+        assert 17 * 16000 <= b - a <= 23 * 16000                 # target +- search window
+    assert seg.split_segments(audio[:16000 * 10], 20.0, 3.0) == [(0, 160000)]  # fits one segment
+    assert seg.split_segments(audio, 0.0, 3.0) == [(0, len(audio))]            # -S 0
+    # search window is clamped to half the segment (qwen_asr.c:944-945)
+    r2 = seg.split_segments(audio, 4.0, 3.0)
+    assert all(b - a >= 2 * 16000 - 800 for a, b in r2[:-1])
+    # the reference's 127-split cap (qwen_asr.c:968)
+    long_audio = np.tile(audio, 3)
+    capped = seg.split_segments(long_audio, 1.0, 0.2)
+    assert len(capped) == 127
+    assert len(seg.split_segments(long_audio, 1.0, 0.2, max_splits=None)) > 127
+
+
+def test_find_split_point_picks_silence(pkg):
+    seg = pkg.segments
+    x = np.full(16000 * 10, 0.1, np.float32)
+    x[16000 * 5 + 800:16000 * 5 + 2400] = 0.0
+    assert abs(seg.find_split_point(x, 16000 * 5, 3.0) - (16000 * 5 + 1600)) <= 800
+    assert seg.pad_short(np.ones(10, np.float32)).shape == (8000,)
+
+
+def test_shard_ranges_cover_everything(pkg):
+    seg = pkg.segments
+    for n in (0, 1, 7, 8, 181):
+        for world in (1, 2, 4, 8):
+            parts = [seg.shard_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    seg = ge.load_package().segments
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_items = 7
+    lo, hi = seg.shard_range(n_items, rank, world)
+    local = [([100 * i, 100 * i + 1], {"seg": i, "rank": rank}) for i in range(lo, hi)]  # stand-in for engine output
+    merged = seg.gather_in_order(local, n_items, rank, world, dist)
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, [m[1]["seg"] for m in merged], [m[0][0] for m in merged]))
+
+
+def test_two_rank_gloo_gather_in_segment_order():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, order, firsts in results:
+        assert order == list(range(7)), f"rank {rank} saw {order}"
+        assert firsts == [100 * i for i in range(7)]
