@@ -120,6 +120,17 @@ int qasr_cuda_generate(qasr_ctx_t *ctx, int first_token, int kv_len, int max_new
 int qasr_cuda_transcribe_ids(qasr_ctx_t *ctx, const float *samples, int n_samples, int max_new,
                              int *out_ids, int *out_n, double *timings_ms, int *out_enc_tokens);
 
+/* Benchmark plumbing: keep a segment's samples resident in HBM and transcribe from there (no
+ * per-call host->device copy), a CUDA-event stopwatch on the library's own stream (the stream
+ * every kernel here is launched on), and the accumulated device time / step count of the greedy
+ * decode-step launches since the last reset (for the decode roofline). */
+int qasr_cuda_stage_audio(qasr_ctx_t *ctx, const float *samples, int n_samples);
+int qasr_cuda_transcribe_staged(qasr_ctx_t *ctx, int max_new, int *out_ids, int *out_n, double *timings_ms,
+                                int *out_enc_tokens);
+int qasr_cuda_timer_start(qasr_ctx_t *ctx);
+int qasr_cuda_timer_stop(qasr_ctx_t *ctx, double *out_ms);
+int qasr_cuda_decode_stats(qasr_ctx_t *ctx, long long *steps, double *ms, int reset);
+
 /* Test hooks: copy KV rows [0,len) of one layer to the host ([len, kv_heads*head_dim] f32),
  * and the bf16 embedding row of a token upcast to f32 (reference qwen_asr.c:412-419). */
 int qasr_cuda_read_kv(qasr_ctx_t *ctx, int layer, int len, float *k_out, float *v_out);

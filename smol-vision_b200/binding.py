@@ -46,6 +46,11 @@ SIGNATURES = {
     "qasr_cuda_step_logits": (ci, [vp, f32p, ci, f32p]),
     "qasr_cuda_generate": (ci, [vp, ci, ci, ci, i32p, ip, ip]),
     "qasr_cuda_transcribe_ids": (ci, [vp, f32p, ci, ci, i32p, ip, vp, ip]),
+    "qasr_cuda_stage_audio": (ci, [vp, f32p, ci]),
+    "qasr_cuda_transcribe_staged": (ci, [vp, ci, i32p, ip, vp, ip]),
+    "qasr_cuda_timer_start": (ci, [vp]),
+    "qasr_cuda_timer_stop": (ci, [vp, C.POINTER(C.c_double)]),
+    "qasr_cuda_decode_stats": (ci, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_double), ci]),
     "qasr_cuda_read_kv": (ci, [vp, ci, ci, f32p, f32p]),
     "qasr_cuda_embed_token": (ci, [vp, ci, f32p]),
     "qasr_cuda_last_decode_ms": (C.c_double, [vp]),
@@ -241,6 +246,31 @@ class QasrCuda:
                                                    tm.ctypes.data_as(vp), C.byref(T)))
         return ids[:n.value].copy(), dict(mel_ms=tm[0], enc_ms=tm[1], prefill_ms=tm[2], decode_ms=tm[3],
                                           enc_tokens=T.value)
+
+    # ---- benchmark plumbing
+    def stage_audio(self, samples):
+        samples = _f32(samples)
+        self._ck(self.lib.qasr_cuda_stage_audio(self.ctx, samples, len(samples)))
+
+    def transcribe_staged(self, max_new, ids_buf=None):
+        ids = ids_buf if ids_buf is not None else np.zeros(max(max_new, 1), np.int32)
+        tm = np.zeros(4, np.float64)
+        n, T = ci(0), ci(0)
+        self._ck(self.lib.qasr_cuda_transcribe_staged(self.ctx, max_new, ids, C.byref(n), tm.ctypes.data_as(vp), C.byref(T)))
+        return ids[:n.value], dict(mel_ms=tm[0], enc_ms=tm[1], prefill_ms=tm[2], decode_ms=tm[3], enc_tokens=T.value)
+
+    def timer_start(self):
+        self._ck(self.lib.qasr_cuda_timer_start(self.ctx))
+
+    def timer_stop(self):
+        ms = C.c_double(0.0)
+        self._ck(self.lib.qasr_cuda_timer_stop(self.ctx, C.byref(ms)))
+        return ms.value
+
+    def decode_stats(self, reset=False):
+        steps, ms = C.c_longlong(0), C.c_double(0.0)
+        self._ck(self.lib.qasr_cuda_decode_stats(self.ctx, C.byref(steps), C.byref(ms), 1 if reset else 0))
+        return steps.value, ms.value
 
     # ---- level 2 operator surface (names follow the reference's qwen_* ops)
     def linear(self, x, W, b=None):

@@ -114,7 +114,11 @@ struct qasr_ctx {
     int *d_gmax = nullptr;
     int mel_frames = 0, enc_T = 0;
     cudaEvent_t ev[5] = {};
+    cudaEvent_t tev[2] = {};
     double last_decode_ms = 0.0;
+    double decode_ms_total = 0.0;
+    long long decode_steps_total = 0;
+    int staged_samples = 0;
     long long launches = 0;
 };
 
@@ -168,6 +172,7 @@ void qasr_cuda_free(qasr_ctx_t *c) {
     c->ws_samples.release(); c->ws_meltmp.release(); c->ws_mel.release(); c->ws_enc.release();
     c->ws_encout.release(); c->ws_pre.release(); c->ws_ids.release(); c->ws_geom.release();
     for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 2; i++) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -521,12 +526,13 @@ int qasr_cuda_encoder_tokens(int frames) {
     return T;
 }
 
+// samples == NULL: use the n device-resident samples staged by qasr_cuda_stage_audio
 static int mel_device(qasr_ctx_t *c, const float *samples, int n, int *frames_out) {
     const int frames = n / 160; // (n + 400 - 400)/160 + 1 - 1, reference :311-312
     if (frames <= 0) return set_err(QASR_ERR_ARG, "audio too short (%d samples)", n); // reference returns NULL (:313-317)
-    if (c->ws_samples.reserve((size_t)n * 4) || c->ws_meltmp.reserve((size_t)frames * 128 * 4) || c->ws_mel.reserve((size_t)frames * 128 * 4))
+    if ((samples && c->ws_samples.reserve((size_t)n * 4)) || c->ws_meltmp.reserve((size_t)frames * 128 * 4) || c->ws_mel.reserve((size_t)frames * 128 * 4))
         return set_err(QASR_ERR_NOMEM, "mel workspace allocation failed");
-    CK(cudaMemcpyAsync(c->ws_samples.p, samples, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (samples) CK(cudaMemcpyAsync(c->ws_samples.p, samples, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
     launch_mel(c->stream, c->ws_samples.as<float>(), n, frames, c->mel_cos, c->mel_sin, c->mel_win, c->mel_fb,
                c->ws_meltmp.as<float>(), c->d_gmax, c->ws_mel.as<float>());
     c->launches += 3;
@@ -920,6 +926,8 @@ static int generate_device(qasr_ctx_t *c, int first_token, int kv_len, int max_n
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
         c->last_decode_ms = ms;
+        c->decode_ms_total += ms;
+        c->decode_steps_total += n - 1;
         c->x_token = tok;
     }
     *out_n = n;
@@ -936,11 +944,11 @@ int qasr_cuda_generate(qasr_ctx_t *c, int first_token, int kv_len, int max_new, 
 }
 
 // Whole offline segment. reference transcribe_segment, qwen_asr.c:649-842
-int qasr_cuda_transcribe_ids(qasr_ctx_t *c, const float *samples, int n_samples, int max_new, int *out_ids, int *out_n,
-                             double *timings_ms, int *out_enc_tokens) {
+static int transcribe_impl(qasr_ctx_t *c, const float *samples, int n_samples, int max_new, int *out_ids, int *out_n,
+                           double *timings_ms, int *out_enc_tokens) {
     static const int PRE[] = {151644, 8948, 198, 151645, 198, 151644, 872, 198, 151669}; // qwen_asr.c:388-393
     static const int SUF[] = {151670, 151645, 198, 151644, 77091, 198};                  // qwen_asr.c:394-396
-    if (!c || !samples || !out_ids || !out_n) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c || !out_ids || !out_n) return set_err(QASR_ERR_ARG, "null argument");
     if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
     CK(cudaSetDevice(c->device));
     int frames = 0, T = 0, first = 0;
@@ -971,6 +979,54 @@ int qasr_cuda_transcribe_ids(qasr_ctx_t *c, const float *samples, int n_samples,
     CKR(generate_device(c, first, kv0 + 1, max_new, out_ids, out_n, &kv_out));
     if (timings_ms) { timings_ms[0] = t_mel; timings_ms[1] = t_enc; timings_ms[2] = t_pre; timings_ms[3] = c->last_decode_ms; }
     if (out_enc_tokens) *out_enc_tokens = T;
+    return 0;
+}
+
+int qasr_cuda_transcribe_ids(qasr_ctx_t *c, const float *samples, int n_samples, int max_new, int *out_ids, int *out_n,
+                             double *timings_ms, int *out_enc_tokens) {
+    if (!samples) return set_err(QASR_ERR_ARG, "null samples");
+    return transcribe_impl(c, samples, n_samples, max_new, out_ids, out_n, timings_ms, out_enc_tokens);
+}
+
+int qasr_cuda_stage_audio(qasr_ctx_t *c, const float *samples, int n_samples) {
+    if (!c || !samples || n_samples <= 0) return set_err(QASR_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    if (c->ws_samples.reserve((size_t)n_samples * 4)) return set_err(QASR_ERR_NOMEM, "sample buffer");
+    CK(cudaMemcpyAsync(c->ws_samples.p, samples, (size_t)n_samples * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->staged_samples = n_samples;
+    return 0;
+}
+
+int qasr_cuda_transcribe_staged(qasr_ctx_t *c, int max_new, int *out_ids, int *out_n, double *timings_ms, int *out_enc_tokens) {
+    if (!c || c->staged_samples <= 0) return set_err(QASR_ERR_STATE, "no staged audio: call qasr_cuda_stage_audio first");
+    return transcribe_impl(c, nullptr, c->staged_samples, max_new, out_ids, out_n, timings_ms, out_enc_tokens);
+}
+
+// CUDA-event stopwatch on the context's stream (the stream every kernel of this library runs on)
+int qasr_cuda_timer_start(qasr_ctx_t *c) {
+    if (!c) return set_err(QASR_ERR_ARG, "null context");
+    CK(cudaSetDevice(c->device));
+    if (!c->tev[0]) { CK(cudaEventCreate(&c->tev[0])); CK(cudaEventCreate(&c->tev[1])); }
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->tev[0], c->stream));
+    return 0;
+}
+int qasr_cuda_timer_stop(qasr_ctx_t *c, double *out_ms) {
+    if (!c || !out_ms || !c->tev[0]) return set_err(QASR_ERR_ARG, "timer not started");
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->tev[1], c->stream));
+    CK(cudaEventSynchronize(c->tev[1]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->tev[0], c->tev[1]));
+    *out_ms = ms;
+    return 0;
+}
+int qasr_cuda_decode_stats(qasr_ctx_t *c, long long *steps, double *ms, int reset) {
+    if (!c) return set_err(QASR_ERR_ARG, "null context");
+    if (steps) *steps = c->decode_steps_total;
+    if (ms) *ms = c->decode_ms_total;
+    if (reset) { c->decode_steps_total = 0; c->decode_ms_total = 0.0; }
     return 0;
 }
 
