@@ -109,6 +109,11 @@ struct qasr_ctx {
     cudaGraph_t graph = nullptr;
     int graph_nodes = 0;
     bool use_graph = true;
+    bool use_mega = true; // persistent cooperative decode kernel (QASR_DECODE=graph selects per-phase kernels)
+    float *head_val = nullptr;
+    int *head_idx = nullptr;
+    unsigned *grid_bar = nullptr;
+    long long *mega_prof = nullptr;
     // scratch
     DevBuf ws_samples, ws_meltmp, ws_mel, ws_enc, ws_encout, ws_pre, ws_ids, ws_geom;
     int *d_gmax = nullptr;
@@ -151,6 +156,14 @@ qasr_ctx_t *qasr_cuda_init(int device) {
     for (int i = 0; i < 5; i++) cudaEventCreate(&c->ev[i]);
     const char *ng = getenv("QASR_NO_GRAPH");
     c->use_graph = !(ng && ng[0] == '1');
+    const char *dm = getenv("QASR_DECODE");
+    c->use_mega = !(dm && strcmp(dm, "graph") == 0);
+    if (c->use_mega && mega_init() != 0) {
+        set_err(QASR_ERR_CUDA, "%s", mega_error());
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return nullptr;
+    }
     if (gemm_tc_init() != 0) {
         set_err(QASR_ERR_CUDA, "%s", gemm_tc_error());
         cudaStreamDestroy(c->stream);
@@ -504,6 +517,9 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
     c->d_pos = (int *)dalloc(4); c->d_done = (int *)dalloc(4); c->d_step = (int *)dalloc(4);
     c->d_tokens = (int *)dalloc((size_t)c->max_steps * 4);
     c->d_gmax = (int *)dalloc(4);
+    c->head_val = (float *)dalloc(1024 * 4); c->head_idx = (int *)dalloc(1024 * 4);
+    c->grid_bar = (unsigned *)dalloc(64 * 4); // count and generation live in separate 128-byte lines
+    if (getenv("QASR_MEGA_PROF")) c->mega_prof = (long long *)dalloc(3 * 4096 * 8);
     if (!c->x || !c->logits || !c->d_gmax) return set_err(QASR_ERR_NOMEM, "state allocation failed");
     CK(cudaHostAlloc((void **)&c->h_tokens, (size_t)c->max_steps * 4, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void **)&c->dh_tokens, c->h_tokens, 0));
@@ -805,6 +821,28 @@ static int ensure_graph(qasr_ctx_t *c) {
 
 // Enqueue n greedy steps (each consumes c->x, leaves the next embedding in c->x).
 static int enqueue_steps(qasr_ctx_t *c, int n) {
+    if (c->use_mega) { // one persistent cooperative launch runs all n steps (stops itself after an EOS token)
+        if (c->dec_layers > 28) return set_err(QASR_ERR_ARG, "decode megakernel supports up to 28 decoder layers");
+        MegaParams p;
+        for (int l = 0; l < c->dec_layers; l++) {
+            const DecLayerW &L = c->dec[l];
+            p.layers[l] = MegaLayer{L.wqkv, L.wo, L.wgu, L.wdown, L.qn, L.kn, L.in_norm, L.post_norm};
+        }
+        p.n_layers = c->dec_layers; p.H = c->H; p.I = c->I; p.V = c->V; p.n_steps = n; p.eps = 1e-6f;
+        p.emb = c->emb; p.final_norm = c->final_norm;
+        p.x = c->x; p.qkv = c->qkv; p.act = c->act; p.attn_part = c->attn_part;
+        p.kv_k = c->kv_k; p.kv_v = c->kv_v; p.kv_layer_stride = (size_t)c->kv_max * c->kv_heads * c->hd;
+        p.rope_cos = c->rope_cos; p.rope_sin = c->rope_sin;
+        p.head_val = c->head_val; p.head_idx = c->head_idx;
+        p.d_pos = c->d_pos; p.d_step = c->d_step; p.d_tokens = c->d_tokens; p.h_tokens = c->dh_tokens;
+        p.bar_count = c->grid_bar; p.bar_gen = c->grid_bar + 32;
+        p.prof = c->mega_prof; p.prof_cap = 4096;
+        { const char *dbg = getenv("QASR_MEGA_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+        CK(cudaMemsetAsync(c->grid_bar, 0, 4, c->stream)); // arrival counter of the grid barrier
+        if (launch_decode_mega(c->stream, p) != 0) return set_err(QASR_ERR_CUDA, "%s", mega_error());
+        c->launches += 1;
+        return 0;
+    }
     if (c->use_graph) {
         CKR(ensure_graph(c));
         for (int i = 0; i < n; i++) CK(cudaGraphLaunch(c->graph_exec, c->stream));
@@ -1051,6 +1089,13 @@ int qasr_cuda_embed_token(qasr_ctx_t *c, int token_id, float *out) {
     CK(cudaMemcpy(h.data(), c->emb + (size_t)token_id * c->H, (size_t)c->H * 2, cudaMemcpyDeviceToHost));
     for (int i = 0; i < c->H; i++) out[i] = bf16_to_f32(h[i]);
     return 0;
+}
+
+// debug: copy the megakernel phase stamps (2 x 4096 clock64 values) to the host
+extern "C" int qasr_debug_mega_prof(qasr_ctx_t *c, long long *out) {
+    if (!c || !c->mega_prof) return -1;
+    cudaStreamSynchronize(c->stream);
+    return cudaMemcpy(out, c->mega_prof, 3 * 4096 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
 }
 
 // ------------------------------------------------------------------ accessors for qasr_ops.cu

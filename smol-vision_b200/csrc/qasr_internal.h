@@ -38,6 +38,34 @@ void launch_attn_decode(cudaStream_t s, const float *qkv, const float *qn, const
 void launch_set_state(cudaStream_t s, int *d_pos, int pos, int *d_done, int done, int *d_step, int step);
 void launch_embed_gather(cudaStream_t s, const bf16_t *E, const int *d_ids, int n, int H, float *out);
 
+// ---- persistent cooperative decode kernel (qasr_mega.cu)
+struct MegaLayer {
+    const bf16_t *wqkv, *wo, *wgu, *wdown;
+    const float *qn, *kn, *in_norm, *post_norm;
+};
+struct MegaParams {
+    MegaLayer layers[28];
+    int n_layers, H, I, V, n_steps;
+    float eps;
+    const bf16_t *emb;
+    const float *final_norm;
+    float *x, *qkv, *act, *attn_part;      // [H], [4096], [I], [8][16][2][132]
+    float *kv_k, *kv_v;
+    size_t kv_layer_stride;                // elements between layers of the KV cache
+    const float *rope_cos, *rope_sin;      // [pos][64]
+    float *head_val;                       // [grid] per-CTA argmax winners
+    int *head_idx;
+    int *d_pos, *d_step, *d_tokens;
+    volatile int *h_tokens;                // mapped pinned ring (may be NULL)
+    unsigned *bar_count, *bar_gen;         // grid barrier state (zero-initialised once)
+    long long *prof;                       // optional clock64 stamps [2][prof_cap] (CTA 0, last CTA) or NULL
+    int prof_cap;
+    int debug;                             // bit0: skip grid barriers (timing experiments only)
+};
+int mega_init(void);
+int launch_decode_mega(cudaStream_t s, const MegaParams &p);
+const char *mega_error(void);
+
 // ---- row-wise / prefill / encoder kernels (qasr_rows.cu)
 void launch_rmsnorm(cudaStream_t s, const float *x, const float *gamma, float eps, int M, int H, float *out_f32,
                     bf16_t *out_hi, bf16_t *out_lo);
