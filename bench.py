@@ -255,7 +255,7 @@ def main():
                "ids_head": ids[:8],
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": None, "peak_source": peak_src,
-                            "kernel": "decode-step launch (CUDA graph: 112 gemv_bf16 + 28 attn_decode + argmax_gemv + finalize)",
+                            "kernel": "decode step of decode_mega_kernel (persistent cooperative kernel; QASR_DECODE=graph: CUDA graph of 112 gemv_bf16 + 28 attn_decode + argmax_gemv + finalize)",
                             "bytes_per_launch": step_bytes, "ms_per_launch": dec_ms_per_step,
                             "frac_of_8000_nominal": achieved / 8000.0}}
         if not args.no_cpu_baseline:

@@ -114,6 +114,7 @@ struct qasr_ctx {
     int *head_idx = nullptr;
     unsigned *grid_bar = nullptr;
     long long *mega_prof = nullptr;
+    void *mega_maps = nullptr; // device array of CUtensorMap (128 B each): decoder matrices in phase order + embedding
     // scratch
     DevBuf ws_samples, ws_meltmp, ws_mel, ws_enc, ws_encout, ws_pre, ws_ids, ws_geom;
     int *d_gmax = nullptr;
@@ -518,7 +519,24 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
     c->d_tokens = (int *)dalloc((size_t)c->max_steps * 4);
     c->d_gmax = (int *)dalloc(4);
     c->head_val = (float *)dalloc(1024 * 4); c->head_idx = (int *)dalloc(1024 * 4);
-    c->grid_bar = (unsigned *)dalloc(64 * 4); // count and generation live in separate 128-byte lines
+    c->grid_bar = (unsigned *)dalloc(64 * 4);
+    { // TMA descriptors of the decode weight stream: [layer][QKV, WO, GU, DOWN] + tied embedding
+        const size_t MS = 128; // sizeof(CUtensorMap)
+        std::vector<uint8_t> maps((size_t)(c->dec_layers * 4 + 1) * MS);
+        int mrc = 0;
+        for (int l = 0; l < c->dec_layers; l++) {
+            const DecLayerW &L = c->dec[l];
+            mrc |= tc_encode_map(&maps[(size_t)(l * 4 + 0) * MS], L.wqkv, 4096, H, 64, 16);
+            mrc |= tc_encode_map(&maps[(size_t)(l * 4 + 1) * MS], L.wo, H, 2048, 64, 16);
+            mrc |= tc_encode_map(&maps[(size_t)(l * 4 + 2) * MS], L.wgu, 2 * I, H, 64, 16);
+            mrc |= tc_encode_map(&maps[(size_t)(l * 4 + 3) * MS], L.wdown, H, I, 64, 16);
+        }
+        mrc |= tc_encode_map(&maps[(size_t)(c->dec_layers * 4) * MS], c->emb, c->V, H, 64, 16);
+        if (mrc) return set_err(QASR_ERR_CUDA, "%s", gemm_tc_error());
+        c->mega_maps = dalloc(maps.size());
+        if (!c->mega_maps) return set_err(QASR_ERR_NOMEM, "tensor map allocation failed");
+        CK(cudaMemcpy(c->mega_maps, maps.data(), maps.size(), cudaMemcpyHostToDevice));
+    } // count and generation live in separate 128-byte lines
     if (getenv("QASR_MEGA_PROF")) c->mega_prof = (long long *)dalloc(3 * 4096 * 8);
     if (!c->x || !c->logits || !c->d_gmax) return set_err(QASR_ERR_NOMEM, "state allocation failed");
     CK(cudaHostAlloc((void **)&c->h_tokens, (size_t)c->max_steps * 4, cudaHostAllocMapped));
@@ -824,6 +842,7 @@ static int enqueue_steps(qasr_ctx_t *c, int n) {
     if (c->use_mega) { // one persistent cooperative launch runs all n steps (stops itself after an EOS token)
         if (c->dec_layers > 28) return set_err(QASR_ERR_ARG, "decode megakernel supports up to 28 decoder layers");
         MegaParams p;
+        p.maps = (const CUtensorMap_st *)c->mega_maps;
         for (int l = 0; l < c->dec_layers; l++) {
             const DecLayerW &L = c->dec[l];
             p.layers[l] = MegaLayer{L.wqkv, L.wo, L.wgu, L.wdown, L.qn, L.kn, L.in_norm, L.post_norm};
@@ -838,6 +857,7 @@ static int enqueue_steps(qasr_ctx_t *c, int n) {
         p.bar_count = c->grid_bar; p.bar_gen = c->grid_bar + 32;
         p.prof = c->mega_prof; p.prof_cap = 4096;
         { const char *dbg = getenv("QASR_MEGA_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+        { const char *tc = getenv("QASR_MEGA_TRACE_CTA"); p.trace_cta = tc ? atoi(tc) : 0; }
         CK(cudaMemsetAsync(c->grid_bar, 0, 4, c->stream)); // arrival counter of the grid barrier
         if (launch_decode_mega(c->stream, p) != 0) return set_err(QASR_ERR_CUDA, "%s", mega_error());
         c->launches += 1;

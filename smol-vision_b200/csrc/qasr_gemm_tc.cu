@@ -303,6 +303,23 @@ static int make_map(CUtensorMap *m, const bf16_t *ptr, int rows, int K, int box_
     return 0;
 }
 
+static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+int tc_encode_map(void *out_map64, const bf16_t *ptr, int rows, int K, int box_cols, int box_rows) {
+    if (gemm_tc_init() != 0) return -1;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode((CUtensorMap *)out_map64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)ptr, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d", (int)r, rows, K);
+        return -1;
+    }
+    return 0;
+}
+
 int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M, int K, const bf16_t *W, int N,
                    const GemmEpilogue &epi) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;

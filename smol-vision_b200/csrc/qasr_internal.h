@@ -43,7 +43,9 @@ struct MegaLayer {
     const bf16_t *wqkv, *wo, *wgu, *wdown;
     const float *qn, *kn, *in_norm, *post_norm;
 };
+struct CUtensorMap_st;
 struct MegaParams {
+    const CUtensorMap_st *maps;            // [n_layers*4 + 1] 2-D maps (box 64 cols x 16 rows, 128B swizzle), device memory
     MegaLayer layers[28];
     int n_layers, H, I, V, n_steps;
     float eps;
@@ -61,6 +63,7 @@ struct MegaParams {
     long long *prof;                       // optional clock64 stamps [2][prof_cap] (CTA 0, last CTA) or NULL
     int prof_cap;
     int debug;                             // bit0: skip grid barriers (timing experiments only)
+    int trace_cta;                         // CTA whose warp 0 writes the per-unit trace (debug bit 6)
 };
 int mega_init(void);
 int launch_decode_mega(cudaStream_t s, const MegaParams &p);
@@ -114,3 +117,5 @@ int gemm_tc_init(void); // resolves cuTensorMapEncodeTiled, sets smem attributes
 int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M, int K, const bf16_t *W, int N,
                    const GemmEpilogue &epi);
 const char *gemm_tc_error(void);
+// encode a 2-D bf16 [rows, K] row-major tensor map with the given box and 128B swizzle into *out (sizeof(CUtensorMap) = 128 bytes, host)
+int tc_encode_map(void *out_map64, const bf16_t *ptr, int rows, int K, int box_cols, int box_rows);

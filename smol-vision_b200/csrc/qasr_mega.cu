@@ -6,11 +6,22 @@
 // Why: a decode step is 3.44 GB (1.7B) / 1.19 GB (0.6B) of bf16 weights read exactly once, i.e.
 // purely HBM-bound, but split over 142 dependent phases.  As separate kernels each phase pays
 // launch + first-byte latency with an empty memory pipe (measured 35 % of HBM peak).  Here one CTA
-// per SM (12 warps) stays resident; every warp owns a private 4-slot shared-memory ring fed by
-// cp.async.bulk (TMA 1-D bulk copy, mbarrier complete_tx) over its static list of weight
-// "units" (row x <=2048-column piece, <= 4 KB, contiguous in the checkpoint layout).  Weight
-// addresses do not depend on activations, so the rings keep streaming ACROSS the grid barriers
-// that separate the dependent phases: up to 192 KB per SM is in flight while a CTA waits.
+// per SM (16 consumer warps) stays resident and every warp streams its static list of weight
+// "units" through a private 3-slot shared-memory ring with TMA tensor copies (mbarrier
+// complete_tx).  Weight addresses do not depend on activations, so the rings keep
+// filling ACROSS the grid barriers that separate the dependent phases.
+//
+// Unit = 16 weight rows x 128 columns, fetched as two [16 x 64] cp.async.bulk.tensor.2d boxes with
+// the 128-byte swizzle (ldmatrix is bank-conflict free; one elected lane issues 2 TMA ops per 4 KB -
+// per-row cp.async.bulk copies cost ~0.1 us of issue time EACH and paced the stream, see
+// profiles/).  The dot products run on tensor cores:
+//     mma.sync.m16n8k16 (bf16 x bf16 -> f32):  A = the 16x16 weight tile straight from the ring,
+//     B = the phase input x as two columns, x_hi = RN(x) and x_lo = RN(x - x_hi),
+// so D[:,0] + D[:,1] = W . x to ~2^-17 relative (weights are exact bf16; same hi/lo device as the
+// prefill GEMMs).  2 instructions (ldmatrix.x4 + mma) consume 256 weights, versus 17 on the FFMA
+// path of round 1 whose consumer, not HBM, paced the stream (profiles/r01_megakernel_*).
+// Warp w owns column slices {w, w+16, ...} of every 16-row group of the CTA; the <=16 per-slice
+// partial sums of a row are added in fixed order => bitwise reproducible run to run.
 //
 // Phases per layer (grid barrier after each):
 //   QKV  : qkv = Wqkv . rmsnorm(x)                         rows 4096
@@ -19,42 +30,35 @@
 //   GU   : act = silu(g) * u,  [g;u] = Wgu . rmsnorm(x)    rows 2I (interleaved gate/up)
 //   DOWN : x += Wdown . act                                rows H
 // then HEAD: per-CTA argmax over its vocab rows of E . rmsnorm(x); barrier; every CTA reduces the
-// 148 winners (lowest index wins ties, reference qwen_asr_kernels.c:536-541); CTA 0 publishes the
-// token and gathers the next input row; barrier.  Every reduction order is fixed => bitwise
-// reproducible run to run.
+// per-CTA winners (lowest index wins ties, reference qwen_asr_kernels.c:536-541); CTA 0 publishes
+// the token and gathers the next input row; barrier.
 #include "qasr_common.cuh"
 #include "qasr_internal.h"
 
+#include <cuda.h>
 #include <stdio.h>
 #include <type_traits>
 
-#define MG_THREADS 384 /* consumer threads */
-#define MG_WARPS 12    /* consumer warps */
-#define MG_ALL_THREADS (MG_THREADS + 32) /* + 1 producer warp */
-#define MG_SLOTS 4
-#define MG_SLOT_BYTES 4096
+#define MG_WARPS 16
+#define MG_THREADS (MG_WARPS * 32)
+#define MG_SLOTS 3
+#define MG_KS 128                       /* columns per unit */
+#define MG_UNIT_BYTES 4096              /* two 128B-swizzled [16 rows x 64 cols] TMA boxes */
 #define MG_MAX_K 6144
-#define MG_MAX_UNITS 1100
-#ifndef MG_PF_AHEAD
-#define MG_PF_AHEAD 0 /* L2 prefetch distance in units per consumer warp; measured slower than none (TMA queue contention) */
-#endif
+#define MG_CHUNK_GROUPS 6               /* 16-row groups reduced together (96 rows) */
+#define MG_PSTRIDE 17
 
 struct MegaSmem {
-    uint8_t ring[MG_WARPS][MG_SLOTS][MG_SLOT_BYTES]; // 196608 B, 16-byte aligned pieces of weight rows
-    float xs[MG_MAX_K];                              // phase input, lane-interleaved (see stage_x)
-    float partial[MG_MAX_UNITS];                     // one dot product per unit
-    uint64_t bar[MG_WARPS][MG_SLOTS];   // full: bulk copy landed
-    uint64_t empty[MG_WARPS][MG_SLOTS]; // empty: consumer warp released the slot
-    volatile int issued[MG_WARPS];
-    volatile int limit_step;           // producer issues units of steps < limit_step only
-    float red[MG_WARPS * 2];
+    uint8_t ring[MG_WARPS][MG_SLOTS][MG_UNIT_BYTES]; // 196608 B, 1024-byte aligned tiles
+    float xs[MG_MAX_K];                              // phase input (f32, natural order)
+    float partial[MG_CHUNK_GROUPS * 16][MG_PSTRIDE]; // [row in chunk][slice owner]
+    uint64_t bar[MG_WARPS][MG_SLOTS];
+    float red[MG_WARPS * 3];
     int redi[MG_WARPS];
     int s_tok;
 };
 
-// barrier over the 12 consumer warps only (the producer warp never joins it)
 __device__ __forceinline__ void csync() { asm volatile("bar.sync 1, %0;" ::"n"(MG_THREADS) : "memory"); }
-
 __device__ __forceinline__ uint32_t mg_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mg_mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mg_smem_u32(bar)), "r"(count) : "memory");
@@ -71,25 +75,17 @@ __device__ __forceinline__ void mg_mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     } while (!done);
 }
-// one elected lane: arm the barrier with the byte count, then start the bulk copy global -> smem
-__device__ __forceinline__ void mg_bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    // WAR on the slot (generic-proxy reads by the warp, then this async-proxy write) is ordered by the
-    // __syncwarp() before the elected lane gets here, as in TMA producer/consumer pipelines
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mg_smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(mg_smem_u32(dst)), "l"(src), "r"(bytes), "r"(mg_smem_u32(bar))
-                 : "memory");
-}
 
 // Grid barrier over a monotonically increasing arrival counter (zeroed by the host before every
 // launch; all CTAs are co-resident: cooperative launch).  Arrival is a fire-and-forget release
-// reduction; the k-th barrier completes when the counter reaches k * nblocks.
-__device__ __forceinline__ void grid_barrier(unsigned *count, unsigned &target, unsigned nblocks, int debug = 0) {
+// reduction (cumulative over the CTA's writes ordered by bar.sync); the k-th barrier completes
+// when the counter reaches k * nblocks.
+__device__ __forceinline__ void grid_barrier(unsigned *count, unsigned &target, unsigned nblocks, int debug) {
     if (debug & 1) { csync(); return; } // timing experiment only: no inter-CTA ordering (wrong results)
     target += nblocks;
     csync();
     if (threadIdx.x == 0) {
-        if (debug & 16) __threadfence(); // not needed: red.release is cumulative over writes ordered by bar.sync
+        if (debug & 16) __threadfence();
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(count) : "memory");
         unsigned c;
         do {
@@ -102,16 +98,16 @@ __device__ __forceinline__ void grid_barrier(unsigned *count, unsigned &target, 
 // ---- static weight schedule -----------------------------------------------------------------
 struct PhaseGeom {
     const bf16_t *W;
-    int K, PC, KP;   // columns, pieces per row, columns per piece
-    int row0, rows;  // first row / row count of this CTA
-    int wpp;         // warps per piece: warp w owns piece w % PC and rows w / PC + j * wpp
+    int K;          // columns
+    int n_slices;   // K / 128
+    int g0, g1;     // 16-row groups [g0, g1) of this CTA
+    int wps;        // warps per slice when n_slices < 16 (else 1)
 };
 
 __device__ __forceinline__ PhaseGeom phase_geom(const MegaParams &p, int wp, int b, int G) {
     PhaseGeom g;
     unsigned N;
-    const int n_w = p.n_layers * 4;
-    if (wp < n_w) {
+    if (wp < p.n_layers * 4) {
         const MegaLayer &L = p.layers[wp >> 2];
         switch (wp & 3) {
             case 0: g.W = L.wqkv; N = 4096; g.K = p.H; break;
@@ -122,42 +118,28 @@ __device__ __forceinline__ PhaseGeom phase_geom(const MegaParams &p, int wp, int
     } else {
         g.W = p.emb; N = p.V; g.K = p.H;
     }
-    g.PC = (g.K + 2047) >> 11;
-    g.KP = g.K / g.PC;
-    g.wpp = MG_WARPS / g.PC;
-    const unsigned groups = N >> 1; // rows are dealt in pairs so SwiGLU gate/up stay together (< 2^17, b < 2^8)
-    const unsigned g0 = groups * (unsigned)b / (unsigned)G, g1 = groups * (unsigned)(b + 1) / (unsigned)G;
-    g.row0 = 2 * (int)g0;
-    g.rows = 2 * (int)(g1 - g0);
+    g.n_slices = g.K / MG_KS;
+    g.wps = g.n_slices < MG_WARPS ? MG_WARPS / g.n_slices : 1;
+    const unsigned groups = N >> 4;
+    g.g0 = (int)(groups * (unsigned)b / (unsigned)G);
+    g.g1 = (int)(groups * (unsigned)(b + 1) / (unsigned)G);
     return g;
 }
+// slices owned by warp w: n_slices >= 16: {w, w+16, w+32}; else the single slice w % n_slices
+__device__ __forceinline__ int warp_nsl(const PhaseGeom &g, int w) {
+    return g.n_slices >= MG_WARPS ? (g.n_slices - w + MG_WARPS - 1) / MG_WARPS : 1;
+}
+__device__ __forceinline__ int warp_slice(const PhaseGeom &g, int w, int si) {
+    return g.n_slices >= MG_WARPS ? w + si * MG_WARPS : w % g.n_slices;
+}
+__device__ __forceinline__ int warp_sub(const PhaseGeom &g, int w) { return g.n_slices >= MG_WARPS ? 0 : w / g.n_slices; }
 
-struct UnitStream { // per-warp cursor over (step, weighted phase, j); unit = (row w/PC + j*wpp, piece w%PC)
-    int step, wp, j;
+struct UnitStream { // per-warp issue cursor: (step, weighted phase, row group, slice index)
+    int step, wp, grp, si, nsl;
     PhaseGeom g;
 };
 
-__device__ __forceinline__ bool warp_has_unit(const PhaseGeom &g, int warp, int j) {
-    return warp < g.wpp * g.PC && warp / g.PC + j * g.wpp < g.rows;
-}
-
-__device__ __forceinline__ void stream_seek(UnitStream &s, const MegaParams &p, int b, int G, int warp, int n_wp) {
-    // move to the next (wp, j) that holds a unit for this warp (or step == n_steps)
-    while (s.step < p.n_steps && !warp_has_unit(s.g, warp, s.j)) {
-        s.j = 0;
-        s.wp++;
-        if (s.wp == n_wp) { s.wp = 0; s.step++; }
-        if (s.step < p.n_steps) s.g = phase_geom(p, s.wp, b, G);
-    }
-}
-
-// Stage the K-vector of a phase into shared memory in the lane-interleaved order the dot loop
-// reads it: element e = 8*(32*i + lane) + 4*half + off  ->  xs[((2*i + half)*32 + lane)*4 + off]
-// so each warp-wide float4 read is one conflict-free 512-byte wavefront.
-__device__ __forceinline__ int xs_index(int e) {
-    const int i = e >> 8, lane = (e >> 3) & 31, half = (e >> 2) & 1, off = e & 3;
-    return (((i << 1) + half) * 32 + lane) * 4 + off;
-}
+__device__ __forceinline__ bool mg_better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
 
 __device__ __forceinline__ float block_sum(float v, float *red, int tid) {
     v = warp_sum(v);
@@ -174,9 +156,10 @@ __device__ __forceinline__ float block_sum(float v, float *red, int tid) {
 // One pass: every thread keeps its <= 12 elements (and the norm weights) in registers across the
 // block reduction, so the critical path is a single L2 round trip.
 __device__ __forceinline__ void stage_x(MegaSmem &sm, const float *x, const float *gamma, int K, float eps, int tid) {
-    float v[MG_MAX_K / MG_THREADS], gm[MG_MAX_K / MG_THREADS];
+    constexpr int PER = MG_MAX_K / MG_THREADS;
+    float v[PER], gm[PER];
 #pragma unroll
-    for (int i = 0; i < MG_MAX_K / MG_THREADS; i++) {
+    for (int i = 0; i < PER; i++) {
         const int e = tid + i * MG_THREADS;
         v[i] = e < K ? __ldcg(x + e) : 0.0f;
         gm[i] = (gamma && e < K) ? gamma[e] : 1.0f;
@@ -185,148 +168,170 @@ __device__ __forceinline__ void stage_x(MegaSmem &sm, const float *x, const floa
     if (gamma) {
         float ss = 0.0f;
 #pragma unroll
-        for (int i = 0; i < MG_MAX_K / MG_THREADS; i++) ss = fmaf(v[i], v[i], ss);
+        for (int i = 0; i < PER; i++) ss = fmaf(v[i], v[i], ss);
         const float tot = block_sum(ss, sm.red, tid);
         inv = 1.0f / sqrtf(tot / (float)K + eps);
     }
 #pragma unroll
-    for (int i = 0; i < MG_MAX_K / MG_THREADS; i++) {
+    for (int i = 0; i < PER; i++) {
         const int e = tid + i * MG_THREADS;
-        if (e < K) sm.xs[xs_index(e)] = gamma ? v[i] * inv * gm[i] : v[i];
+        if (e < K) sm.xs[e] = gamma ? v[i] * inv * gm[i] : v[i];
     }
     csync();
 }
 
-__device__ __forceinline__ bool mg_better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
-
-__device__ __forceinline__ bool mg_mbar_test(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(mg_smem_u32(bar)), "r"(parity)
-        : "memory");
-    return done != 0;
-}
-__device__ __forceinline__ void mg_mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mg_smem_u32(bar)) : "memory");
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b); // .x = a (low half), .y = b
+    return *reinterpret_cast<const uint32_t *>(&v);
 }
 
-__global__ void __launch_bounds__(MG_ALL_THREADS, 1) decode_mega_kernel(const MegaParams p) {
-    extern __shared__ __align__(128) uint8_t mg_raw[];
-    MegaSmem &sm = *reinterpret_cast<MegaSmem *>(mg_raw);
+__global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaParams p) {
+    extern __shared__ __align__(1024) uint8_t mg_raw[];
+    MegaSmem &sm = *reinterpret_cast<MegaSmem *>((reinterpret_cast<uintptr_t>(mg_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gid = lane >> 2, tig = lane & 3; // mma fragment coordinates
     const int b = blockIdx.x, G = gridDim.x;
     const int n_wp = p.n_layers * 4 + 1;
 
-    if (warp < MG_WARPS && lane == 0)
-        for (int s = 0; s < MG_SLOTS; s++) { mg_mbar_init(&sm.bar[warp][s], 1); mg_mbar_init(&sm.empty[warp][s], 1); }
-    if (tid == 0) sm.limit_step = p.n_steps;
+    if (lane == 0)
+        for (int s = 0; s < MG_SLOTS; s++) mg_mbar_init(&sm.bar[warp][s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    if (warp == MG_WARPS) {
-        // ===== producer warp: lane i streams consumer warp i's static unit list into its ring.
-        // Issue is decoupled from consumption, so bulk copies for LATER phases keep entering free
-        // slots while the consumers sit in a grid barrier or stage activations.
-        if (lane < MG_WARPS && !(p.debug & 32)) {
-            sm.issued[lane] = 0; // default (coupled) mode: every consumer warp issues its own bulk copies
-        } else if (lane < MG_WARPS) {
-            UnitStream is;
-            is.step = 0; is.wp = 0; is.j = 0;
-            is.g = phase_geom(p, 0, b, G);
-            stream_seek(is, p, b, G, lane, n_wp);
-            // second cursor: L2 prefetch runs MG_PF_AHEAD units ahead of the shared-memory ring, so HBM
-            // keeps streaming into the 126 MB L2 while the (192 KB) ring is full during a stall and the
-            // ring refills at L2 latency/bandwidth afterwards
-            UnitStream pf = is;
-            unsigned issued = 0, prefetched = 0;
-            while (is.step < sm.limit_step) {
-                if (prefetched < issued + MG_PF_AHEAD && pf.step < sm.limit_step) {
-                    const int row = pf.g.row0 + lane / pf.g.PC + pf.j * pf.g.wpp, piece = lane % pf.g.PC;
-                    const bf16_t *src = pf.g.W + (size_t)row * pf.g.K + (size_t)piece * pf.g.KP;
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)pf.g.KP * 2) : "memory");
-                    prefetched++;
-                    pf.j++;
-                    stream_seek(pf, p, b, G, lane, n_wp);
+    // ---- per-warp weight stream: the issue cursor runs MG_SLOTS units ahead of consumption
+    UnitStream is;
+    is.step = 0; is.wp = 0; is.si = 0;
+    is.g = phase_geom(p, 0, b, G);
+    is.nsl = warp_nsl(is.g, warp);
+    is.grp = is.g.g0 + warp_sub(is.g, warp);
+    auto stream_seek = [&]() { // move to the next phase that holds a unit for this warp
+        while (is.step < p.n_steps && is.grp >= is.g.g1) {
+            is.wp++;
+            if (is.wp == n_wp) { is.wp = 0; is.step++; }
+            if (is.step < p.n_steps) {
+                is.g = phase_geom(p, is.wp, b, G);
+                is.nsl = warp_nsl(is.g, warp);
+                is.grp = is.g.g0 + warp_sub(is.g, warp);
+                is.si = 0;
+            }
+        }
+    };
+    stream_seek();
+    unsigned issued = 0, consumed = 0;
+    auto top_up = [&]() {
+        while (issued - consumed < MG_SLOTS && is.step < p.n_steps) {
+            const int slot = issued % MG_SLOTS;
+            if (lane == 0) { // one elected lane: two [16 rows x 64 cols] boxes (128B swizzle) = one 4 KB unit
+                const uint32_t bar = mg_smem_u32(&sm.bar[warp][slot]), dst = mg_smem_u32(sm.ring[warp][slot]);
+                const CUtensorMap *map = p.maps + is.wp;
+                const int c0 = warp_slice(is.g, warp, is.si) * MG_KS, r0 = is.grp * 16;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(MG_UNIT_BYTES) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                             ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(r0) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                             ::"r"(dst + 2048), "l"(map), "r"(bar), "r"(c0 + 64), "r"(r0) : "memory");
+            }
+            issued++;
+            if (++is.si == is.nsl) { is.si = 0; is.grp += is.g.wps; }
+            stream_seek();
+        }
+    };
+    top_up();
+
+    // ---- one weighted phase: y[row] = W[row,:] . xs for the CTA's rows, handed to `epi(row, y)`
+    // in chunks of <= 96 rows.  NSL = column slices owned by this warp (1, 2 or 3).
+    auto run_phase_n = [&](const PhaseGeom &g, auto nsl_c, auto &&epi, const float *resid) {
+        constexpr int NSL = decltype(nsl_c)::value;
+        // residual phases: the old x of this thread's row of the FIRST chunk is fetched now, off the critical path
+        float res0 = 0.0f;
+        if (resid && tid < (min(g.g1, g.g0 + MG_CHUNK_GROUPS) - g.g0) * 16) res0 = __ldcg(resid + g.g0 * 16 + tid);
+        // B fragments of x for this warp's slices: lanes with gid 0 carry x_hi, gid 1 carry x_lo
+        uint32_t bf[NSL][8][2];
+#pragma unroll
+        for (int si = 0; si < NSL; si++) {
+            const int k0 = warp_slice(g, warp, si) * MG_KS + 2 * tig;
+#pragma unroll
+            for (int kb = 0; kb < 8; kb++) {
+                float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+                if (gid < 2) {
+                    const float2 a = *reinterpret_cast<const float2 *>(sm.xs + k0 + kb * 16);
+                    const float2 c = *reinterpret_cast<const float2 *>(sm.xs + k0 + kb * 16 + 8);
+                    v0 = a.x; v1 = a.y; v2 = c.x; v3 = c.y;
+                    if (gid == 1) { // residual after rounding to bf16
+                        v0 -= __bfloat162float(__float2bfloat16_rn(v0)); v1 -= __bfloat162float(__float2bfloat16_rn(v1));
+                        v2 -= __bfloat162float(__float2bfloat16_rn(v2)); v3 -= __bfloat162float(__float2bfloat16_rn(v3));
+                    }
                 }
-                const int slot = issued % MG_SLOTS;
-                if (!mg_mbar_test(&sm.empty[lane][slot], ((issued / MG_SLOTS) & 1) ^ 1)) { __nanosleep(64); continue; } // ring full
-                const int row = is.g.row0 + lane / is.g.PC + is.j * is.g.wpp, piece = lane % is.g.PC;
-                const bf16_t *src = is.g.W + (size_t)row * is.g.K + (size_t)piece * is.g.KP;
-                mg_bulk_load(sm.ring[lane][slot], src, (uint32_t)is.g.KP * 2, &sm.bar[lane][slot]);
-                issued++;
-                is.j++;
-                stream_seek(is, p, b, G, lane, n_wp);
+                bf[si][kb][0] = pack_bf16(v0, v1);
+                bf[si][kb][1] = pack_bf16(v2, v3);
             }
-            sm.issued[lane] = (int)issued;
         }
-        __syncthreads(); // joins the consumers' final barrier
-        return;
-    }
-
-    // ===== consumer warps
-    unsigned consumed = 0, issued_c = 0;
-    const bool coupled = (p.debug & 32) == 0; // bit 5 selects the dedicated producer warp instead (measured slower)
-    UnitStream cs;
-    cs.step = 0; cs.wp = 0; cs.j = 0;
-    cs.g = phase_geom(p, 0, b, G);
-    if (coupled) stream_seek(cs, p, b, G, warp, n_wp);
-    auto top_up = [&]() { // coupled mode only: refill the slots this warp has freed
-        while (issued_c - consumed < MG_SLOTS && cs.step < p.n_steps) {
-            if (lane == 0) {
-                const int row = cs.g.row0 + warp / cs.g.PC + cs.j * cs.g.wpp, piece = warp % cs.g.PC;
-                const bf16_t *src = cs.g.W + (size_t)row * cs.g.K + (size_t)piece * cs.g.KP;
-                const int slot = issued_c % MG_SLOTS;
-                mg_bulk_load(sm.ring[warp][slot], src, (uint32_t)cs.g.KP * 2, &sm.bar[warp][slot]);
+        const int sub = warp_sub(g, warp);
+        const int pidx = g.n_slices >= MG_WARPS ? warp : warp % g.n_slices; // column of partial[][] this warp fills
+        const int np = g.n_slices >= MG_WARPS ? MG_WARPS : g.n_slices;     // partial sums per row
+        // ldmatrix.x4 lane address inside a tile: matrices (rows 0-7,k 0-7) (rows 8-15,k 0-7) (rows 0-7,k 8-15) (rows 8-15,k 8-15).
+        // A box row is 128 bytes = 8 chunks of 16 B; TMA's 128B swizzle stores chunk c of row r at chunk c ^ (r & 7).
+        const int lm_row = ((lane >> 3) & 1) * 8 + (lane & 7), lm_hi = lane >> 4;
+        const uint32_t lm_rowoff = (uint32_t)(lm_row * 128);
+        for (int cg0 = g.g0; cg0 < g.g1; cg0 += MG_CHUNK_GROUPS) {
+            const int cg1 = min(cg0 + MG_CHUNK_GROUPS, g.g1);
+            // this warp's groups in the chunk: (grp - g.g0) % wps == sub
+            int first = cg0;
+            { const int r = (first - g.g0) % g.wps; first += (sub - r + g.wps) % g.wps; }
+            for (int grp = first; grp < cg1; grp += g.wps) {
+                float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+                for (int si = 0; si < NSL; si++) {
+                    const int slot = consumed % MG_SLOTS;
+                    const bool tr = (p.debug & 64) && p.prof && b == p.trace_cta && tid == 0 && consumed < 1300;
+                    if (tr) p.prof[2 * p.prof_cap + 3 * consumed] = clock64();
+                    mg_mbar_wait(&sm.bar[warp][slot], (consumed / MG_SLOTS) & 1);
+                    if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 1] = clock64();
+                    const uint32_t tile = mg_smem_u32(sm.ring[warp][slot]) + lm_rowoff;
+#pragma unroll
+                    for (int kb = 0; kb < 8; kb++) {
+                        uint32_t a0, a1, a2, a3;
+                        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                                     : "r"(tile + (kb >> 2) * 2048 + (((((kb & 3) << 1) | lm_hi) ^ (lm_row & 7)) << 4)));
+                        if (kb & 1)
+                            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                         : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
+                                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf[si][kb][0]), "r"(bf[si][kb][1]));
+                        else
+                            asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                         : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(bf[si][kb][0]), "r"(bf[si][kb][1]));
+                    }
+                    if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 2] = clock64();
+                    __syncwarp();
+                    consumed++;
+                    top_up(); // the freed slot immediately takes the next unit (possibly of a later phase/token)
+                }
+                if (tig == 0) { // column 0 = x_hi sums, column 1 = x_lo sums; rows gid and gid+8
+                    const int r = (grp - cg0) * 16 + gid;
+                    sm.partial[r][pidx] = (c0 + d0) + (c1 + d1);
+                    sm.partial[r + 8][pidx] = (c2 + d2) + (c3 + d3);
+                }
             }
-            issued_c++;
-            cs.j++;
-            stream_seek(cs, p, b, G, warp, n_wp);
+            csync();
+            const int rows = (cg1 - cg0) * 16;
+            if (tid < rows) {
+                auto rowsum = [&](int r) { // fixed-order sum of the per-slice partials of chunk row r
+                    float y = 0.0f;
+                    for (int i = 0; i < np; i++) y += sm.partial[r][i];
+                    return y;
+                };
+                epi(cg0 * 16 + tid, tid, rowsum, (resid && cg0 != g.g0) ? __ldcg(resid + cg0 * 16 + tid) : res0);
+            }
+            csync();
         }
     };
-    if (coupled) top_up();
-
-    // Dot products of this warp's units of one weighted phase -> sm.partial[row_local*PC + piece].
-    // The warp's slice of the phase input (<= 2048 columns of its piece) is pulled from sm.xs into
-    // 64 registers ONCE, so the per-unit shared-memory traffic is just the 4 KB of weights and the
-    // consumer runs several times faster than HBM can refill the rings.
-    auto run_units_n = [&](const PhaseGeom &g, auto nit_c) {
-        constexpr int NIT = decltype(nit_c)::value; // 256-column iterations per unit (KP / 256)
-        const int piece = warp % g.PC;
-        float4 xa[NIT], xb[NIT];
-        {
-            const float4 *xv = reinterpret_cast<const float4 *>(sm.xs) + (size_t)piece * (g.KP >> 2);
-#pragma unroll
-            for (int it = 0; it < NIT; it++) { xa[it] = xv[it * 64 + lane]; xb[it] = xv[it * 64 + 32 + lane]; }
-        }
-        for (int rl = warp / g.PC; rl < g.rows; rl += g.wpp) {
-            const int slot = consumed % MG_SLOTS;
-            const bool tr = (p.debug & 64) && p.prof && b == 0 && tid == 0 && consumed < 1300;
-            if (tr) p.prof[2 * p.prof_cap + 3 * consumed] = clock64();
-            mg_mbar_wait(&sm.bar[warp][slot], (consumed / MG_SLOTS) & 1);
-            if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 1] = clock64();
-            const uint4 *wv = reinterpret_cast<const uint4 *>(sm.ring[warp][slot]);
-            float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f}; // 4 independent FMA chains (latency, not throughput, bounds a unit)
-#pragma unroll
-            for (int it = 0; it < NIT; it++) acc4[it & 3] = dot8(wv[it * 32 + lane], xa[it], xb[it], acc4[it & 3]);
-            float acc = warp_sum((acc4[0] + acc4[1]) + (acc4[2] + acc4[3]));
-            if (lane == 0) sm.partial[rl * g.PC + piece] = acc;
-            if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 2] = clock64();
-            __syncwarp();
-            if (lane == 0 && !coupled) mg_mbar_arrive(&sm.empty[warp][slot]); // slot free: the producer may refill it
-            consumed++;
-            if (coupled) top_up();
-        }
-    };
-    auto run_units = [&](const PhaseGeom &g) {
-        if (warp >= g.wpp * g.PC) return;
-        switch (g.KP >> 8) {
-            case 8: run_units_n(g, std::integral_constant<int, 8>{}); break;
-            case 6: run_units_n(g, std::integral_constant<int, 6>{}); break;
-            default: run_units_n(g, std::integral_constant<int, 4>{}); break;
+    auto run_phase = [&](const PhaseGeom &g, auto &&epi, const float *resid = nullptr) {
+        switch (warp_nsl(g, warp)) {
+            case 3: run_phase_n(g, std::integral_constant<int, 3>{}, epi, resid); break;
+            case 2: run_phase_n(g, std::integral_constant<int, 2>{}, epi, resid); break;
+            default: run_phase_n(g, std::integral_constant<int, 1>{}, epi, resid); break;
         }
     };
 
@@ -351,17 +356,15 @@ __global__ void __launch_bounds__(MG_ALL_THREADS, 1) decode_mega_kernel(const Me
                 mark();
                 stage_x(sm, p.x, L.in_norm, p.H, p.eps, tid);
                 mark();
-                run_units(g);
-                csync();
+                run_phase(g, [&](int row, int r, auto &&rowsum, float) { p.qkv[row] = rowsum(r); });
                 mark();
-                for (int r = tid; r < g.rows; r += MG_THREADS) p.qkv[g.row0 + r] = sm.partial[r];
                 mark();
             }
             grid_barrier(p.bar_count, bar_target, G, p.debug);
             mark();
             // ---------------- ATTN (flash-decoding partials); S splits of the pos+1 keys
             const int n_keys = pos + 1;
-            int S = (n_keys + 63) / 64;
+            int S = (n_keys + 95) / 96;
             S = S < 1 ? 1 : (S > QASR_ATTN_SPLITS ? QASR_ATTN_SPLITS : S);
             if (b < 8 * S) {
                 const int h = b / S, split = b % S;
@@ -378,10 +381,15 @@ __global__ void __launch_bounds__(MG_ALL_THREADS, 1) decode_mega_kernel(const Me
                     q1 = __ldcg(p.qkv + (2 * h + 1) * 128 + tid);
                     kk = owner ? __ldcg(p.qkv + 2048 + h * 128 + tid) : 0.0f;
                 }
-                const float s0 = block_sum(q0 * q0, sm.red, tid);
-                const float s1 = block_sum(q1 * q1, sm.red, tid);
-                const float s2 = block_sum(kk * kk, sm.red, tid);
+                { // three sums of squares in one block reduction (only warps 0-3 hold data)
+                    const float a = warp_sum(q0 * q0), c2 = warp_sum(q1 * q1), d2 = warp_sum(kk * kk);
+                    if (lane == 0 && warp < 4) { sm.red[warp] = a; sm.red[4 + warp] = c2; sm.red[8 + warp] = d2; }
+                }
+                csync();
                 if (tid < 128) {
+                    const float s0 = sm.red[0] + sm.red[1] + sm.red[2] + sm.red[3];
+                    const float s1 = sm.red[4] + sm.red[5] + sm.red[6] + sm.red[7];
+                    const float s2 = sm.red[8] + sm.red[9] + sm.red[10] + sm.red[11];
                     tmp[tid] = q0 * (1.0f / sqrtf(s0 / 128.0f + p.eps)) * L.qn[tid];
                     tmp[128 + tid] = q1 * (1.0f / sqrtf(s1 / 128.0f + p.eps)) * L.qn[tid];
                     tmp[256 + tid] = kk * (1.0f / sqrtf(s2 / 128.0f + p.eps)) * L.kn[tid];
@@ -458,9 +466,8 @@ __global__ void __launch_bounds__(MG_ALL_THREADS, 1) decode_mega_kernel(const Me
             // ---------------- WO: input = merged attention output (every CTA merges the S partials itself)
             {
                 const PhaseGeom g = phase_geom(p, l * 4 + 1, b, G);
-                // merge the S split partials: softmax factors per (head, split) first, then one
-                // pass of independent coalesced loads per output element
-                float *fac = sm.partial; // [16 heads][S] normalised weights (partial[] is free here)
+                // softmax factors per (head, split) first, then one pass of independent coalesced loads
+                float *fac = &sm.partial[0][0]; // [16 heads][16 splits] normalised weights (partial[] is free here)
                 if (tid < 16) {
                     const int hh = tid >> 1, hd = tid & 1;
                     float m[QASR_ATTN_SPLITS], lv[QASR_ATTN_SPLITS], M = -1e30f;
@@ -482,28 +489,25 @@ __global__ void __launch_bounds__(MG_ALL_THREADS, 1) decode_mega_kernel(const Me
                     for (int sp = 0; sp < S; sp++)
                         A += __ldcg(p.attn_part + ((size_t)(hh * QASR_ATTN_SPLITS + sp) * 2 + hd) * QASR_ATTN_PART_STRIDE + d) *
                              fac[hq * QASR_ATTN_SPLITS + sp];
-                    sm.xs[xs_index(e)] = A;
+                    sm.xs[e] = A;
                 }
                 csync();
                 mark();
-                run_units(g);
-                csync();
+                run_phase(g, [&](int row, int r, auto &&rowsum, float xold) { p.x[row] = xold + rowsum(r); }, p.x);
                 mark();
-                for (int r = tid; r < g.rows; r += MG_THREADS) p.x[g.row0 + r] = __ldcg(p.x + g.row0 + r) + sm.partial[r];
                 mark();
             }
             grid_barrier(p.bar_count, bar_target, G, p.debug);
             mark();
-            // ---------------- GU + SwiGLU
+            // ---------------- GU + SwiGLU: rows (2j, 2j+1) = (gate_j, up_j) are neighbours in a chunk
             {
                 const PhaseGeom g = phase_geom(p, l * 4 + 2, b, G);
                 stage_x(sm, p.x, L.post_norm, p.H, p.eps, tid);
                 mark();
-                run_units(g);
-                csync();
+                run_phase(g, [&](int row, int r, auto &&rowsum, float) {
+                    if (!(row & 1)) p.act[row >> 1] = silu(rowsum(r)) * rowsum(r + 1);
+                });
                 mark();
-                for (int r = tid; r < g.rows / 2; r += MG_THREADS)
-                    p.act[g.row0 / 2 + r] = silu(sm.partial[2 * r]) * sm.partial[2 * r + 1];
                 mark();
             }
             grid_barrier(p.bar_count, bar_target, G, p.debug);
@@ -513,15 +517,8 @@ __global__ void __launch_bounds__(MG_ALL_THREADS, 1) decode_mega_kernel(const Me
                 const PhaseGeom g = phase_geom(p, l * 4 + 3, b, G);
                 stage_x(sm, p.act, nullptr, p.I, p.eps, tid);
                 mark();
-                run_units(g);
-                csync();
+                run_phase(g, [&](int row, int r, auto &&rowsum, float xold) { p.x[row] = xold + rowsum(r); }, p.x);
                 mark();
-                const int rows = g.rows;
-                for (int r = tid; r < rows; r += MG_THREADS) {
-                    float v = 0.0f;
-                    for (int pc = 0; pc < g.PC; pc++) v += sm.partial[r * g.PC + pc];
-                    p.x[g.row0 + r] = __ldcg(p.x + g.row0 + r) + v;
-                }
                 mark();
             }
             grid_barrier(p.bar_count, bar_target, G, p.debug);
@@ -531,12 +528,9 @@ __global__ void __launch_bounds__(MG_ALL_THREADS, 1) decode_mega_kernel(const Me
         {
             const PhaseGeom g = phase_geom(p, p.n_layers * 4, b, G);
             stage_x(sm, p.x, p.final_norm, p.H, p.eps, tid);
-            run_units(g);
-            csync();
             float bv = -1e30f;
             int bi = 0x7fffffff;
-            for (int r = tid; r < g.rows; r += MG_THREADS)
-                if (mg_better(sm.partial[r], g.row0 + r, bv, bi)) { bv = sm.partial[r]; bi = g.row0 + r; }
+            run_phase(g, [&](int row, int r, auto &&rowsum, float) { const float y = rowsum(r); if (mg_better(y, row, bv, bi)) { bv = y; bi = row; } });
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const float ov = __shfl_xor_sync(QASR_FULL, bv, o);
@@ -581,15 +575,11 @@ __global__ void __launch_bounds__(MG_ALL_THREADS, 1) decode_mega_kernel(const Me
                 }
             }
             stop = (tok == 151643 || tok == 151645); // reference qwen_asr.c:792
-            if (stop && tid == 0) sm.limit_step = step + 1;
         }
         grid_barrier(p.bar_count, bar_target, G, p.debug);
     }
     if (b == 0 && tid == 0) { *p.d_pos = pos; *p.d_step = step; }
-    // join the producer, then drain bulk copies that were prefetched past an early stop before the
-    // CTA's shared memory goes away
-    __syncthreads();
-    const unsigned issued = coupled ? issued_c : (unsigned)sm.issued[warp];
+    // drain bulk copies that were prefetched past an early stop before the CTA's shared memory goes away
     while (consumed < issued) {
         mg_mbar_wait(&sm.bar[warp][consumed % MG_SLOTS], (consumed / MG_SLOTS) & 1);
         consumed++;
@@ -606,8 +596,8 @@ int mega_init(void) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MegaSmem));
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_mega_kernel, MG_ALL_THREADS, sizeof(MegaSmem));
+    cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MegaSmem) + 1024);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_mega_kernel, MG_THREADS, sizeof(MegaSmem) + 1024);
     if (e != cudaSuccess || !coop || per_sm < 1 || sms < 1) {
         snprintf(g_mega_err, sizeof g_mega_err, "decode megakernel unavailable: %s (coop=%d, blocks/SM=%d, smem=%zu)",
                  cudaGetErrorString(e), coop, per_sm, sizeof(MegaSmem));
@@ -620,14 +610,14 @@ int mega_init(void) {
 
 int launch_decode_mega(cudaStream_t s, const MegaParams &p) {
     if (mega_init() != 0) return -1;
-    auto kp_ok = [](int K) { const int kp = K / ((K + 2047) / 2048); return kp == 1024 || kp == 1536 || kp == 2048; };
-    if (p.H > MG_MAX_K || p.I > MG_MAX_K || !kp_ok(p.H) || !kp_ok(p.I) || p.n_steps > 64) {
-        snprintf(g_mega_err, sizeof g_mega_err, "decode megakernel: unsupported dims H=%d I=%d", p.H, p.I);
+    auto k_ok = [](int K) { return K % MG_KS == 0 && K <= MG_MAX_K && (K / MG_KS <= MG_WARPS ? MG_WARPS % (K / MG_KS) == 0 : K / MG_KS <= 3 * MG_WARPS); };
+    if (!k_ok(p.H) || !k_ok(p.I) || p.n_steps > 64 || p.n_layers > 28 || (p.V & 15) || (p.H & 15) || (p.I & 7)) {
+        snprintf(g_mega_err, sizeof g_mega_err, "decode megakernel: unsupported dims H=%d I=%d V=%d", p.H, p.I, p.V);
         return -1;
     }
     void *args[] = {(void *)&p};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)decode_mega_kernel, dim3(g_mega_grid), dim3(MG_ALL_THREADS), args,
-                                                sizeof(MegaSmem), s);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)decode_mega_kernel, dim3(g_mega_grid), dim3(MG_THREADS), args,
+                                                sizeof(MegaSmem) + 1024, s);
     if (e != cudaSuccess) {
         snprintf(g_mega_err, sizeof g_mega_err, "decode megakernel launch: %s", cudaGetErrorString(e));
         return -1;

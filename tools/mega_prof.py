@@ -12,7 +12,7 @@ audio = pkg.synth_audio(3.64, 100)
 ids, info = eng.transcribe_ids(audio, 8)
 eng.kv_len = info["enc_tokens"] + 15 + 8 - 1
 tok = eng.step_token(int(ids[-1]))      # one single-step launch -> stamps of exactly one token
-buf = np.zeros(2 * 4096, np.int64)
+buf = np.zeros(3 * 4096, np.int64)
 eng.lib.qasr_debug_mega_prof.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(dtype=np.int64)]
 assert eng.lib.qasr_debug_mega_prof(eng.ctx, buf) == 0
 for which, name in ((0, "CTA0"), (1, "CTAlast")):
