@@ -47,8 +47,10 @@ const char *qasr_cuda_last_error(void) { return g_err; }
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool grew = false;
     int reserve(size_t bytes) {
         if (bytes <= cap) return 0;
+        grew = true;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -114,6 +116,9 @@ struct qasr_ctx {
     int *head_idx = nullptr;
     unsigned *grid_bar = nullptr;
     long long *mega_prof = nullptr;
+    struct GraphEntry { long long key[4]; cudaGraphExec_t exec; long long n_launch; };
+    std::vector<GraphEntry> graph_cache; // captured encoder / prefill launch sequences, keyed by shape
+    long long ws_gen = 0;                // bumped whenever a workspace the graphs point into is reallocated
     void *mega_maps = nullptr; // device array of CUtensorMap (128 B each): decoder matrices in phase order + embedding
     // scratch
     DevBuf ws_samples, ws_meltmp, ws_mel, ws_enc, ws_encout, ws_pre, ws_ids, ws_geom;
@@ -129,6 +134,7 @@ struct qasr_ctx {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static void note_growth(qasr_ctx_t *c, DevBuf &b) { if (b.grew) { c->ws_gen++; b.grew = false; } }
 
 // ------------------------------------------------------------------ lifecycle
 int qasr_cuda_device_count(void) {
@@ -165,7 +171,7 @@ qasr_ctx_t *qasr_cuda_init(int device) {
         delete c;
         return nullptr;
     }
-    if (gemm_tc_init() != 0) {
+    if (gemm_tc_prepare() != 0) {
         set_err(QASR_ERR_CUDA, "%s", gemm_tc_error());
         cudaStreamDestroy(c->stream);
         delete c;
@@ -180,6 +186,7 @@ void qasr_cuda_free(qasr_ctx_t *c) {
     cudaStreamSynchronize(c->stream);
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->graph) cudaGraphDestroy(c->graph);
+    for (auto &ge : c->graph_cache) cudaGraphExecDestroy(ge.exec);
     for (void *p : c->owned) cudaFree(p);
     cudaFree(c->kv_k); cudaFree(c->kv_v); cudaFree(c->rope_cos); cudaFree(c->rope_sin);
     if (c->h_tokens) cudaFreeHost(c->h_tokens);
@@ -372,6 +379,7 @@ static int ensure_rope(qasr_ctx_t *c, int need_pos) {
     CK(cudaMemcpy(ns, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice));
     cudaFree(c->rope_cos); cudaFree(c->rope_sin);
     c->rope_cos = nc; c->rope_sin = ns; c->rope_cap = cap;
+    c->ws_gen++;
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; } // pointers changed
     return 0;
 }
@@ -396,6 +404,7 @@ static int ensure_kv(qasr_ctx_t *c, int need_pos, int keep) {
         }
     cudaFree(c->kv_k); cudaFree(c->kv_v);
     c->kv_k = nk; c->kv_v = nv; c->kv_max = cap;
+    c->ws_gen++;
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
     return 0;
 }
@@ -547,6 +556,35 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
     return 0;
 }
 
+// Launch sequences of the encoder / prefill are captured once per shape into a CUDA graph and replayed:
+// at these sizes the ~230 + ~170 launches of one utterance are CPU-launch-bound otherwise (each
+// tensor-core GEMM launch also encodes two TMA descriptors on the host).
+template <class F>
+static int run_cached_graph(qasr_ctx_t *c, long long k0, long long k1, long long k2, F &&enqueue) {
+    if (!c->use_graph) return enqueue();
+    const long long key[4] = {k0, k1, k2, c->ws_gen};
+    for (auto &ge : c->graph_cache)
+        if (!memcmp(ge.key, key, sizeof key)) { CK(cudaGraphLaunch(ge.exec, c->stream)); c->launches += ge.n_launch; return 0; }
+    const long long launches_before = c->launches;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return set_err(QASR_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    cudaGraphExec_t exec = nullptr;
+    CK(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    if (c->graph_cache.size() >= 16) { cudaGraphExecDestroy(c->graph_cache.front().exec); c->graph_cache.erase(c->graph_cache.begin()); }
+    qasr_ctx::GraphEntry ge;
+    memcpy(ge.key, key, sizeof key);
+    ge.exec = exec;
+    ge.n_launch = c->launches - launches_before;
+    c->graph_cache.push_back(ge);
+    CK(cudaGraphLaunch(exec, c->stream));
+    return 0;
+}
+
 // ------------------------------------------------------------------ mel
 int qasr_cuda_mel_frames(int n_samples) { return n_samples / 160; }
 
@@ -640,7 +678,9 @@ static int encode_device(qasr_ctx_t *c, const float *d_mel, int frames, int *T_o
                  o_xn = carve((size_t)T * d * 2 * 2), o_qkv = carve((size_t)T * 3 * d * 4),
                  o_att = carve((size_t)T * d * 2 * 2), o_mid = carve((size_t)T * F * 2 * 2);
     if (c->ws_enc.reserve(off) || c->ws_encout.reserve((size_t)T * H * 4)) return set_err(QASR_ERR_NOMEM, "encoder workspace (%zu bytes)", off);
+    note_growth(c, c->ws_enc); note_growth(c, c->ws_encout); note_growth(c, c->ws_geom); note_growth(c, c->ws_mel);
     uint8_t *B = c->ws_enc.as<uint8_t>();
+    auto enqueue = [&]() -> int {
 #define HI(o) reinterpret_cast<bf16_t *>(B + (o))
 #define LO(o, n) (reinterpret_cast<bf16_t *>(B + (o)) + (size_t)(n))
     cudaStream_t s = c->stream;
@@ -681,6 +721,9 @@ static int encode_device(qasr_ctx_t *c, const float *d_mel, int frames, int *T_o
     CKR(gemm(c, xn_hi, xn_lo, T, d, c->p1w, d, QASR_GEMM_GELU_SPLIT, nullptr, at_hi, at_lo, c->p1b, d));
     CKR(gemm(c, at_hi, at_lo, T, d, c->p2w, H, QASR_GEMM_F32, c->ws_encout.as<float>(), nullptr, nullptr, c->p2b, H));
     c->launches += 1;
+    return 0;
+    };
+    CKR(run_cached_graph(c, 1, frames, c->nsplit, enqueue));
 #undef HI
 #undef LO
     CK(cudaGetLastError());
@@ -733,6 +776,8 @@ static int prefill_device(qasr_ctx_t *c, int P, int kv_len) {
     const bool two = c->nsplit == 2;
     const size_t kvd = (size_t)c->kv_heads * c->hd;
     const float scale = 1.0f / sqrtf((float)c->hd);
+    note_growth(c, c->ws_pre);
+    auto enqueue = [&]() -> int {
     for (int l = 0; l < c->dec_layers; l++) {
         const DecLayerW &L = c->dec[l];
         float *kc = c->kv_k + (size_t)l * c->kv_max * kvd, *vc = c->kv_v + (size_t)l * c->kv_max * kvd;
@@ -746,6 +791,9 @@ static int prefill_device(qasr_ctx_t *c, int P, int kv_len) {
         CKR(gemm(c, ac_hi, ac_lo, P, I, L.wdown, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H));
         c->launches += 4;
     }
+    return 0;
+    };
+    CKR(run_cached_graph(c, 2, P, (long long)kv_len * 8 + c->nsplit, enqueue));
     CK(cudaGetLastError());
     return 0;
 }

@@ -255,6 +255,208 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
 }
 
+
+// ------------------------------------------------------------------ skinny-M variant (M <= 256)
+// At the single-utterance shapes of the encoder / prefill (M = 26...157 rows) a GEMM is a weight
+// stream: bytes = 2*N*K, flops are irrelevant.  Roles are swapped so that the 128-row MMA operand is
+// the WEIGHT tile (each weight byte enters shared memory exactly once) and the activations are the
+// N-side operand (MP = M rounded up to 64/128/256 columns of TMEM); split-K spreads one weight
+// matrix over ~148 CTAs.  D[n (TMEM lane), m (column)] = sum_k W[n,k] * A[m,k].
+// Split-K partials go to a workspace; the LAST CTA of a tile (ticket counter) adds the partials in
+// fixed split order and runs the epilogue => deterministic.  Stores are coalesced along n.
+struct SkParams {
+    int M, N, K, nsplit, S, kb_per; // S = split-K factor, kb_per = k-blocks per split
+    float *ws;                      // [n_tiles][S][MP][128] f32 partials (S > 1)
+    unsigned *tickets;              // [n_tiles], zero between launches
+    GemmEpilogue epi;
+};
+
+template <int MP>
+__device__ __forceinline__ void sk_epilogue_store(const SkParams &p, int n, int m, float v, int lane) {
+    const GemmEpilogue &e = p.epi;
+    if (e.mode == QASR_GEMM_SWIGLU_SPLIT) { // rows (2j, 2j+1) of W = (gate_j, up_j): neighbouring lanes
+        const float up = __shfl_down_sync(0xffffffffu, v, 1);
+        if (!(lane & 1) && n + 1 < p.N && m < p.M) {
+            const float r = silu(v) * up;
+            __nv_bfloat16 hi, lo;
+            split_bf16(r, hi, lo);
+            e.out_hi[(size_t)m * e.ldo + (n >> 1)] = __bfloat16_as_ushort(hi);
+            if (e.out_lo) e.out_lo[(size_t)m * e.ldo + (n >> 1)] = __bfloat16_as_ushort(lo);
+        }
+        return;
+    }
+    if (n >= p.N || m >= p.M) return;
+    if (e.bias) v += e.bias[n];
+    if (e.mode == QASR_GEMM_F32) {
+        e.out_f32[(size_t)m * e.ldo + n] = v;
+    } else if (e.mode == QASR_GEMM_RESIDUAL) {
+        e.out_f32[(size_t)m * e.ldo + n] += v;
+    } else { // GELU_SPLIT
+        v = gelu_tanh(v);
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        e.out_hi[(size_t)m * e.ldo + n] = __bfloat16_as_ushort(hi);
+        if (e.out_lo) e.out_lo[(size_t)m * e.ldo + n] = __bfloat16_as_ushort(lo);
+    }
+}
+
+#define SK_THREADS 224 /* warps: 0 W producer, 1 MMA, 2-5 epilogue, 6 activation producer */
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// tmA: 3-D map {K, M, planes} with box {64, MP, nsplit}: ONE TMA op brings the hi and lo planes of a
+// k-block (a TMA op costs ~0.1 us of issue time on the issuing thread, so ops are kept few and the
+// weight and activation streams are issued by different warps).
+template <int MP, int STAGES>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const SkParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr uint32_t W_BYTES = 128 * TC_BK * 2;  // 16 KB
+    constexpr uint32_t A_BYTES = MP * TC_BK * 2;   // MP x 128 B
+    constexpr uint32_t STAGE_BYTES = W_BYTES + 2 * A_BYTES;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full_bar = empty_bar + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+    int *s_last = reinterpret_cast<int *>(tmem_slot + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, split = blockIdx.y, n0 = tile * 128;
+    const int total_kb = (p.K + TC_BK - 1) / TC_BK;
+    const int kb0 = split * p.kb_per, kb1 = min(total_kb, kb0 + p.kb_per), num_kb = kb1 - kb0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)MP) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx = W_BYTES + (p.nsplit == 2 ? 2 * A_BYTES : A_BYTES);
+            for (int i = 0; i < num_kb; i++) {
+                const int s = i % STAGES;
+                mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
+                uint8_t *st = smem + s * STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], tx); // covers both producers' bytes; the phase cannot complete before this arrive
+                tma_load_2d(st, &tmW, &full_bar[s], (kb0 + i) * TC_BK, n0);
+            }
+        }
+    } else if (warp == 6) {
+        if (lane == 0) { // activation producer
+            for (int i = 0; i < num_kb; i++) {
+                const int s = i % STAGES;
+                mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
+                tma_load_3d(smem + s * STAGE_BYTES + W_BYTES, &tmA, &full_bar[s], (kb0 + i) * TC_BK, 0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // M (instruction) = 128 weight rows, N (instruction) = MP activation rows
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            for (int i = 0; i < num_kb; i++) {
+                const int s = i % STAGES;
+                mbar_wait(&full_bar[s], (i / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t w_addr = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t dw = make_sw128_desc(w_addr);
+                const uint64_t dah = make_sw128_desc(w_addr + W_BYTES);
+                const uint64_t dal = make_sw128_desc(w_addr + W_BYTES + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; k++)
+                    tc_mma_bf16(tmem_base, dw + (uint64_t)(k * 2), dah + (uint64_t)(k * 2), idesc, (i | k) != 0);
+                if (p.nsplit == 2) {
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++)
+                        tc_mma_bf16(tmem_base, dw + (uint64_t)(k * 2), dal + (uint64_t)(k * 2), idesc, 1u);
+                }
+                tc_commit(&empty_bar[s]);
+            }
+            tc_commit(tmem_full_bar);
+        }
+    } else if (warp < 6) {
+        // ===== epilogue warps 2..5: thread <-> weight row n, loops over the activation rows m
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3, nl = q * 32 + lane, n = n0 + nl;
+        float *wsp = p.ws + ((size_t)(tile * p.S + split) * MP) * 128 + nl;
+#pragma unroll 1
+        for (int c0 = 0; c0 < MP; c0 += 32) {
+            if (c0 >= p.M) break; // columns beyond M hold products with zero-filled rows
+            uint32_t r[32];
+            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            if (p.S == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) sk_epilogue_store<MP>(p, n, c0 + j, __uint_as_float(r[j]), lane);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j++)
+                    if (c0 + j < p.M) wsp[(size_t)(c0 + j) * 128] = __uint_as_float(r[j]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)MP) : "memory");
+    }
+    if (p.S == 1) return;
+    // ---- split-K: the last CTA to finish this tile reduces the partials in fixed split order
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(&p.tickets[tile], 1u);
+        *s_last = (old == (unsigned)(p.S - 1));
+        if (*s_last) p.tickets[tile] = 0; // ready for the next launch
+    }
+    __syncthreads();
+    if (!*s_last) return;
+    __threadfence();
+    const float *wst = p.ws + ((size_t)tile * p.S * MP) * 128;
+    for (int idx = threadIdx.x; idx < p.M * 32; idx += SK_THREADS) { // idx = m*32 + float4 column: coalesced along n
+        const int m = idx >> 5, c4 = idx & 31;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int sp = 0; sp < p.S; sp++) {
+            const float4 t = __ldcg(reinterpret_cast<const float4 *>(wst + ((size_t)sp * MP + m) * 128) + c4);
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        const int nb = n0 + c4 * 4;
+        if (p.epi.mode == QASR_GEMM_SWIGLU_SPLIT) { // (gate, up) pairs sit inside the float4
+            const GemmEpilogue &e = p.epi;
+            const float r[2] = {silu(v.x) * v.y, silu(v.z) * v.w};
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+                if (nb + 2 * j + 1 < p.N) {
+                    __nv_bfloat16 hi, lo;
+                    split_bf16(r[j], hi, lo);
+                    e.out_hi[(size_t)m * e.ldo + ((nb >> 1) + j)] = __bfloat16_as_ushort(hi);
+                    if (e.out_lo) e.out_lo[(size_t)m * e.ldo + ((nb >> 1) + j)] = __bfloat16_as_ushort(lo);
+                }
+        } else {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) sk_epilogue_store<MP>(p, nb + j, m, vv[j], 0);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -265,6 +467,14 @@ template <int BN>
 static constexpr size_t tc_smem_bytes() {
     return (size_t)TC_STAGES * (2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 256 + 1024;
 }
+
+template <int MP, int STAGES>
+static constexpr size_t sk_smem_bytes() {
+    return (size_t)STAGES * (128 * TC_BK * 2 + 2 * MP * TC_BK * 2) + 256 + 1024;
+}
+
+struct SkScratch { float *ws = nullptr; size_t ws_bytes = 0; unsigned *tickets = nullptr; };
+static SkScratch g_sk[16]; // per device
 
 int gemm_tc_init(void) {
     if (g_encode) return 0;
@@ -279,6 +489,12 @@ int gemm_tc_init(void) {
     e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tc_skinny_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk_smem_bytes<64, 6>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tc_skinny_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk_smem_bytes<128, 4>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tc_skinny_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk_smem_bytes<256, 2>());
     if (e != cudaSuccess) {
         snprintf(g_tc_err, sizeof g_tc_err, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(e));
         g_encode = nullptr;
@@ -304,6 +520,25 @@ static int make_map(CUtensorMap *m, const bf16_t *ptr, int rows, int K, int box_
 }
 
 static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+// Allocate the per-device split-K scratch up front so launches never allocate or synchronise
+// (they may run inside a CUDA-graph stream capture).
+int gemm_tc_prepare(void) {
+    if (gemm_tc_init() != 0) return -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SkScratch &sc = g_sk[dev & 15];
+    if (sc.tickets) return 0;
+    const size_t ws_bytes = (size_t)32 << 20;
+    if (cudaMalloc(&sc.tickets, 4096 * sizeof(unsigned)) != cudaSuccess || cudaMemset(sc.tickets, 0, 4096 * sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc(&sc.ws, ws_bytes) != cudaSuccess) {
+        snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: scratch allocation failed");
+        cudaGetLastError();
+        return -1;
+    }
+    sc.ws_bytes = ws_bytes;
+    return 0;
+}
+
 int tc_encode_map(void *out_map64, const bf16_t *ptr, int rows, int K, int box_cols, int box_rows) {
     if (gemm_tc_init() != 0) return -1;
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -327,6 +562,50 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
     if ((K & 7) || ((uintptr_t)A_hi & 15) || ((uintptr_t)W & 15) || (A_lo && ((uintptr_t)A_lo & 15))) {
         snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: K must be a multiple of 8 and operands 16-byte aligned (K=%d)", K);
         return -1;
+    }
+    if (M <= 256) { // weight-streaming regime: skinny-M kernel with split-K over ~148 CTAs
+        int dev = 0;
+        cudaGetDevice(&dev);
+        SkScratch &sc = g_sk[dev & 15];
+        const int MP = M <= 64 ? 64 : (M <= 128 ? 128 : 256);
+        const int n_tiles = (N + 127) / 128, total_kb = (K + TC_BK - 1) / TC_BK;
+        int S = (32 + n_tiles - 1) / n_tiles; // a lone CTA ingests ~150 GB/s: 32 CTAs already saturate HBM
+        if (S > total_kb / 4) S = total_kb / 4;
+        if (S < 1) S = 1;
+        const int kb_per = (total_kb + S - 1) / S;
+        S = (total_kb + kb_per - 1) / kb_per;
+        const size_t need = (size_t)n_tiles * S * MP * 128 * sizeof(float);
+        if (!sc.tickets || (S > 1 && need > sc.ws_bytes)) {
+            snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: split-K scratch missing or too small (%zu B needed): call gemm_tc_prepare()", need);
+            return -1;
+        }
+        if (n_tiles > 4096) { snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: N too large for the skinny path"); return -1; }
+        SkParams sp;
+        sp.M = M; sp.N = N; sp.K = K; sp.nsplit = A_lo ? 2 : 1; sp.S = S; sp.kb_per = kb_per;
+        sp.ws = sc.ws; sp.tickets = sc.tickets; sp.epi = epi;
+        if (A_lo && A_lo != A_hi + (size_t)M * K) {
+            snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: lo plane must follow the hi plane (lo = hi + M*K)");
+            return -1;
+        }
+        CUtensorMap mw, ma;
+        if (make_map(&mw, W, N, K, 128) != 0) return -1;
+        { // 3-D {K, M, planes}: box {64, MP, planes}
+            cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)M, (cuuint64_t)(A_lo ? 2 : 1)};
+            cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)M * K * 2};
+            cuuint32_t box[3] = {TC_BK, (cuuint32_t)MP, (cuuint32_t)(A_lo ? 2 : 1)};
+            cuuint32_t estr[3] = {1, 1, 1};
+            CUresult r = g_encode(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void *)A_hi, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(3d) failed (%d) M=%d K=%d", (int)r, M, K); return -1; }
+        }
+        dim3 grid(n_tiles, S);
+        if (MP == 64) gemm_tc_skinny_kernel<64, 6><<<grid, SK_THREADS, sk_smem_bytes<64, 6>(), s>>>(mw, ma, sp);
+        else if (MP == 128) gemm_tc_skinny_kernel<128, 4><<<grid, SK_THREADS, sk_smem_bytes<128, 4>(), s>>>(mw, ma, sp);
+        else gemm_tc_skinny_kernel<256, 2><<<grid, SK_THREADS, sk_smem_bytes<256, 2>(), s>>>(mw, ma, sp);
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc skinny launch: %s", cudaGetErrorString(le)); return -1; }
+        return 0;
     }
     // Narrow tiles when the 128-wide grid would leave most of the 148 SMs idle.
     const int tiles128 = ((M + TC_BM - 1) / TC_BM) * ((N + 127) / 128);

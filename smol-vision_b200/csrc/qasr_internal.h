@@ -114,6 +114,7 @@ void launch_mel(cudaStream_t s, const float *samples, int n, int frames, const f
 // ---- tcgen05 GEMM (qasr_gemm_tc.cu)
 // C[M,N] = A[M,K] * W[N,K]^T with A given as bf16 hi (+ optional lo) planes, W bf16, f32 accumulate in TMEM.
 int gemm_tc_init(void); // resolves cuTensorMapEncodeTiled, sets smem attributes; 0 on success
+int gemm_tc_prepare(void); // per-device split-K scratch (call once per device, outside stream capture)
 int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M, int K, const bf16_t *W, int N,
                    const GemmEpilogue &epi);
 const char *gemm_tc_error(void);

@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             is.wp++;
             if (is.wp == n_wp) { is.wp = 0; is.step++; }
             if (is.step < p.n_steps) {
+                // the TMA unit has to fetch a descriptor before its first copy: warm the NEXT phase's map now
+                if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(p.maps + (is.wp + 1 == n_wp ? 0 : is.wp + 1)) : "memory");
                 is.g = phase_geom(p, is.wp, b, G);
                 is.nsl = warp_nsl(is.g, warp);
                 is.grp = is.g.g0 + warp_sub(is.g, warp);
@@ -216,6 +218,10 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaPa
             }
         }
     };
+    if (lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(p.maps) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(p.maps + 1) : "memory");
+    }
     stream_seek();
     unsigned issued = 0, consumed = 0;
     auto top_up = [&]() {

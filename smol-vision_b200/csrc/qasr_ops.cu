@@ -278,3 +278,30 @@ int qasr_op_apply_rope_neox(qasr_ctx_t *c, float *x, const float *cos_vals, cons
     if (sc.ok) { launch_rope_apply(s, dx, dc, ds, seq, n_heads, head_dim); qasr_internal_count(c, 1); down(x, dx, n * 4, s); }
     return finish(c, sc, s);
 }
+
+// debug / tuning hook (not part of the public header): device-time one tensor-core GEMM shape
+extern "C" int qasr_debug_gemm_bench(qasr_ctx_t *c, int M, int K, int N, int iters, int mode, double *out_us) {
+    OP_BEGIN(c);
+    const size_t na = (size_t)M * K;
+    bf16_t *a = sc.alloc<bf16_t>(2 * na), *w = sc.alloc<bf16_t>((size_t)N * K);
+    float *y = sc.alloc<float>((size_t)M * N);
+    bf16_t *oh = sc.alloc<bf16_t>((size_t)2 * M * N);
+    if (!sc.ok) return finish(c, sc, s);
+    cudaMemsetAsync(a, 0, 2 * na * 2, s); cudaMemsetAsync(w, 0, (size_t)N * K * 2, s); cudaMemsetAsync(y, 0, (size_t)M * N * 4, s);
+    GemmEpilogue e;
+    e.mode = mode; e.out_f32 = y; e.out_hi = oh; e.out_lo = oh + (size_t)M * N; e.bias = nullptr; e.ldo = (mode == QASR_GEMM_SWIGLU_SPLIT) ? N / 2 : N;
+    const bool two = qasr_internal_nsplit(c) == 2;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; i++) launch_gemm_tc(s, a, two ? a + na : nullptr, M, K, w, N, e);
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < iters; i++)
+        if (launch_gemm_tc(s, a, two ? a + na : nullptr, M, K, w, N, e) != 0) return qasr_internal_err(QASR_ERR_CUDA, gemm_tc_error());
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (out_us) *out_us = 1000.0 * ms / iters;
+    return finish(c, sc, s);
+}

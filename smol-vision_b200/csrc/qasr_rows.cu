@@ -15,48 +15,81 @@ __device__ __forceinline__ void store_out(float v, size_t idx, float *of, bf16_t
     }
 }
 
+// Row norms: one 256-thread CTA per row, the row lives in registers (<= 16 values per thread, H <= 4096),
+// one block reduction per statistic.  Emits f32 and/or the bf16 hi/lo operand planes.
+#define NORM_THREADS 256
+#define NORM_MAX_PER 16
+__device__ __forceinline__ float norm_block_sum(float v, float *red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NORM_THREADS / 32; w++) t += red[w];
+    return t;
+}
+
 // ------------------------------------------------------------------ RMSNorm (rows)
-// out = x * rsqrt(mean(x^2)+eps) * w, reference qwen_asr_kernels.c:801-860. One warp per row.
-__global__ void __launch_bounds__(256)
-rmsnorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ gamma, float eps, int M, int H,
-                    float *of, bf16_t *ohi, bf16_t *olo) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= M) return;
-    const float *xr = x + (size_t)row * H;
+// out = x * rsqrt(mean(x^2)+eps) * w, reference qwen_asr_kernels.c:801-860.
+__global__ void __launch_bounds__(NORM_THREADS)
+rmsnorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ gamma, float eps, int H, float *of, bf16_t *ohi,
+                    bf16_t *olo) {
+    __shared__ float red[NORM_THREADS / 32];
+    const size_t base = (size_t)blockIdx.x * H;
+    float v[NORM_MAX_PER];
     float ss = 0.0f;
-    for (int i = lane; i < H; i += 32) { const float v = xr[i]; ss = fmaf(v, v, ss); }
-    ss = warp_sum(ss);
-    const float inv = 1.0f / sqrtf(ss / (float)H + eps);
-    for (int i = lane; i < H; i += 32) store_out(xr[i] * inv * gamma[i], (size_t)row * H + i, of, ohi, olo);
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_PER; i++) {
+        const int e = threadIdx.x + i * NORM_THREADS;
+        v[i] = e < H ? x[base + e] : 0.0f;
+        ss = fmaf(v[i], v[i], ss);
+    }
+    const float inv = 1.0f / sqrtf(norm_block_sum(ss, red) / (float)H + eps);
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_PER; i++) {
+        const int e = threadIdx.x + i * NORM_THREADS;
+        if (e < H) store_out(v[i] * inv * gamma[e], base + e, of, ohi, olo);
+    }
 }
 void launch_rmsnorm(cudaStream_t s, const float *x, const float *gamma, float eps, int M, int H, float *out_f32,
                     bf16_t *out_hi, bf16_t *out_lo) {
-    if (M > 0) rmsnorm_rows_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, gamma, eps, M, H, out_f32, out_hi, out_lo);
+    if (M > 0) rmsnorm_rows_kernel<<<M, NORM_THREADS, 0, s>>>(x, gamma, eps, H, out_f32, out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------ LayerNorm (rows)
 // (x-mean)*rsqrt(var+eps)*w+b, biased variance, reference qwen_asr_kernels.c:691-799.
-__global__ void __launch_bounds__(256)
-layernorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b, float eps,
-                      int M, int H, float *of, bf16_t *ohi, bf16_t *olo) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= M) return;
-    const float *xr = x + (size_t)row * H;
+__global__ void __launch_bounds__(NORM_THREADS)
+layernorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b, float eps, int H,
+                      float *of, bf16_t *ohi, bf16_t *olo) {
+    __shared__ float red[NORM_THREADS / 32];
+    const size_t base = (size_t)blockIdx.x * H;
+    float v[NORM_MAX_PER];
     float sum = 0.0f;
-    for (int i = lane; i < H; i += 32) sum += xr[i];
-    const float mean = warp_sum(sum) / (float)H;
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_PER; i++) {
+        const int e = threadIdx.x + i * NORM_THREADS;
+        v[i] = e < H ? x[base + e] : 0.0f;
+        sum += v[i];
+    }
+    const float mean = norm_block_sum(sum, red) / (float)H;
     float var = 0.0f;
-    for (int i = lane; i < H; i += 32) { const float d = xr[i] - mean; var = fmaf(d, d, var); }
-    var = warp_sum(var) / (float)H;
-    const float inv = 1.0f / sqrtf(var + eps);
-    for (int i = lane; i < H; i += 32) {
-        const float v = (xr[i] - mean) * inv * w[i] + b[i];
-        store_out(v, (size_t)row * H + i, of, ohi, olo);
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_PER; i++) {
+        const int e = threadIdx.x + i * NORM_THREADS;
+        const float d = e < H ? v[i] - mean : 0.0f;
+        var = fmaf(d, d, var);
+    }
+    const float inv = 1.0f / sqrtf(norm_block_sum(var, red) / (float)H + eps);
+#pragma unroll
+    for (int i = 0; i < NORM_MAX_PER; i++) {
+        const int e = threadIdx.x + i * NORM_THREADS;
+        if (e < H) store_out((v[i] - mean) * inv * w[e] + b[e], base + e, of, ohi, olo);
     }
 }
 void launch_layernorm(cudaStream_t s, const float *x, const float *w, const float *b, float eps, int M, int H,
                       float *out_f32, bf16_t *out_hi, bf16_t *out_lo) {
-    if (M > 0) layernorm_rows_kernel<<<(M + 7) / 8, 256, 0, s>>>(x, w, b, eps, M, H, out_f32, out_hi, out_lo);
+    if (M > 0) layernorm_rows_kernel<<<M, NORM_THREADS, 0, s>>>(x, w, b, eps, H, out_f32, out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------ per-head RMSNorm (in place)
@@ -129,50 +162,62 @@ __device__ __forceinline__ void soft_update(float sc, float &m, float &l, float 
 }
 
 // ------------------------------------------------------------------ causal GQA attention (prefill)
-// reference qwen_asr_kernels.c:1101-1148.  head_dim = 128.  One warp owns 2 consecutive query
-// positions x the (n_heads/n_kv_heads = 2) query heads of one kv head => 4 queries share each
-// K/V row load; lane owns dims 4l..4l+3.  Query i attends keys [0, q_offset+i].
-__global__ void __launch_bounds__(128)
+// reference qwen_asr_kernels.c:1101-1148.  head_dim = 128.  CTA = (kv head, 16 query positions), 8 warps;
+// a warp owns 2 consecutive positions x the 2 query heads of the kv head => 4 queries share every K/V
+// row; lane owns dims 4l..4l+3.  K/V rows are staged through shared memory in 32-key tiles (coalesced
+// loads, then ~30-cycle LDS instead of an L2 round trip per key).  Query i attends keys [0, q_offset+i].
+#define ATT_KT 32
+__global__ void __launch_bounds__(256)
 attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, const float *__restrict__ vc,
                     int q_offset, int P, int seq_k, int n_heads, int n_kv_heads, float scale, float *of, bf16_t *ohi,
                     bf16_t *olo) {
+    __shared__ __align__(16) float ks[ATT_KT][128], vs[ATT_KT][128];
     const int kvh = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int i0 = (blockIdx.y * 4 + warp) * 2;
-    if (i0 >= P) return;
+    const int ib = blockIdx.y * 16, i0 = ib + warp * 2;
     const int per = n_heads / n_kv_heads; // 2
     const int qld = n_heads * 128, kld = n_kv_heads * 128;
-    const bool has2 = (i0 + 1 < P);
+    const bool act0 = i0 < P, act1 = i0 + 1 < P;
     float qv[4][4], acc[4][4], m[4], l[4];
 #pragma unroll
     for (int a = 0; a < 4; a++) {
         const int qi = i0 + (a >> 1), hh = kvh * per + (a & 1);
-        const float4 t4 = (a < 2 || has2) ? *reinterpret_cast<const float4 *>(q + (size_t)qi * qld + hh * 128 + lane * 4)
-                                          : make_float4(0, 0, 0, 0);
+        const float4 t4 = ((a < 2) ? act0 : act1) ? *reinterpret_cast<const float4 *>(q + (size_t)qi * qld + hh * 128 + lane * 4)
+                                                 : make_float4(0, 0, 0, 0);
         qv[a][0] = t4.x; qv[a][1] = t4.y; qv[a][2] = t4.z; qv[a][3] = t4.w;
         acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.0f;
         m[a] = -1e30f; l[a] = 0.0f;
     }
-    int kend0 = q_offset + i0 + 1, kend1 = q_offset + i0 + 2;
-    if (kend0 > seq_k) kend0 = seq_k;
-    if (kend1 > seq_k) kend1 = seq_k;
-    const int kmax = has2 ? kend1 : kend0;
-    for (int j = 0; j < kmax; j++) {
-        const float4 k4 = *reinterpret_cast<const float4 *>(kc + (size_t)j * kld + kvh * 128 + lane * 4);
-        const float4 v4 = *reinterpret_cast<const float4 *>(vc + (size_t)j * kld + kvh * 128 + lane * 4);
-        const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-        float sc[4];
+    int kend0 = min(q_offset + i0 + 1, seq_k), kend1 = min(q_offset + i0 + 2, seq_k);
+    if (!act0) kend0 = 0;
+    if (!act1) kend1 = 0;
+    const int kmax_cta = min(q_offset + min(ib + 16, P), seq_k); // keys needed by the last position of the CTA
+    for (int t0 = 0; t0 < kmax_cta; t0 += ATT_KT) {
+        const int nk = min(ATT_KT, kmax_cta - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nk * 32; e += 256) { // 32 float4 per key row
+            const int kk = e >> 5, c4 = e & 31;
+            reinterpret_cast<float4 *>(ks[kk])[c4] = *reinterpret_cast<const float4 *>(kc + (size_t)(t0 + kk) * kld + kvh * 128 + c4 * 4);
+            reinterpret_cast<float4 *>(vs[kk])[c4] = *reinterpret_cast<const float4 *>(vc + (size_t)(t0 + kk) * kld + kvh * 128 + c4 * 4);
+        }
+        __syncthreads();
+        const int jend = min(nk, max(kend0, kend1) - t0);
+        for (int jj = 0; jj < jend; jj++) {
+            const int j = t0 + jj;
+            const float4 k4 = reinterpret_cast<const float4 *>(ks[jj])[lane];
+            const float4 v4 = reinterpret_cast<const float4 *>(vs[jj])[lane];
+            const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+            float sc[4];
 #pragma unroll
-        for (int a = 0; a < 4; a++)
-            sc[a] = warp_sum(qv[a][0] * k4.x + qv[a][1] * k4.y + qv[a][2] * k4.z + qv[a][3] * k4.w) * scale;
+            for (int a = 0; a < 4; a++)
+                sc[a] = warp_sum(qv[a][0] * k4.x + qv[a][1] * k4.y + qv[a][2] * k4.z + qv[a][3] * k4.w) * scale;
 #pragma unroll
-        for (int a = 0; a < 4; a++) {
-            const int ke = (a < 2) ? kend0 : kend1;
-            if (j < ke && (a < 2 || has2)) soft_update<4>(sc[a], m[a], l[a], acc[a], vv);
+            for (int a = 0; a < 4; a++)
+                if (j < ((a < 2) ? kend0 : kend1)) soft_update<4>(sc[a], m[a], l[a], acc[a], vv);
         }
     }
 #pragma unroll
     for (int a = 0; a < 4; a++) {
-        if (a >= 2 && !has2) break;
+        if (!((a < 2) ? act0 : act1)) continue;
         const int qi = i0 + (a >> 1), hh = kvh * per + (a & 1);
         const float inv = l[a] > 0.0f ? 1.0f / l[a] : 0.0f;
         const size_t base = (size_t)qi * qld + hh * 128 + lane * 4;
@@ -183,41 +228,53 @@ attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, c
 void launch_attn_prefill(cudaStream_t s, const float *q, const float *kc, const float *vc, int q_offset, int P, int seq_k,
                          int n_heads, int n_kv_heads, float scale, float *out_f32, bf16_t *out_hi, bf16_t *out_lo) {
     if (P <= 0) return;
-    dim3 grid(n_kv_heads, (P + 7) / 8);
-    attn_prefill_kernel<<<grid, 128, 0, s>>>(q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, out_f32, out_hi, out_lo);
+    dim3 grid(n_kv_heads, (P + 15) / 16);
+    attn_prefill_kernel<<<grid, 256, 0, s>>>(q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, out_f32, out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------ windowed bidirectional attention (encoder)
-// reference qwen_asr_kernels.c:1054-1099.  head_dim = 64: lane owns dims 2l,2l+1; one warp owns
-// 4 consecutive queries of one head inside one window; all keys of the window are visited.
-// q/k/v may be column slices of one [T, ld] buffer (fused QKV GEMM output).
-__global__ void __launch_bounds__(128)
+// reference qwen_asr_kernels.c:1054-1099.  head_dim = 64: lane owns dims 2l,2l+1; CTA = (head, window,
+// 32 queries), 8 warps x 4 consecutive queries; the window's K/V rows of the head are staged through
+// shared memory in 32-key tiles.  q/k/v may be column slices of one [T, ld] buffer (fused QKV output).
+__global__ void __launch_bounds__(256)
 attn_windowed_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v, int ld,
                      const int *__restrict__ window_starts, float scale, int out_ld, float *of, bf16_t *ohi,
                      bf16_t *olo) {
+    __shared__ __align__(16) float ks[ATT_KT][64], vs[ATT_KT][64];
     const int h = blockIdx.x, w = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ws = window_starts[w], we = window_starts[w + 1];
-    const int i0 = ws + (blockIdx.z * 4 + warp) * 4;
-    if (i0 >= we) return;
+    const int ib = ws + blockIdx.z * 32;
+    if (ib >= we) return; // whole CTA
+    const int i0 = ib + warp * 4;
     float qv[4][2], acc[4][2], m[4], l[4];
 #pragma unroll
     for (int a = 0; a < 4; a++) {
         const int qi = i0 + a;
-        const float2 t2 = qi < we ? *reinterpret_cast<const float2 *>(q + (size_t)qi * ld + h * 64 + lane * 2)
-                                  : make_float2(0, 0);
+        const float2 t2 = qi < we ? *reinterpret_cast<const float2 *>(q + (size_t)qi * ld + h * 64 + lane * 2) : make_float2(0, 0);
         qv[a][0] = t2.x; qv[a][1] = t2.y;
         acc[a][0] = acc[a][1] = 0.0f;
         m[a] = -1e30f; l[a] = 0.0f;
     }
-    for (int j = ws; j < we; j++) {
-        const float2 k2 = *reinterpret_cast<const float2 *>(k + (size_t)j * ld + h * 64 + lane * 2);
-        const float2 v2 = *reinterpret_cast<const float2 *>(v + (size_t)j * ld + h * 64 + lane * 2);
-        const float vv[2] = {v2.x, v2.y};
-#pragma unroll
-        for (int a = 0; a < 4; a++) {
-            const float sc = warp_sum(qv[a][0] * k2.x + qv[a][1] * k2.y) * scale;
-            soft_update<2>(sc, m[a], l[a], acc[a], vv);
+    for (int t0 = ws; t0 < we; t0 += ATT_KT) {
+        const int nk = min(ATT_KT, we - t0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < nk * 16; e += 256) { // 16 float4 per key row
+            const int kk = e >> 4, c4 = e & 15;
+            reinterpret_cast<float4 *>(ks[kk])[c4] = *reinterpret_cast<const float4 *>(k + (size_t)(t0 + kk) * ld + h * 64 + c4 * 4);
+            reinterpret_cast<float4 *>(vs[kk])[c4] = *reinterpret_cast<const float4 *>(v + (size_t)(t0 + kk) * ld + h * 64 + c4 * 4);
         }
+        __syncthreads();
+        if (i0 < we)
+            for (int jj = 0; jj < nk; jj++) {
+                const float2 k2 = reinterpret_cast<const float2 *>(ks[jj])[lane];
+                const float2 v2 = reinterpret_cast<const float2 *>(vs[jj])[lane];
+                const float vv[2] = {v2.x, v2.y};
+                float sc[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) sc[a] = warp_sum(qv[a][0] * k2.x + qv[a][1] * k2.y) * scale;
+#pragma unroll
+                for (int a = 0; a < 4; a++) soft_update<2>(sc[a], m[a], l[a], acc[a], vv);
+            }
     }
 #pragma unroll
     for (int a = 0; a < 4; a++) {
@@ -233,8 +290,8 @@ void launch_attn_windowed(cudaStream_t s, const float *q, const float *k, const 
                           const int *d_window_starts, int n_windows, int max_window, float scale, int out_ld,
                           float *out_f32, bf16_t *out_hi, bf16_t *out_lo) {
     if (n_windows <= 0) return;
-    dim3 grid(n_heads, n_windows, (max_window + 15) / 16);
-    attn_windowed_kernel<<<grid, 128, 0, s>>>(q, k, v, ld, d_window_starts, scale, out_ld, out_f32, out_hi, out_lo);
+    dim3 grid(n_heads, n_windows, (max_window + 31) / 32);
+    attn_windowed_kernel<<<grid, 256, 0, s>>>(q, k, v, ld, d_window_starts, scale, out_ld, out_f32, out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------ small element-wise kernels

@@ -1,0 +1,18 @@
+"""Device-time the tensor-core GEMM at the encoder / prefill shapes (debug hook)."""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge
+pkg = ge.load_package()
+eng = pkg.QasrCuda(0)
+f = eng.lib.qasr_debug_gemm_bench
+f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+shapes = [("pre.qkv", 61, 2048, 4096), ("pre.wo", 61, 2048, 2048), ("pre.gu", 61, 2048, 12288), ("pre.down", 61, 6144, 2048),
+          ("enc.qkv", 47, 1024, 3072), ("enc.wo", 47, 1024, 1024), ("enc.fc1", 47, 1024, 4096), ("enc.fc2", 47, 4096, 1024),
+          ("conv2", 1456, 4320, 480), ("conv3", 384, 4320, 480), ("convout", 47, 7680, 1024),
+          ("jfk.qkv", 157, 1024, 4096), ("30s.gu", 404, 2048, 12288)]
+for name, M, K, N in shapes:
+    us = C.c_double(0)
+    rc = f(eng.ctx, M, K, N, 20, 0, C.byref(us))
+    mb = 2.0 * N * K / 1e6
+    print(f"{name:9s} M={M:4d} K={K:5d} N={N:5d}  {us.value:8.1f} us   weights {mb:6.1f} MB -> {mb / us.value * 1e3 / 1e3:6.2f} TB/s   {2.0*M*N*K*2/us.value/1e6:7.1f} TFLOP/s(hi+lo)" if rc == 0 else f"{name} failed {eng._err()}")
