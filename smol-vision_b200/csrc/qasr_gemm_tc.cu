@@ -429,14 +429,28 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     if (!*s_last) return;
     __threadfence();
     const float *wst = p.ws + ((size_t)tile * p.S * MP) * 128;
-    for (int idx = threadIdx.x; idx < p.M * 32; idx += SK_THREADS) { // idx = m*32 + float4 column: coalesced along n
-        const int m = idx >> 5, c4 = idx & 31;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+    // 4 output float4s per thread per pass, all S x 4 loads issued before the first add (one L2 round trip per pass)
+    for (int base = 0; base < p.M * 32; base += SK_THREADS * 4) {
+        float4 acc4[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int sp = 0; sp < p.S; sp++) {
-            const float4 t = __ldcg(reinterpret_cast<const float4 *>(wst + ((size_t)sp * MP + m) * 128) + c4);
-            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+            float4 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int idx = base + u * SK_THREADS + threadIdx.x;
+                t[u] = idx < p.M * 32 ? __ldcg(reinterpret_cast<const float4 *>(wst + ((size_t)sp * MP + (idx >> 5)) * 128) + (idx & 31))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) { acc4[u].x += t[u].x; acc4[u].y += t[u].y; acc4[u].z += t[u].z; acc4[u].w += t[u].w; }
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+        const int idx = base + u * SK_THREADS + threadIdx.x;
+        if (idx >= p.M * 32) continue;
+        const int m = idx >> 5, c4 = idx & 31;
+        const float4 v = acc4[u];
         const int nb = n0 + c4 * 4;
         if (p.epi.mode == QASR_GEMM_SWIGLU_SPLIT) { // (gate, up) pairs sit inside the float4
             const GemmEpilogue &e = p.epi;
@@ -453,6 +467,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; j++) sk_epilogue_store<MP>(p, nb + j, m, vv[j], 0);
+        }
         }
     }
 }

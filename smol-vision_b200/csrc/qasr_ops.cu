@@ -279,29 +279,43 @@ int qasr_op_apply_rope_neox(qasr_ctx_t *c, float *x, const float *cos_vals, cons
     return finish(c, sc, s);
 }
 
-// debug / tuning hook (not part of the public header): device-time one tensor-core GEMM shape
+// debug / tuning hook (not part of the public header): device-time one tensor-core GEMM shape.
+// `iters` launches over NW rotating weight matrices (so weights come from HBM, not L2) are captured
+// into one CUDA graph and the graph launch is timed: no host launch overhead in the number.
 extern "C" int qasr_debug_gemm_bench(qasr_ctx_t *c, int M, int K, int N, int iters, int mode, double *out_us) {
     OP_BEGIN(c);
-    const size_t na = (size_t)M * K;
-    bf16_t *a = sc.alloc<bf16_t>(2 * na), *w = sc.alloc<bf16_t>((size_t)N * K);
+    const int NW = 8;
+    const size_t na = (size_t)M * K, nw = (size_t)N * K;
+    bf16_t *a = sc.alloc<bf16_t>(2 * na), *w = sc.alloc<bf16_t>(nw * NW);
     float *y = sc.alloc<float>((size_t)M * N);
     bf16_t *oh = sc.alloc<bf16_t>((size_t)2 * M * N);
     if (!sc.ok) return finish(c, sc, s);
-    cudaMemsetAsync(a, 0, 2 * na * 2, s); cudaMemsetAsync(w, 0, (size_t)N * K * 2, s); cudaMemsetAsync(y, 0, (size_t)M * N * 4, s);
+    cudaMemsetAsync(a, 0, 2 * na * 2, s); cudaMemsetAsync(w, 0, nw * NW * 2, s); cudaMemsetAsync(y, 0, (size_t)M * N * 4, s);
     GemmEpilogue e;
     e.mode = mode; e.out_f32 = y; e.out_hi = oh; e.out_lo = oh + (size_t)M * N; e.bias = nullptr; e.ldo = (mode == QASR_GEMM_SWIGLU_SPLIT) ? N / 2 : N;
     const bool two = qasr_internal_nsplit(c) == 2;
+    for (int i = 0; i < 2; i++) launch_gemm_tc(s, a, two ? a + na : nullptr, M, K, w, N, e);
+    cudaStreamSynchronize(s);
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+    int rc = 0;
+    for (int i = 0; i < iters && rc == 0; i++) rc = launch_gemm_tc(s, a, two ? a + na : nullptr, M, K, w + (size_t)(i % NW) * nw, N, e);
+    cudaStreamEndCapture(s, &graph);
+    if (rc != 0 || !graph) return qasr_internal_err(QASR_ERR_CUDA, gemm_tc_error());
+    cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphLaunch(exec, s);
+    cudaStreamSynchronize(s);
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    for (int i = 0; i < 3; i++) launch_gemm_tc(s, a, two ? a + na : nullptr, M, K, w, N, e);
     cudaEventRecord(e0, s);
-    for (int i = 0; i < iters; i++)
-        if (launch_gemm_tc(s, a, two ? a + na : nullptr, M, K, w, N, e) != 0) return qasr_internal_err(QASR_ERR_CUDA, gemm_tc_error());
+    cudaGraphLaunch(exec, s);
     cudaEventRecord(e1, s);
     cudaEventSynchronize(e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
     if (out_us) *out_us = 1000.0 * ms / iters;
     return finish(c, sc, s);
 }

@@ -13,6 +13,6 @@ shapes = [("pre.qkv", 61, 2048, 4096), ("pre.wo", 61, 2048, 2048), ("pre.gu", 61
           ("jfk.qkv", 157, 1024, 4096), ("30s.gu", 404, 2048, 12288)]
 for name, M, K, N in shapes:
     us = C.c_double(0)
-    rc = f(eng.ctx, M, K, N, 20, 0, C.byref(us))
+    rc = f(eng.ctx, M, K, N, 64, 0, C.byref(us))
     mb = 2.0 * N * K / 1e6
     print(f"{name:9s} M={M:4d} K={K:5d} N={N:5d}  {us.value:8.1f} us   weights {mb:6.1f} MB -> {mb / us.value * 1e3 / 1e3:6.2f} TB/s   {2.0*M*N*K*2/us.value/1e6:7.1f} TFLOP/s(hi+lo)" if rc == 0 else f"{name} failed {eng._err()}")
