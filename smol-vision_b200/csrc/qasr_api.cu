@@ -112,6 +112,11 @@ struct qasr_ctx {
     int graph_nodes = 0;
     bool use_graph = true;
     bool use_mega = true; // persistent cooperative decode kernel (QASR_DECODE=graph selects per-phase kernels)
+    bool use_stream = true; // qasr_stream.cu (default); QASR_DECODE=mega2 selects the round-2 TMA-box kernel
+    uint8_t *sk_image = nullptr;           // decode weight image (pre-tiled, per-warp streams)
+    unsigned long long *sk_cta_off = nullptr;
+    unsigned long long *ll_qkv = nullptr, *ll_att = nullptr, *ll_xwo = nullptr, *ll_act = nullptr, *ll_xdn = nullptr, *ll_head = nullptr;
+    unsigned sk_tag = 1;                   // next free exchange tag
     float *head_val = nullptr;
     int *head_idx = nullptr;
     unsigned *grid_bar = nullptr;
@@ -165,8 +170,9 @@ qasr_ctx_t *qasr_cuda_init(int device) {
     c->use_graph = !(ng && ng[0] == '1');
     const char *dm = getenv("QASR_DECODE");
     c->use_mega = !(dm && strcmp(dm, "graph") == 0);
-    if (c->use_mega && mega_init() != 0) {
-        set_err(QASR_ERR_CUDA, "%s", mega_error());
+    c->use_stream = c->use_mega && !(dm && strcmp(dm, "mega2") == 0);
+    if (c->use_mega && (c->use_stream ? stream_init() : mega_init()) != 0) {
+        set_err(QASR_ERR_CUDA, "%s", c->use_stream ? stream_error() : mega_error());
         cudaStreamDestroy(c->stream);
         delete c;
         return nullptr;
@@ -546,6 +552,28 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
         if (!c->mega_maps) return set_err(QASR_ERR_NOMEM, "tensor map allocation failed");
         CK(cudaMemcpy(c->mega_maps, maps.data(), maps.size(), cudaMemcpyHostToDevice));
     } // count and generation live in separate 128-byte lines
+    if (c->use_stream) { // decode weight image: every decoder matrix + the tied lm_head re-tiled into per-warp streams
+        const int G = stream_grid();
+        std::vector<unsigned long long> off((size_t)G + 1);
+        const size_t image_bytes = stream_image_layout(c->dec_layers, H, I, c->V, off.data());
+        if (!image_bytes) return set_err(QASR_ERR_CUDA, "%s", stream_error());
+        c->sk_image = (uint8_t *)dev_alloc(c, image_bytes);
+        c->sk_cta_off = (unsigned long long *)dalloc(off.size() * 8);
+        if (!c->sk_image || !c->sk_cta_off) return set_err(QASR_ERR_NOMEM, "decode weight image (%zu bytes)", image_bytes);
+        CK(cudaMemcpy(c->sk_cta_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice));
+        std::vector<const bf16_t *> mats;
+        for (int l = 0; l < c->dec_layers; l++) {
+            const DecLayerW &L = c->dec[l];
+            mats.push_back(L.wqkv); mats.push_back(L.wo); mats.push_back(L.wgu); mats.push_back(L.wdown);
+        }
+        if (stream_build_image(c->stream, c->dec_layers, H, I, c->V, mats.data(), c->emb, c->sk_cta_off, c->sk_image) != 0)
+            return set_err(QASR_ERR_CUDA, "%s", stream_error());
+        CK(cudaStreamSynchronize(c->stream));
+        c->ll_qkv = (unsigned long long *)dalloc(4096 * 8); c->ll_att = (unsigned long long *)dalloc((size_t)QASR_STREAM_ATT_WORDS * 8);
+        c->ll_xwo = (unsigned long long *)dalloc((size_t)H * 8); c->ll_act = (unsigned long long *)dalloc((size_t)I * 8);
+        c->ll_xdn = (unsigned long long *)dalloc((size_t)H * 8); c->ll_head = (unsigned long long *)dalloc((size_t)2 * 1024 * 8);
+        if (!c->ll_head) return set_err(QASR_ERR_NOMEM, "exchange buffers");
+    }
     if (getenv("QASR_MEGA_PROF")) c->mega_prof = (long long *)dalloc(3 * 4096 * 8);
     if (!c->x || !c->logits || !c->d_gmax) return set_err(QASR_ERR_NOMEM, "state allocation failed");
     CK(cudaHostAlloc((void **)&c->h_tokens, (size_t)c->max_steps * 4, cudaHostAllocMapped));
@@ -887,7 +915,36 @@ static int ensure_graph(qasr_ctx_t *c) {
 
 // Enqueue n greedy steps (each consumes c->x, leaves the next embedding in c->x).
 static int enqueue_steps(qasr_ctx_t *c, int n) {
-    if (c->use_mega) { // one persistent cooperative launch runs all n steps (stops itself after an EOS token)
+    if (c->use_stream) { // one persistent cooperative launch runs all n steps (stops itself after an EOS token)
+        StreamParams p;
+        p.image = c->sk_image; p.cta_off = c->sk_cta_off;
+        p.n_layers = c->dec_layers; p.H = c->H; p.I = c->I; p.V = c->V; p.n_steps = n; p.eps = 1e-6f;
+        p.emb = c->emb; p.final_norm = c->final_norm;
+        for (int l = 0; l < c->dec_layers; l++) {
+            const DecLayerW &L = c->dec[l];
+            p.in_norm[l] = L.in_norm; p.post_norm[l] = L.post_norm; p.qn[l] = L.qn; p.kn[l] = L.kn;
+        }
+        p.x_io = c->x;
+        p.kv_k = c->kv_k; p.kv_v = c->kv_v; p.kv_layer_stride = (size_t)c->kv_max * c->kv_heads * c->hd;
+        p.rope_cos = c->rope_cos; p.rope_sin = c->rope_sin;
+        p.ll_qkv = c->ll_qkv; p.ll_att = c->ll_att; p.ll_xwo = c->ll_xwo; p.ll_act = c->ll_act; p.ll_xdn = c->ll_xdn; p.ll_head = c->ll_head;
+        const unsigned span = (unsigned)n * (unsigned)(c->dec_layers + 1) + 1;
+        if (c->sk_tag > 0xF0000000u) { // tag space exhausted: clear the exchange buffers and start over
+            CK(cudaMemsetAsync(c->ll_qkv, 0, 4096 * 8, c->stream)); CK(cudaMemsetAsync(c->ll_att, 0, (size_t)QASR_STREAM_ATT_WORDS * 8, c->stream));
+            CK(cudaMemsetAsync(c->ll_xwo, 0, (size_t)c->H * 8, c->stream)); CK(cudaMemsetAsync(c->ll_act, 0, (size_t)c->I * 8, c->stream));
+            CK(cudaMemsetAsync(c->ll_xdn, 0, (size_t)c->H * 8, c->stream)); CK(cudaMemsetAsync(c->ll_head, 0, (size_t)2 * 1024 * 8, c->stream));
+            c->sk_tag = 1;
+        }
+        p.tag_base = c->sk_tag;
+        c->sk_tag += span;
+        p.d_pos = c->d_pos; p.d_step = c->d_step; p.d_tokens = c->d_tokens; p.h_tokens = c->dh_tokens;
+        p.prof = c->mega_prof; p.prof_cap = 4096;
+        { const char *dbg = getenv("QASR_MEGA_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+        if (launch_decode_stream(c->stream, p) != 0) return set_err(QASR_ERR_CUDA, "%s", stream_error());
+        c->launches += 1;
+        return 0;
+    }
+    if (c->use_mega) { // round-2 kernel (QASR_DECODE=mega2): 2-D TMA boxes + grid barriers
         if (c->dec_layers > 28) return set_err(QASR_ERR_ARG, "decode megakernel supports up to 28 decoder layers");
         MegaParams p;
         p.maps = (const CUtensorMap_st *)c->mega_maps;

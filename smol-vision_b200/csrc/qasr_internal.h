@@ -69,6 +69,36 @@ int mega_init(void);
 int launch_decode_mega(cudaStream_t s, const MegaParams &p);
 const char *mega_error(void);
 
+// ---- streaming decode kernel (qasr_stream.cu): pre-tiled weight image + flag-in-data exchanges
+struct StreamParams {
+    const uint8_t *image;                  // decode weight image (units of 16x64 bf16 in A-fragment order, per-warp streams)
+    const unsigned long long *cta_off;     // [grid+1] byte offsets of each CTA's 16 streams
+    int n_layers, H, I, V, n_steps;
+    float eps;
+    const bf16_t *emb;                     // row-major tied embedding (next-input gather)
+    const float *in_norm[28], *post_norm[28], *qn[28], *kn[28];
+    const float *final_norm;
+    float *x_io;                           // [H] input row in / last gathered row out
+    float *kv_k, *kv_v;
+    size_t kv_layer_stride;
+    const float *rope_cos, *rope_sin;      // [pos][64]
+    unsigned long long *ll_qkv, *ll_att, *ll_xwo, *ll_act, *ll_xdn, *ll_head; // {f32, tag} exchange buffers
+    unsigned tag_base;                     // tags of this launch: tag_base + step*(L+1) + layer + 1
+    int *d_pos, *d_step, *d_tokens;
+    volatile int *h_tokens;                // mapped pinned ring (may be NULL)
+    long long *prof;                       // optional clock64 stamps [2][prof_cap] (CTA 0, last CTA) or NULL
+    int prof_cap;
+    int debug;
+};
+int stream_init(void);
+int stream_grid(void);
+size_t stream_image_layout(int L, int H, int I, int V, unsigned long long *cta_off_host /* [grid+1] */);
+int stream_build_image(cudaStream_t s, int L, int H, int I, int V, const bf16_t *const *layer_mats /* [L*4] */, const bf16_t *emb,
+                       const unsigned long long *d_cta_off, uint8_t *image);
+int launch_decode_stream(cudaStream_t s, const StreamParams &p);
+const char *stream_error(void);
+#define QASR_STREAM_ATT_WORDS (16 * 4 * 130)
+
 // ---- row-wise / prefill / encoder kernels (qasr_rows.cu)
 void launch_rmsnorm(cudaStream_t s, const float *x, const float *gamma, float eps, int M, int H, float *out_f32,
                     bf16_t *out_hi, bf16_t *out_lo);
