@@ -89,6 +89,8 @@ struct StreamParams {
     long long *prof;                       // optional clock64 stamps [2][prof_cap] (CTA 0, last CTA) or NULL
     int prof_cap;
     int debug;
+    int trace_cta;                         // CTA whose warp 0 writes the per-unit trace (debug bit 6)
+    int l2_ahead_units;                    // second-level prefetch distance into L2, in 2 KB units per warp (0 = off)
 };
 int stream_init(void);
 int stream_grid(void);

@@ -57,8 +57,8 @@ struct SkSmem {
     uint32_t xf[SK_MAX_K];                                 // phase input, B-fragment order: [kb][8 lanes][2] (24576 B); attention scratch
     float x[SK_MAX_H];                                     // residual stream (replicated in every CTA)
     float partial[2][SK_CHUNK_GROUPS * 16][SK_PSTRIDE];    // [buffer][row in chunk][warp]
-    uint64_t bar[SK_WARPS][SK_SLOTS];
     float red[64];
+    float ssq[SK_WARPS];                                   // per-warp sums of squares of the last normalised input
     int redi[SK_WARPS];
 };
 
@@ -121,18 +121,6 @@ __global__ void __launch_bounds__(SK_THREADS) sk_retile_kernel(const RetileArgs 
 // ---- device helpers ----------------------------------------------------------------------------
 __device__ __forceinline__ void sk_csync() { asm volatile("bar.sync 1, %0;" ::"n"(SK_THREADS) : "memory"); }
 __device__ __forceinline__ uint32_t sk_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void sk_mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(sk_smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
 __device__ __forceinline__ void ll_store(u64 *p, float v, unsigned tag) {
     const u64 w = ((u64)tag << 32) | (u64)__float_as_uint(v);
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
@@ -149,14 +137,22 @@ __device__ __forceinline__ u64 ll_load1(const u64 *p) {
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
     return a;
 }
-__device__ __forceinline__ float ll_wait1(const u64 *p, unsigned tag) {
-    u64 w = ll_load1(p);
-    while ((unsigned)(w >> 32) != tag) w = ll_load1(p);
+// All poll loops are warp-uniform (the whole warp stays in the loop until every lane has its words), so the
+// service functor - the weight-stream top-up, whose cursor state must stay identical across lanes - runs converged.
+template <class Svc>
+__device__ __forceinline__ float ll_wait1(const u64 *p, unsigned tag, bool active, Svc &&svc) {
+    u64 w = active ? ll_load1(p) : (u64)tag << 32;
+    for (;;) {
+        const bool ok = (unsigned)(w >> 32) == tag;
+        if (__all_sync(QASR_FULL, ok)) break;
+        svc();
+        if (!ok) w = ll_load1(p);
+    }
     return __uint_as_float((unsigned)w);
 }
 // Poll NP pairs of consecutive words per thread (pair p = tid + i*512, valid while p < npairs).
-template <int NP>
-__device__ __forceinline__ void ll_gather_pairs(const u64 *buf, int npairs, unsigned tag, int tid, float (&v)[NP][2]) {
+template <int NP, class Svc>
+__device__ __forceinline__ void ll_gather_pairs(const u64 *buf, int npairs, unsigned tag, int tid, float (&v)[NP][2], Svc &&svc) {
     u64 w[NP][2];
 #pragma unroll
     for (int i = 0; i < NP; i++) {
@@ -164,16 +160,16 @@ __device__ __forceinline__ void ll_gather_pairs(const u64 *buf, int npairs, unsi
         if (p < npairs) ll_load2(buf + 2 * p, w[i][0], w[i][1]);
         else w[i][0] = w[i][1] = (u64)tag << 32;
     }
-    bool ok;
-    do {
-        ok = true;
+    for (;;) {
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < NP; i++) ok = ok && (unsigned)(w[i][0] >> 32) == tag && (unsigned)(w[i][1] >> 32) == tag;
+        if (__all_sync(QASR_FULL, ok)) break;
+        svc();
 #pragma unroll
         for (int i = 0; i < NP; i++)
-            if ((unsigned)(w[i][0] >> 32) != tag || (unsigned)(w[i][1] >> 32) != tag) {
-                ll_load2(buf + 2 * (tid + i * SK_THREADS), w[i][0], w[i][1]);
-                ok = false;
-            }
-    } while (!ok);
+            if ((unsigned)(w[i][0] >> 32) != tag || (unsigned)(w[i][1] >> 32) != tag) ll_load2(buf + 2 * (tid + i * SK_THREADS), w[i][0], w[i][1]);
+    }
 #pragma unroll
     for (int i = 0; i < NP; i++) { v[i][0] = __uint_as_float((unsigned)w[i][0]); v[i][1] = __uint_as_float((unsigned)w[i][1]); }
 }
@@ -210,35 +206,53 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
     const int b = blockIdx.x, G = gridDim.x;
     const int L = p.n_layers, H = p.H, I = p.I;
 
-    if (lane == 0)
-        for (int s = 0; s < SK_SLOTS; s++)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sk_smem_u32(&sm.bar[warp][s])) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int e = tid; e < H; e += SK_THREADS) sm.x[e] = p.x_io[e];
     __syncthreads();
 
-    // ---- per-warp weight stream (contiguous, cyclic): the fetch cursor runs SK_SLOTS units ahead
+    // ---- per-warp weight stream (contiguous, cyclic).  Every lane copies its own 4 x 16 B of each unit with
+    // cp.async (LDGSTS, L1 bypass, L2 evict-first) into its private bytes of the warp's SK_SLOTS-deep ring and
+    // later reads back exactly those bytes as its A fragments: a per-lane FIFO, so completion is tracked by the
+    // per-thread cp.async group counter alone (one group per unit, always SK_SLOTS groups outstanding).
     const u64 coff = p.cta_off[b];
     const uint32_t slen = (uint32_t)((p.cta_off[b + 1] - coff) / SK_WARPS);
-    const uint8_t *sbase = p.image + coff + (u64)warp * slen;
+    const uint8_t *wbase = p.image + coff + (u64)warp * slen;
+    const uint8_t *sbase = wbase + lane * 16;
+    // Second-level prefetch, driven by the exchange waits: while a warp polls, it pulls the units that follow its
+    // ring (up to `l2_window` of them) into L2, so HBM keeps streaming during the stalls the 160 KB ring cannot
+    // cover; the later cp.async fetches then hit L2.  Nothing is issued while the consumer is HBM-bound.
+    const unsigned l2_window = (unsigned)p.l2_ahead_units;
+    unsigned fpos = 0, lpos = 0;
+    uint32_t loff = 0;
+    const uint32_t ring0 = sk_smem_u32(sm.ring[warp][0]) + lane * 16;
     uint32_t foff = 0;
     int fsteps = 0;
-    unsigned issued = 0, consumed = 0;
-    auto top_up = [&]() {
-        while (issued - consumed < SK_SLOTS && fsteps < p.n_steps) {
-            if (lane == 0) {
-                const unsigned slot = issued % SK_SLOTS;
-                const uint32_t bar = sk_smem_u32(&sm.bar[warp][slot]), dst = sk_smem_u32(sm.ring[warp][slot]);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(SK_UNIT) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(dst), "l"(sbase + foff), "n"(SK_UNIT), "r"(bar) : "memory");
-            }
-            issued++;
+    unsigned consumed = 0;
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    auto fetch_into = [&](unsigned slot) { // next unit of the stream -> ring slot; always commits one group
+        if (fsteps < p.n_steps) {
+            const uint8_t *src = sbase + foff;
+            const uint32_t dst = ring0 + slot * SK_UNIT;
+#pragma unroll
+            for (int kb = 0; kb < 4; kb++)
+                asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + kb * 512), "l"(src + kb * 512), "l"(pol) : "memory");
             foff += SK_UNIT;
             if (foff == slen) { foff = 0; fsteps++; }
+            fpos++;
+            if (lpos < fpos) { lpos = fpos; loff = foff; }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int i = 0; i < SK_SLOTS; i++) fetch_into(i);
+    auto top_up = [&]() { // service hook of every poll loop (runs converged: the loops are warp-uniform)
+        if (lpos - fpos < l2_window) {
+            if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + loff + lane * 128) : "memory");
+            lpos++;
+            loff += SK_UNIT;
+            if (loff == slen) loff = 0;
         }
     };
-    top_up();
 
     // ---- one weighted phase: y[row] = W[row,:] . x for the CTA's rows, handed to epi(row, r, rowsum)
     // in chunks of <= 128 rows; `rowsum(r)` adds the 16 per-warp partials of chunk row r in fixed order.
@@ -252,7 +266,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                 float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
                 for (int j = 0; j < nj; j++) {
                     const unsigned slot = consumed % SK_SLOTS;
-                    sk_mbar_wait(&sm.bar[warp][slot], (consumed / SK_SLOTS) & 1);
+                    const bool tr = (p.debug & 64) && p.prof && b == p.trace_cta && tid == 0 && consumed < 1300;
+                    if (tr) p.prof[2 * p.prof_cap + 3 * consumed] = clock64();
+                    asm volatile("cp.async.wait_group %0;" ::"n"(SK_SLOTS - 1) : "memory"); // this lane's bytes of the oldest unit have landed
+                    if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 1] = clock64();
                     const uint4 *tile = reinterpret_cast<const uint4 *>(sm.ring[warp][slot]) + lane;
                     const uint2 *xb = reinterpret_cast<const uint2 *>(sm.xf) + (size_t)(warp + 16 * j) * 32 + (lane & 7);
                     uint4 a[4];
@@ -271,9 +288,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                                  : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(a[2].x), "r"(a[2].y), "r"(a[2].z), "r"(a[2].w), "r"(bb[2].x), "r"(bb[2].y));
                     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                                  : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a[3].x), "r"(a[3].y), "r"(a[3].z), "r"(a[3].w), "r"(bb[3].x), "r"(bb[3].y));
-                    __syncwarp();
+                    if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 2] = clock64();
                     consumed++;
-                    top_up(); // the freed slot immediately takes the next unit (possibly of a later phase / token)
+                    fetch_into(slot); // the freed slot immediately takes the next unit (possibly of a later phase / token)
                 }
                 if (tig == 0) { // column 0 = x_hi sums, column 1 = x_lo sums; rows gid and gid+8
                     const int r = (grp - cg0) * 16 + gid;
@@ -297,11 +314,32 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
     };
 
     // x (shared, or gathered from an exchange buffer first) -> RMSNorm -> B-fragment image
-    auto stage_norm = [&](const u64 *src, unsigned tag, const float *gamma) {
+    // Sentinel pre-poll: one word per producer CTA (the last row it writes) before the batch load, so the lines
+    // being written are not hammered by 148 x 512 polling threads (tools/microbench/ll_exchange.cu: 1.1 vs 1.7 us).
+    auto wait_producers = [&](const u64 *buf, int NG, int rows_per_word_shift, unsigned tag) {
+        if (!(p.debug & 2)) return;
+        bool ok = true;
+        const u64 *w = buf;
+        if (tid < G) {
+            const int g0 = sk_g0(NG, tid, G), g1 = sk_g0(NG, tid + 1, G);
+            ok = g1 <= g0;
+            w = buf + ((g1 * 16) >> rows_per_word_shift) - 1;
+        }
+        for (;;) {
+            if (!ok) ok = (unsigned)(ll_load1(w) >> 32) == tag;
+            if (__all_sync(QASR_FULL, ok)) break;
+        }
+        sk_csync();
+    };
+    // x (shared, or gathered from an exchange buffer first) -> x * gamma -> B-fragment image.  The RMSNorm scale
+    // 1/sqrt(mean(x^2)+eps) is a scalar, so it is applied to the phase OUTPUT (norm_scale() in the epilogue):
+    // the block reduction of the squares leaves the critical path between the gather and the first MMA.
+    auto stage_norm = [&](const u64 *src, unsigned tag, const float2 (&gm)[2]) {
         float v[2][2];
         const int npairs = H >> 1;
         if (src) {
-            ll_gather_pairs<2>(src, npairs, tag, tid, v);
+            wait_producers(src, H >> 4, 0, tag);
+            ll_gather_pairs<2>(src, npairs, tag, tid, v, top_up);
 #pragma unroll
             for (int i = 0; i < 2; i++) {
                 const int pr = tid + i * SK_THREADS;
@@ -317,18 +355,27 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
         }
         float ss = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 2; i++) ss = fmaf(v[i][0], v[i][0], fmaf(v[i][1], v[i][1], ss));
-        const float tot = sk_block_sum(ss, sm.red, tid);
-        const float inv = 1.0f / sqrtf(tot / (float)H + p.eps);
+        for (int i = 0; i < 2; i++) {
+            const int pr = tid + i * SK_THREADS;
+            ss = fmaf(v[i][0], v[i][0], fmaf(v[i][1], v[i][1], ss));
+            if (pr < npairs) sk_put_pair(sm.xf, pr, v[i][0] * gm[i].x, v[i][1] * gm[i].y);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) sm.ssq[warp] = ss;
+        sk_csync();
+    };
+    auto norm_scale = [&]() {
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < SK_WARPS; w++) t += sm.ssq[w];
+        return 1.0f / sqrtf(t / (float)H + p.eps);
+    };
+    auto load_gamma = [&](const float *g, float2 (&gm)[2]) {
 #pragma unroll
         for (int i = 0; i < 2; i++) {
             const int pr = tid + i * SK_THREADS;
-            if (pr < npairs) {
-                const float2 gm = *reinterpret_cast<const float2 *>(gamma + 2 * pr);
-                sk_put_pair(sm.xf, pr, v[i][0] * inv * gm.x, v[i][1] * inv * gm.y);
-            }
+            gm[i] = pr < (H >> 1) ? __ldg(reinterpret_cast<const float2 *>(g) + pr) : make_float2(0.f, 0.f);
         }
-        sk_csync();
     };
 
     long long *prof = (p.prof && (b == 0 || b == G - 1) && tid == 0) ? p.prof + (b == 0 ? 0 : p.prof_cap) : nullptr;
@@ -342,6 +389,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
     bool stop = false;
 
     for (; step < p.n_steps && !stop; step++) {
+        const float4 rope_c = __ldg(reinterpret_cast<const float4 *>(p.rope_cos + (size_t)pos * 64) + (lane & 15));
+        const float4 rope_s = __ldg(reinterpret_cast<const float4 *>(p.rope_sin + (size_t)pos * 64) + (lane & 15));
         for (int l = 0; l < L; l++) {
             const unsigned tag = p.tag_base + (unsigned)(step * (L + 1) + l + 1);
             float *kc = p.kv_k + (size_t)l * p.kv_layer_stride, *vc = p.kv_v + (size_t)l * p.kv_layer_stride;
@@ -354,70 +403,108 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             const int per = (n_keys + S - 1) / S;
             const int k0 = sp * per, k1 = min(n_keys, k0 + per);
             if (att) // K/V rows of this split -> L2 while the QKV phase runs
-                for (int j = k0 + tid; j < k1 && j < pos; j += SK_THREADS) {
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;" ::"l"(kc + (size_t)j * kvd + hkv * 128) : "memory");
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], 512;" ::"l"(vc + (size_t)j * kvd + hkv * 128) : "memory");
-                }
+                if (!(p.debug & 8))
+                    for (int j = k0 * 8 + tid; j < k1 * 8 && j < pos * 8; j += SK_THREADS) { // 8 lines of 128 B per key (K row + V row)
+                        const float *row = ((j & 4) ? vc : kc) + (size_t)(j >> 3) * kvd + hkv * 128 + (j & 3) * 32;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row) : "memory");
+                    }
+            // small per-layer parameters: issue the loads now, use them after the exchange waits
+            float2 g_in[2], g_post[2];
+            load_gamma(p.in_norm[l], g_in);
+            load_gamma(p.post_norm[l], g_post);
+            const float4 qn4 = __ldg(reinterpret_cast<const float4 *>(p.qn[l]) + lane), kn4 = __ldg(reinterpret_cast<const float4 *>(p.kn[l]) + lane);
             mark();
             // ---------------- QKV
-            stage_norm(l > 0 ? p.ll_xdn : nullptr, tag - 1, p.in_norm[l]);
+            stage_norm(l > 0 ? p.ll_xdn : nullptr, tag - 1, g_in);
             mark();
-            run_phase(4096, H, [&](int row, int r, auto &&rowsum) { ll_store(p.ll_qkv + row, rowsum(r), tag); });
+            run_phase(4096, H, [&](int row, int r, auto &&rowsum) { ll_store(p.ll_qkv + row, rowsum(r) * norm_scale(), tag); });
             mark();
-            // ---------------- ATTN
+            // ---------------- ATTN (attention CTAs only): everything up to the final merge is warp-local.
+            // Every warp gathers q of the head itself (4 dims per lane), RMS-normalises and ropes it with shuffles;
+            // the warp that owns the new key does the same for k and appends k/v to the cache.  The K/V rows of the
+            // cached keys do not depend on this layer's output: their loads are issued BEFORE the q words are polled.
             if (att) {
                 float *sc = reinterpret_cast<float *>(sm.xf); // the QKV input image is dead: attention scratch
-                float *qs = sc, *knew = sc + 128, *vnew = sc + 256, *tmp = sc + 384, *wacc = sc + 640, *wml = sc + 640 + SK_WARPS * 128;
+                float *wacc = sc, *wml = sc + SK_WARPS * 128;
                 const bool has_new = (k1 == n_keys) && (k0 < k1);
-                const bool writer = has_new && !(hq & 1);
-                float val = 0.0f;
-                const int d = tid & 127;
-                if (tid < 384) {
-                    const int src = tid < 128 ? hq * 128 + d : (tid < 256 ? 2048 + hkv * 128 + d : 3072 + hkv * 128 + d);
-                    val = ll_wait1(p.ll_qkv + src, tag);
-                }
-                { // sums of squares of q (warps 0-3) and k (warps 4-7)
-                    const float s2 = warp_sum(val * val);
-                    if (lane == 0 && warp < 8) sm.red[warp] = s2;
-                }
-                sk_csync();
-                if (tid < 256) {
-                    const int q4 = (tid >> 7) * 4;
-                    const float s = sm.red[q4] + sm.red[q4 + 1] + sm.red[q4 + 2] + sm.red[q4 + 3];
-                    tmp[tid] = val * (1.0f / sqrtf(s / 128.0f + p.eps)) * (tid < 128 ? p.qn[l][d] : p.kn[l][d]);
-                } else if (tid < 384) {
-                    vnew[d] = val;
-                    if (writer) vc[(size_t)pos * kvd + hkv * 128 + d] = val;
-                }
-                sk_csync();
-                if (tid < 256) {
-                    const int dd = d & 63, base = tid & 128;
-                    const float c = p.rope_cos[(size_t)pos * 64 + dd], sn = p.rope_sin[(size_t)pos * 64 + dd];
-                    const int partner = d < 64 ? d + 64 : d - 64;
-                    const float sgn = d < 64 ? -1.0f : 1.0f;
-                    const float r = tmp[tid] * c + sgn * tmp[base + partner] * sn;
-                    if (tid < 128) qs[d] = r;
-                    else {
-                        knew[d] = r;
-                        if (writer) kc[(size_t)pos * kvd + hkv * 128 + d] = r;
+                const int w_new = has_new ? ((pos - k0) & (SK_WARPS - 1)) : -1; // warp whose key list contains `pos`
+                const size_t hoff = (size_t)hkv * 128 + lane * 4;
+                float4 kr[8], vr[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int j = k0 + warp + SK_WARPS * i;
+                    if (j < k1 && j != pos) {
+                        kr[i] = __ldcg(reinterpret_cast<const float4 *>(kc + (size_t)j * kvd + hoff));
+                        vr[i] = __ldcg(reinterpret_cast<const float4 *>(vc + (size_t)j * kvd + hoff));
                     }
                 }
-                sk_csync();
-                const float4 q4v = *reinterpret_cast<const float4 *>(qs + lane * 4);
+                // q (all warps), k and v (owning warp): 4 consecutive words per lane
+                u64 wq[4], wk[4], wv[4];
+                const u64 *pq = p.ll_qkv + hq * 128 + lane * 4, *pk = p.ll_qkv + 2048 + hkv * 128 + lane * 4, *pv = pk + 1024;
+                const bool own = warp == w_new;
+                ll_load2(pq, wq[0], wq[1]); ll_load2(pq + 2, wq[2], wq[3]);
+                if (own) { ll_load2(pk, wk[0], wk[1]); ll_load2(pk + 2, wk[2], wk[3]); ll_load2(pv, wv[0], wv[1]); ll_load2(pv + 2, wv[2], wv[3]); }
+                else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) wk[i] = wv[i] = (u64)tag << 32;
+                }
+                for (;;) {
+                    bool ok = true;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) ok = ok && (unsigned)(wq[i] >> 32) == tag && (unsigned)(wk[i] >> 32) == tag && (unsigned)(wv[i] >> 32) == tag;
+                    if (__all_sync(QASR_FULL, ok)) break;
+                    top_up();
+                    if ((unsigned)(wq[0] >> 32) != tag || (unsigned)(wq[1] >> 32) != tag) ll_load2(pq, wq[0], wq[1]);
+                    if ((unsigned)(wq[2] >> 32) != tag || (unsigned)(wq[3] >> 32) != tag) ll_load2(pq + 2, wq[2], wq[3]);
+                    if (own) {
+                        if ((unsigned)(wk[0] >> 32) != tag || (unsigned)(wk[1] >> 32) != tag) ll_load2(pk, wk[0], wk[1]);
+                        if ((unsigned)(wk[2] >> 32) != tag || (unsigned)(wk[3] >> 32) != tag) ll_load2(pk + 2, wk[2], wk[3]);
+                        if ((unsigned)(wv[0] >> 32) != tag || (unsigned)(wv[1] >> 32) != tag) ll_load2(pv, wv[0], wv[1]);
+                        if ((unsigned)(wv[2] >> 32) != tag || (unsigned)(wv[3] >> 32) != tag) ll_load2(pv + 2, wv[2], wv[3]);
+                    }
+                }
+                mark();
+                // RMSNorm over the 128-vector (warp_sum), split-half RoPE: dims d and d+-64 live in lanes l and l^16
+                auto norm_rope = [&](const u64 (&w)[4], const float4 nw) {
+                    float4 v = make_float4(__uint_as_float((unsigned)w[0]), __uint_as_float((unsigned)w[1]), __uint_as_float((unsigned)w[2]), __uint_as_float((unsigned)w[3]));
+                    const float s2 = warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+                    const float inv = 1.0f / sqrtf(s2 / 128.0f + p.eps);
+                    v.x = v.x * inv * nw.x; v.y = v.y * inv * nw.y; v.z = v.z * inv * nw.z; v.w = v.w * inv * nw.w;
+                    float4 o;
+                    o.x = __shfl_xor_sync(QASR_FULL, v.x, 16); o.y = __shfl_xor_sync(QASR_FULL, v.y, 16);
+                    o.z = __shfl_xor_sync(QASR_FULL, v.z, 16); o.w = __shfl_xor_sync(QASR_FULL, v.w, 16);
+                    const float sgn = lane < 16 ? -1.0f : 1.0f;
+                    return make_float4(v.x * rope_c.x + sgn * o.x * rope_s.x, v.y * rope_c.y + sgn * o.y * rope_s.y,
+                                       v.z * rope_c.z + sgn * o.z * rope_s.z, v.w * rope_c.w + sgn * o.w * rope_s.w);
+                };
+                const float4 q4v = norm_rope(wq, qn4);
+                float4 k_new = make_float4(0.f, 0.f, 0.f, 0.f), v_new = k_new;
+                if (w_new >= 0) { // CTA-uniform branch; only the owning warp holds real k/v words
+                    k_new = norm_rope(wk, kn4);
+                    v_new = make_float4(__uint_as_float((unsigned)wv[0]), __uint_as_float((unsigned)wv[1]), __uint_as_float((unsigned)wv[2]), __uint_as_float((unsigned)wv[3]));
+                    if (own) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) if (k0 + warp + SK_WARPS * i == pos) { kr[i] = k_new; vr[i] = v_new; }
+                        if (!(hq & 1)) { // one writer per kv head appends the new row (reference qwen_asr_decoder.c:640-646)
+                            *reinterpret_cast<float4 *>(kc + (size_t)pos * kvd + hoff) = k_new;
+                            *reinterpret_cast<float4 *>(vc + (size_t)pos * kvd + hoff) = v_new;
+                        }
+                    }
+                }
+                mark();
                 float m = -1e30f, lsum = 0.0f;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int base = k0; base < k1; base += 8 * SK_WARPS) {
-                    float4 kr[8], vr[8];
+                    if (base != k0) { // later batches (only when a split holds more than 128 keys)
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
-                        const int j = base + warp + SK_WARPS * i;
-                        if (j < k1) {
-                            if (j == pos) {
-                                kr[i] = *reinterpret_cast<const float4 *>(knew + lane * 4);
-                                vr[i] = *reinterpret_cast<const float4 *>(vnew + lane * 4);
-                            } else {
-                                kr[i] = __ldcg(reinterpret_cast<const float4 *>(kc + (size_t)j * kvd + hkv * 128 + lane * 4));
-                                vr[i] = __ldcg(reinterpret_cast<const float4 *>(vc + (size_t)j * kvd + hkv * 128 + lane * 4));
+                        for (int i = 0; i < 8; i++) {
+                            const int j = base + warp + SK_WARPS * i;
+                            if (j < k1) {
+                                if (j == pos) { kr[i] = k_new; vr[i] = v_new; } // never read the row being appended from the cache
+                                else {
+                                    kr[i] = __ldcg(reinterpret_cast<const float4 *>(kc + (size_t)j * kvd + hoff));
+                                    vr[i] = __ldcg(reinterpret_cast<const float4 *>(vc + (size_t)j * kvd + hoff));
+                                }
                             }
                         }
                     }
@@ -447,6 +534,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                         }
                     }
                 }
+                mark();
                 if (lane == 0) { wml[warp * 2] = m; wml[warp * 2 + 1] = lsum; }
                 *reinterpret_cast<float4 *>(wacc + warp * 128 + lane * 4) = acc;
                 sk_csync();
@@ -477,19 +565,34 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                     const u64 *pb = p.ll_att + (size_t)(hh * SK_ATT_MAXS) * SK_ATT_STRIDE;
                     float o0 = 0.f, o1 = 0.f, Ls = 0.f, M = -1e30f;
                     float a0[SK_ATT_MAXS], a1[SK_ATT_MAXS], ms[SK_ATT_MAXS], ls[SK_ATT_MAXS];
+                    u64 w[SK_ATT_MAXS][4];
 #pragma unroll
                     for (int s = 0; s < SK_ATT_MAXS; s++) {
                         if (s < S) {
-                            u64 w0, w1, w2, w3;
-                            ll_load2(pb + s * SK_ATT_STRIDE + dd, w0, w1);
-                            ll_load2(pb + s * SK_ATT_STRIDE + 128, w2, w3);
-                            while ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag) ll_load2(pb + s * SK_ATT_STRIDE + dd, w0, w1);
-                            while ((unsigned)(w2 >> 32) != tag || (unsigned)(w3 >> 32) != tag) ll_load2(pb + s * SK_ATT_STRIDE + 128, w2, w3);
-                            a0[s] = __uint_as_float((unsigned)w0); a1[s] = __uint_as_float((unsigned)w1);
-                            ms[s] = __uint_as_float((unsigned)w2); ls[s] = __uint_as_float((unsigned)w3);
-                            M = fmaxf(M, ms[s]);
+                            ll_load2(pb + s * SK_ATT_STRIDE + dd, w[s][0], w[s][1]);
+                            ll_load2(pb + s * SK_ATT_STRIDE + 128, w[s][2], w[s][3]);
+                        } else w[s][0] = w[s][1] = w[s][2] = w[s][3] = (u64)tag << 32;
+                    }
+                    for (;;) {
+                        bool ok = true;
+#pragma unroll
+                        for (int s = 0; s < SK_ATT_MAXS; s++)
+                            ok = ok && (unsigned)(w[s][0] >> 32) == tag && (unsigned)(w[s][1] >> 32) == tag && (unsigned)(w[s][2] >> 32) == tag && (unsigned)(w[s][3] >> 32) == tag;
+                        if (__all_sync(QASR_FULL, ok)) break;
+                        top_up();
+#pragma unroll
+                        for (int s = 0; s < SK_ATT_MAXS; s++) {
+                            if ((unsigned)(w[s][0] >> 32) != tag || (unsigned)(w[s][1] >> 32) != tag) ll_load2(pb + s * SK_ATT_STRIDE + dd, w[s][0], w[s][1]);
+                            if ((unsigned)(w[s][2] >> 32) != tag || (unsigned)(w[s][3] >> 32) != tag) ll_load2(pb + s * SK_ATT_STRIDE + 128, w[s][2], w[s][3]);
                         }
                     }
+#pragma unroll
+                    for (int s = 0; s < SK_ATT_MAXS; s++)
+                        if (s < S) {
+                            a0[s] = __uint_as_float((unsigned)w[s][0]); a1[s] = __uint_as_float((unsigned)w[s][1]);
+                            ms[s] = __uint_as_float((unsigned)w[s][2]); ls[s] = __uint_as_float((unsigned)w[s][3]);
+                            M = fmaxf(M, ms[s]);
+                        }
 #pragma unroll
                     for (int s = 0; s < SK_ATT_MAXS; s++)
                         if (s < S) {
@@ -505,16 +608,20 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             }
             mark();
             // ---------------- GU + SwiGLU: rows (2j, 2j+1) = (gate_j, up_j) are neighbours in a chunk
-            stage_norm(p.ll_xwo, tag, p.post_norm[l]);
+            stage_norm(p.ll_xwo, tag, g_post);
             mark();
             run_phase(2 * I, H, [&](int row, int r, auto &&rowsum) {
-                if (!(row & 1)) ll_store(p.ll_act + (row >> 1), silu(rowsum(r)) * rowsum(r + 1), tag);
+                if (!(row & 1)) {
+                    const float inv = norm_scale();
+                    ll_store(p.ll_act + (row >> 1), silu(rowsum(r) * inv) * (rowsum(r + 1) * inv), tag);
+                }
             });
             mark();
             // ---------------- DOWN
             {
                 float v[6][2];
-                ll_gather_pairs<6>(p.ll_act, I >> 1, tag, tid, v);
+                wait_producers(p.ll_act, (2 * I) >> 4, 1, tag);
+                ll_gather_pairs<6>(p.ll_act, I >> 1, tag, tid, v, top_up);
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
                     const int pr = tid + i * SK_THREADS;
@@ -528,7 +635,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
         }
         // ---------------- HEAD: greedy argmax over this CTA's vocab rows of the tied embedding
         const unsigned htag = p.tag_base + (unsigned)(step * (L + 1) + L + 1);
-        stage_norm(p.ll_xdn, htag - 1, p.final_norm);
+        float2 g_fin[2];
+        load_gamma(p.final_norm, g_fin);
+        stage_norm(p.ll_xdn, htag - 1, g_fin); // argmax is invariant under the positive RMSNorm scale: not applied
         float bv = -1e30f;
         int bi = 0x7fffffff;
         run_phase(p.V, H, [&](int row, int r, auto &&rowsum) { const float y = rowsum(r); if (sk_better(y, row, bv, bi)) { bv = y; bi = row; } });
@@ -552,12 +661,17 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
         { // every CTA reduces the G winners identically
             float wv = -1e30f;
             int wi = 0x7fffffff;
-            if (tid < G) {
-                u64 w0, w1;
-                ll_load2(p.ll_head + 2 * tid, w0, w1);
-                while ((unsigned)(w0 >> 32) != htag || (unsigned)(w1 >> 32) != htag) ll_load2(p.ll_head + 2 * tid, w0, w1);
-                wv = __uint_as_float((unsigned)w0);
-                wi = (int)(unsigned)w1;
+            {
+                const bool active = tid < G;
+                u64 w0 = (u64)htag << 32, w1 = (u64)htag << 32;
+                if (active) ll_load2(p.ll_head + 2 * tid, w0, w1);
+                for (;;) {
+                    const bool ok = (unsigned)(w0 >> 32) == htag && (unsigned)(w1 >> 32) == htag;
+                    if (__all_sync(QASR_FULL, ok)) break;
+                    top_up();
+                    if (!ok) ll_load2(p.ll_head + 2 * tid, w0, w1);
+                }
+                if (active) { wv = __uint_as_float((unsigned)w0); wi = (int)(unsigned)w1; }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -590,11 +704,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
         for (int e = tid; e < H; e += SK_THREADS) p.x_io[e] = sm.x[e];
         if (tid == 0) { *p.d_pos = pos; *p.d_step = step; }
     }
-    // drain bulk copies that were prefetched past an early stop before the CTA's shared memory goes away
-    while (consumed < issued) {
-        sk_mbar_wait(&sm.bar[warp][consumed % SK_SLOTS], (consumed / SK_SLOTS) & 1);
-        consumed++;
-    }
+    // drain copies that were prefetched past an early stop before the CTA's shared memory goes away
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // ---- host side ---------------------------------------------------------------------------------
