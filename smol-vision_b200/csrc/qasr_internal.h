@@ -99,7 +99,7 @@ int stream_build_image(cudaStream_t s, int L, int H, int I, int V, const bf16_t 
                        const unsigned long long *d_cta_off, uint8_t *image);
 int launch_decode_stream(cudaStream_t s, const StreamParams &p);
 const char *stream_error(void);
-#define QASR_STREAM_ATT_WORDS (16 * 4 * 130)
+#define QASR_STREAM_ATT_WORDS (16 * 9 * 130) /* room for up to 9 key splits per head */
 
 // ---- row-wise / prefill / encoder kernels (qasr_rows.cu)
 void launch_rmsnorm(cudaStream_t s, const float *x, const float *gamma, float eps, int M, int H, float *out_f32,

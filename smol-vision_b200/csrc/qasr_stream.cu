@@ -38,16 +38,25 @@
 #include "qasr_internal.h"
 
 #include <stdio.h>
+#include <type_traits>
 
 #define SK_WARPS 16
 #define SK_THREADS (SK_WARPS * 32)
+#ifndef SK_SLOTS
 #define SK_SLOTS 5
+#endif
 #define SK_UNIT 2048          /* 16 rows x 64 cols bf16, A-fragment order: [kb 0..3][lane][a0..a3] */
 #define SK_CHUNK_GROUPS 8     /* 16-row groups reduced together (128 rows) */
 #define SK_PSTRIDE 17
 #define SK_MAX_K 6144
 #define SK_MAX_H 2048
+#ifndef SK_ATT_MAXS
 #define SK_ATT_MAXS 4
+#endif
+#ifndef SK_ATT_BATCH
+#define SK_ATT_BATCH 4
+#endif
+//      SK_ATT_BATCH:      /* cached keys per warp whose K/V rows are loaded ahead of the q words */
 #define SK_ATT_STRIDE 130     /* 128 acc + m + l */
 
 typedef unsigned long long u64;
@@ -223,12 +232,12 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
     const unsigned l2_window = (unsigned)p.l2_ahead_units;
     unsigned fpos = 0, lpos = 0;
     uint32_t loff = 0;
-    const uint32_t ring0 = sk_smem_u32(sm.ring[warp][0]) + lane * 16;
     uint32_t foff = 0;
     int fsteps = 0;
     unsigned consumed = 0;
     u64 pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    const uint32_t ring0 = sk_smem_u32(sm.ring[warp][0]) + lane * 16;
     auto fetch_into = [&](unsigned slot) { // next unit of the stream -> ring slot; always commits one group
         if (fsteps < p.n_steps) {
             const uint8_t *src = sbase + foff;
@@ -265,32 +274,42 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             for (int grp = cg0; grp < cg1; grp++) {
                 float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
                 for (int j = 0; j < nj; j++) {
-                    const unsigned slot = consumed % SK_SLOTS;
                     const bool tr = (p.debug & 64) && p.prof && b == p.trace_cta && tid == 0 && consumed < 1300;
                     if (tr) p.prof[2 * p.prof_cap + 3 * consumed] = clock64();
-                    asm volatile("cp.async.wait_group %0;" ::"n"(SK_SLOTS - 1) : "memory"); // this lane's bytes of the oldest unit have landed
-                    if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 1] = clock64();
-                    const uint4 *tile = reinterpret_cast<const uint4 *>(sm.ring[warp][slot]) + lane;
                     const uint2 *xb = reinterpret_cast<const uint2 *>(sm.xf) + (size_t)(warp + 16 * j) * 32 + (lane & 7);
-                    uint4 a[4];
                     uint2 bb[4];
 #pragma unroll
                     for (int kb = 0; kb < 4; kb++) {
-                        a[kb] = tile[kb * 32];
                         bb[kb] = xb[kb * 8];
                         if (lane >= 8) bb[kb] = make_uint2(0u, 0u);
                     }
-                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(a[0].x), "r"(a[0].y), "r"(a[0].z), "r"(a[0].w), "r"(bb[0].x), "r"(bb[0].y));
-                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a[1].x), "r"(a[1].y), "r"(a[1].z), "r"(a[1].w), "r"(bb[1].x), "r"(bb[1].y));
-                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(a[2].x), "r"(a[2].y), "r"(a[2].z), "r"(a[2].w), "r"(bb[2].x), "r"(bb[2].y));
-                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a[3].x), "r"(a[3].y), "r"(a[3].z), "r"(a[3].w), "r"(bb[3].x), "r"(bb[3].y));
+                    auto mma4 = [&](uint4 (&a)[4]) {
+                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(a[0].x), "r"(a[0].y), "r"(a[0].z), "r"(a[0].w), "r"(bb[0].x), "r"(bb[0].y));
+                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a[1].x), "r"(a[1].y), "r"(a[1].z), "r"(a[1].w), "r"(bb[1].x), "r"(bb[1].y));
+                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(a[2].x), "r"(a[2].y), "r"(a[2].z), "r"(a[2].w), "r"(bb[2].x), "r"(bb[2].y));
+                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a[3].x), "r"(a[3].y), "r"(a[3].z), "r"(a[3].w), "r"(bb[3].x), "r"(bb[3].y));
+                    };
+                        default: mma4(rr[2]); issue_unit(rr[2]); break;
+                    }
+                    if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 1] = p.prof[2 * p.prof_cap + 3 * consumed + 2] = clock64();
+                    consumed++;
+#else
+                    const unsigned slot = consumed % SK_SLOTS;
+                    asm volatile("cp.async.wait_group %0;" ::"n"(SK_SLOTS - 1) : "memory"); // this lane's bytes of the oldest unit have landed
+                    if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 1] = clock64();
+                    const uint4 *tile = reinterpret_cast<const uint4 *>(sm.ring[warp][slot]) + lane;
+                    uint4 a[4];
+#pragma unroll
+                    for (int kb = 0; kb < 4; kb++) a[kb] = tile[kb * 32];
+                    mma4(a);
                     if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 2] = clock64();
                     consumed++;
                     fetch_into(slot); // the freed slot immediately takes the next unit (possibly of a later phase / token)
+#endif
                 }
                 if (tig == 0) { // column 0 = x_hi sums, column 1 = x_lo sums; rows gid and gid+8
                     const int r = (grp - cg0) * 16 + gid;
@@ -396,7 +415,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             float *kc = p.kv_k + (size_t)l * p.kv_layer_stride, *vc = p.kv_v + (size_t)l * p.kv_layer_stride;
             // attention role of this CTA: q head hq, key split sp of S
             const int n_keys = pos + 1;
-            int S = (n_keys + 127) >> 7;
+            int S = (n_keys + SK_ATT_BATCH * SK_WARPS - 1) / (SK_ATT_BATCH * SK_WARPS);
             S = S > SK_ATT_MAXS ? SK_ATT_MAXS : S;
             const bool att = b < 16 * S;
             const int hq = b / S, sp = b - hq * S, hkv = hq >> 1;
@@ -429,9 +448,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                 const bool has_new = (k1 == n_keys) && (k0 < k1);
                 const int w_new = has_new ? ((pos - k0) & (SK_WARPS - 1)) : -1; // warp whose key list contains `pos`
                 const size_t hoff = (size_t)hkv * 128 + lane * 4;
-                float4 kr[8], vr[8];
+                float4 kr[SK_ATT_BATCH], vr[SK_ATT_BATCH];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
+                for (int i = 0; i < SK_ATT_BATCH; i++) {
                     const int j = k0 + warp + SK_WARPS * i;
                     if (j < k1 && j != pos) {
                         kr[i] = __ldcg(reinterpret_cast<const float4 *>(kc + (size_t)j * kvd + hoff));
@@ -484,7 +503,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                     v_new = make_float4(__uint_as_float((unsigned)wv[0]), __uint_as_float((unsigned)wv[1]), __uint_as_float((unsigned)wv[2]), __uint_as_float((unsigned)wv[3]));
                     if (own) {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) if (k0 + warp + SK_WARPS * i == pos) { kr[i] = k_new; vr[i] = v_new; }
+                        for (int i = 0; i < SK_ATT_BATCH; i++) if (k0 + warp + SK_WARPS * i == pos) { kr[i] = k_new; vr[i] = v_new; }
                         if (!(hq & 1)) { // one writer per kv head appends the new row (reference qwen_asr_decoder.c:640-646)
                             *reinterpret_cast<float4 *>(kc + (size_t)pos * kvd + hoff) = k_new;
                             *reinterpret_cast<float4 *>(vc + (size_t)pos * kvd + hoff) = v_new;
@@ -494,10 +513,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                 mark();
                 float m = -1e30f, lsum = 0.0f;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int base = k0; base < k1; base += 8 * SK_WARPS) {
-                    if (base != k0) { // later batches (only when a split holds more than 128 keys)
+                for (int base = k0; base < k1; base += SK_ATT_BATCH * SK_WARPS) {
+                    if (base != k0) { // later batches (only when a split holds more than 64 keys)
 #pragma unroll
-                        for (int i = 0; i < 8; i++) {
+                        for (int i = 0; i < SK_ATT_BATCH; i++) {
                             const int j = base + warp + SK_WARPS * i;
                             if (j < k1) {
                                 if (j == pos) { kr[i] = k_new; vr[i] = v_new; } // never read the row being appended from the cache
@@ -508,16 +527,16 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                             }
                         }
                     }
-                    float sc8[8];
+                    float sc8[SK_ATT_BATCH];
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
+                    for (int i = 0; i < SK_ATT_BATCH; i++) {
                         const int j = base + warp + SK_WARPS * i;
                         float d4 = 0.0f;
                         if (j < k1) d4 = q4v.x * kr[i].x + q4v.y * kr[i].y + q4v.z * kr[i].z + q4v.w * kr[i].w;
                         sc8[i] = warp_sum(d4) * scale;
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; i++) {
+                    for (int i = 0; i < SK_ATT_BATCH; i++) {
                         const int j = base + warp + SK_WARPS * i;
                         if (j < k1) {
                             const float s = sc8[i];
@@ -558,50 +577,52 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             mark();
             // ---------------- WO: input = attention output merged over the S key splits
             {
+                auto merge_splits = [&](auto ns_c) { // NS = compile-time bound on S (1 for contexts of <= 64 keys)
+                    constexpr int NS = decltype(ns_c)::value;
+#pragma unroll 1
+                    for (int i = 0; i < 2; i++) {
+                        const int pr = tid + i * SK_THREADS; // elements 2pr, 2pr+1 of the 2048-wide head-major vector
+                        const int hh = pr >> 6, dd = (pr & 63) * 2;
+                        const u64 *pb = p.ll_att + (size_t)(hh * SK_ATT_MAXS) * SK_ATT_STRIDE;
+                        u64 w[NS][4];
 #pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const int pr = tid + i * SK_THREADS; // elements 2pr, 2pr+1 of the 2048-wide head-major vector
-                    const int hh = pr >> 6, dd = (pr & 63) * 2;
-                    const u64 *pb = p.ll_att + (size_t)(hh * SK_ATT_MAXS) * SK_ATT_STRIDE;
-                    float o0 = 0.f, o1 = 0.f, Ls = 0.f, M = -1e30f;
-                    float a0[SK_ATT_MAXS], a1[SK_ATT_MAXS], ms[SK_ATT_MAXS], ls[SK_ATT_MAXS];
-                    u64 w[SK_ATT_MAXS][4];
+                        for (int s = 0; s < NS; s++) {
+                            if (s < S) {
+                                ll_load2(pb + s * SK_ATT_STRIDE + dd, w[s][0], w[s][1]);
+                                ll_load2(pb + s * SK_ATT_STRIDE + 128, w[s][2], w[s][3]);
+                            } else w[s][0] = w[s][1] = w[s][2] = w[s][3] = (u64)tag << 32;
+                        }
+                        for (;;) {
+                            bool ok = true;
 #pragma unroll
-                    for (int s = 0; s < SK_ATT_MAXS; s++) {
-                        if (s < S) {
-                            ll_load2(pb + s * SK_ATT_STRIDE + dd, w[s][0], w[s][1]);
-                            ll_load2(pb + s * SK_ATT_STRIDE + 128, w[s][2], w[s][3]);
-                        } else w[s][0] = w[s][1] = w[s][2] = w[s][3] = (u64)tag << 32;
+                            for (int s = 0; s < NS; s++)
+                                ok = ok && (unsigned)(w[s][0] >> 32) == tag && (unsigned)(w[s][1] >> 32) == tag && (unsigned)(w[s][2] >> 32) == tag && (unsigned)(w[s][3] >> 32) == tag;
+                            if (__all_sync(QASR_FULL, ok)) break;
+                            top_up();
+#pragma unroll
+                            for (int s = 0; s < NS; s++) {
+                                if ((unsigned)(w[s][0] >> 32) != tag || (unsigned)(w[s][1] >> 32) != tag) ll_load2(pb + s * SK_ATT_STRIDE + dd, w[s][0], w[s][1]);
+                                if ((unsigned)(w[s][2] >> 32) != tag || (unsigned)(w[s][3] >> 32) != tag) ll_load2(pb + s * SK_ATT_STRIDE + 128, w[s][2], w[s][3]);
+                            }
+                        }
+                        float M = -1e30f, Ls = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+                        for (int s = 0; s < NS; s++)
+                            if (s < S) M = fmaxf(M, __uint_as_float((unsigned)w[s][2]));
+#pragma unroll
+                        for (int s = 0; s < NS; s++)
+                            if (s < S) {
+                                const float e = expf(__uint_as_float((unsigned)w[s][2]) - M);
+                                Ls += __uint_as_float((unsigned)w[s][3]) * e;
+                                o0 += __uint_as_float((unsigned)w[s][0]) * e;
+                                o1 += __uint_as_float((unsigned)w[s][1]) * e;
+                            }
+                        const float invL = Ls > 0.0f ? 1.0f / Ls : 0.0f;
+                        sk_put_pair(sm.xf, pr, o0 * invL, o1 * invL);
                     }
-                    for (;;) {
-                        bool ok = true;
-#pragma unroll
-                        for (int s = 0; s < SK_ATT_MAXS; s++)
-                            ok = ok && (unsigned)(w[s][0] >> 32) == tag && (unsigned)(w[s][1] >> 32) == tag && (unsigned)(w[s][2] >> 32) == tag && (unsigned)(w[s][3] >> 32) == tag;
-                        if (__all_sync(QASR_FULL, ok)) break;
-                        top_up();
-#pragma unroll
-                        for (int s = 0; s < SK_ATT_MAXS; s++) {
-                            if ((unsigned)(w[s][0] >> 32) != tag || (unsigned)(w[s][1] >> 32) != tag) ll_load2(pb + s * SK_ATT_STRIDE + dd, w[s][0], w[s][1]);
-                            if ((unsigned)(w[s][2] >> 32) != tag || (unsigned)(w[s][3] >> 32) != tag) ll_load2(pb + s * SK_ATT_STRIDE + 128, w[s][2], w[s][3]);
-                        }
-                    }
-#pragma unroll
-                    for (int s = 0; s < SK_ATT_MAXS; s++)
-                        if (s < S) {
-                            a0[s] = __uint_as_float((unsigned)w[s][0]); a1[s] = __uint_as_float((unsigned)w[s][1]);
-                            ms[s] = __uint_as_float((unsigned)w[s][2]); ls[s] = __uint_as_float((unsigned)w[s][3]);
-                            M = fmaxf(M, ms[s]);
-                        }
-#pragma unroll
-                    for (int s = 0; s < SK_ATT_MAXS; s++)
-                        if (s < S) {
-                            const float e = expf(ms[s] - M);
-                            Ls += ls[s] * e; o0 += a0[s] * e; o1 += a1[s] * e;
-                        }
-                    const float invL = Ls > 0.0f ? 1.0f / Ls : 0.0f;
-                    sk_put_pair(sm.xf, pr, o0 * invL, o1 * invL);
-                }
+                };
+                if (S == 1) merge_splits(std::integral_constant<int, 1>{});
+                else merge_splits(std::integral_constant<int, SK_ATT_MAXS>{});
                 sk_csync();
                 mark();
                 run_phase(H, 2048, [&](int row, int r, auto &&rowsum) { ll_store(p.ll_xwo + row, sm.x[row] + rowsum(r), tag); });
