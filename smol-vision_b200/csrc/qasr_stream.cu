@@ -293,11 +293,6 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                         asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                                      : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a[3].x), "r"(a[3].y), "r"(a[3].z), "r"(a[3].w), "r"(bb[3].x), "r"(bb[3].y));
                     };
-                        default: mma4(rr[2]); issue_unit(rr[2]); break;
-                    }
-                    if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 1] = p.prof[2 * p.prof_cap + 3 * consumed + 2] = clock64();
-                    consumed++;
-#else
                     const unsigned slot = consumed % SK_SLOTS;
                     asm volatile("cp.async.wait_group %0;" ::"n"(SK_SLOTS - 1) : "memory"); // this lane's bytes of the oldest unit have landed
                     if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 1] = clock64();
@@ -309,7 +304,6 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                     if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 2] = clock64();
                     consumed++;
                     fetch_into(slot); // the freed slot immediately takes the next unit (possibly of a later phase / token)
-#endif
                 }
                 if (tig == 0) { // column 0 = x_hi sums, column 1 = x_lo sums; rows gid and gid+8
                     const int r = (grp - cg0) * 16 + gid;
