@@ -48,6 +48,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic_per_step(variant):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel per greedy step, from the committed
+    `ncu --set full` capture (profiles/r01_stream_ncu_summary.json, taken on the 1.7B workload); None otherwise."""
+    p = os.path.join(ROOT, "profiles", "r01_stream_ncu_summary.json")
+    if variant != "1.7b" or not os.path.exists(p):
+        return None
+    return float(json.load(open(p))["dram_bytes_per_step"])
+
+
 def decode_bytes_per_step(cfg, kv_positions):
     """Algorithmic bytes of one decode step: bf16 decoder-layer weights + tied lm_head
     + f32 KV rows read (229 376 B per cached position)."""
@@ -254,8 +263,8 @@ def main():
                "stage_ms": {k: v / args.steps for k, v in stage_acc.items()},
                "ids_head": ids[:8],
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "peak_source": peak_src,
-                            "kernel": "decode step of decode_mega_kernel (persistent cooperative kernel; QASR_DECODE=graph: CUDA graph of 112 gemv_bf16 + 28 attn_decode + argmax_gemv + finalize)",
+                            "traffic": ncu_traffic_per_step(variant), "peak_source": peak_src,
+                            "kernel": "one greedy step of decode_stream_kernel (persistent cooperative kernel, qasr_stream.cu; a launch runs up to 16 steps)",
                             "bytes_per_launch": step_bytes, "ms_per_launch": dec_ms_per_step,
                             "frac_of_8000_nominal": achieved / 8000.0}}
         if not args.no_cpu_baseline:

@@ -54,7 +54,7 @@
 #define SK_ATT_MAXS 4
 #endif
 #ifndef SK_ATT_BATCH
-#define SK_ATT_BATCH 4
+#define SK_ATT_BATCH 2
 #endif
 //      SK_ATT_BATCH:      /* cached keys per warp whose K/V rows are loaded ahead of the q words */
 #define SK_ATT_STRIDE 130     /* 128 acc + m + l */
