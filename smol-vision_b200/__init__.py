@@ -8,3 +8,4 @@ The directory name contains a hyphen, so import it through `__graft_entry__.load
 from .binding import LIB_PATH, SIGNATURES, QasrCuda, QasrError, load_library  # noqa: F401
 from .synth import SAMPLE_RATE, ensure_model_dir, synth_audio  # noqa: F401
 from . import segments  # noqa: F401
+from . import streaming  # noqa: F401

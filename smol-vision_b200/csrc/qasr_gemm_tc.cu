@@ -23,6 +23,7 @@
 
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define TC_BM 128
@@ -584,8 +585,14 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
         SkScratch &sc = g_sk[dev & 15];
         const int MP = M <= 64 ? 64 : (M <= 128 ? 128 : 256);
         const int n_tiles = (N + 127) / 128, total_kb = (K + TC_BK - 1) / TC_BK;
-        int S = (32 + n_tiles - 1) / n_tiles; // a lone CTA ingests ~150 GB/s: 32 CTAs already saturate HBM
-        if (S > total_kb / 4) S = total_kb / 4;
+        static int target_ctas = 0, min_kb = 0;
+        if (!target_ctas) {
+            const char *e = getenv("QASR_GEMM_TARGET_CTAS"), *m = getenv("QASR_GEMM_MIN_KB");
+            target_ctas = e ? atoi(e) : 74;
+            min_kb = m ? atoi(m) : 4;
+        }
+        int S = (target_ctas + n_tiles - 1) / n_tiles; // split K until ~target_ctas CTAs stream weights
+        if (S > total_kb / min_kb) S = total_kb / min_kb;
         if (S < 1) S = 1;
         const int kb_per = (total_kb + S - 1) / S;
         S = (total_kb + kb_per - 1) / kb_per;

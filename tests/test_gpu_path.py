@@ -176,3 +176,43 @@ def test_config2_1p7b_vs_oracle(pkg, model17, oracle_lib):
     finally:
         eng.close()
         ora.close()
+
+
+def test_stream_session_ids_match_oracle(gpu06, oracle06, pkg):
+    """configs[3] (--stream): the same host session drives the B200 path and the CPU oracle; per chunk the
+    reused prefix, the delta prefill and the greedy ids must be identical (window completion, cached-window reuse
+    and KV rollback are all exercised with 1 s chunks over 2 s windows)."""
+    audio = pkg.synth_audio(3.0, seed=21)
+    kw = dict(window_sec=2.0, max_windows=2, max_new=4)
+    got = pkg.streaming.run_stream(gpu06, audio, 1.0, **kw)
+    want = pkg.streaming.run_stream(oracle06, audio, 1.0, **kw)
+    assert len(got) == len(want) == 3
+    for g, w in zip(got, want):
+        assert (g["rows"], g["new_windows"]) == (w["rows"], w["new_windows"])
+        assert g["reused"] == w["reused"] and g["prefilled"] == w["prefilled"]
+        assert g["ids"] == w["ids"]
+    assert got[2]["reused"] > len(pkg.streaming.PROMPT_PRE)   # the completed window's rows were reused from the KV cache
+
+
+def test_long_context_decode_matches_oracle(gpu06, oracle06):
+    """> 512 cached positions: the decode kernel runs 4 key splits per head with several key batches per warp
+    (qasr_stream.cu SK_ATT_MAXS / SK_ATT_BATCH); ids must still equal the CPU oracle's."""
+    rng = np.random.default_rng(5)
+    H = gpu06.cfg["dec_hidden"]
+    rows = np.stack([gpu06.embed(int(t)) for t in rng.integers(0, 151000, 40)])
+    embeds = rows[rng.integers(0, 40, 540)] + (0.01 * rng.standard_normal((540, H))).astype(np.float32)
+    embeds = np.ascontiguousarray(embeds, np.float32)
+    ids = []
+    for eng in (gpu06, oracle06):
+        eng.kv_len = 0
+        eng.prefill(embeds[:-1])
+        tok = eng.step(embeds[-1])
+        out = [tok]
+        for _ in range(5):
+            tok = eng.step(eng.embed(tok))
+            out.append(tok)
+        ids.append(out)
+        assert eng.kv_len == 545
+    assert ids[0] == ids[1]
+    gpu06.kv_len = 540
+    assert list(gpu06.generate(ids[0][0], 6)) == ids[0]      # device greedy loop from the same state

@@ -98,3 +98,66 @@ def test_two_rank_gloo_gather_in_segment_order():
     for rank, order, firsts in results:
         assert order == list(range(7)), f"rank {rank} saw {order}"
         assert firsts == [100 * i for i in range(7)]
+
+
+# ---------------------------------------------------------------- streaming session (host logic)
+class _FakeEngine:
+    """Deterministic stand-in with the duck-typed engine interface (mel/encode/embed/prefill/step/kv_len):
+    records what the session asks the device to do."""
+
+    def __init__(self, H=8):
+        self.H, self.kv_len, self.log = H, 0, []
+
+    def embed(self, tok):
+        return np.full(self.H, float(tok % 97), np.float32)
+
+    def mel(self, samples):
+        # like the real front end, every value depends on the whole span (dynamic max normalisation)
+        return np.tile(np.float32(samples[: (len(samples) // 160) * 160: 160]) + np.float32(len(samples) * 1e-3), (128, 1))
+
+    def encode(self, mel):
+        T = max(1, mel.shape[1] // 8)
+        return (mel[:1, : T * 8].reshape(T, 8).mean(axis=1, keepdims=True) * np.ones((1, self.H))).astype(np.float32)
+
+    def prefill(self, embeds):
+        self.log.append(("prefill", self.kv_len, len(embeds)))
+        self.kv_len += len(embeds)
+
+    def step(self, embed):
+        self.log.append(("step", self.kv_len))
+        self.kv_len += 1
+        return 7
+
+
+def test_stream_session_reuses_prefix_and_caches_windows(pkg):
+    st = pkg.streaming
+    rng = np.random.default_rng(0)
+    audio = rng.standard_normal(16000 * 5).astype(np.float32)
+    eng = _FakeEngine()
+    sess = st.StreamSession(eng, window_sec=2.0, max_windows=2, max_new=3)
+    r1 = sess.feed(audio[:16000])          # 1 s: only a tail
+    assert r1["reused"] == 0 and r1["new_windows"] == 0 and r1["ids"] == [7, 7, 7]
+    r2 = sess.feed(audio[:32000])          # 2 s: first full window completes, no tail
+    assert r2["new_windows"] == 1 and r2["reused"] == len(st.PROMPT_PRE)   # prompt prefix rows reused
+    r3 = sess.feed(audio[:48000])          # 3 s: window 0 cached (rows reused), new tail
+    assert r3["new_windows"] == 0
+    n_w0 = len(sess.win_rows[0])
+    assert r3["reused"] == len(st.PROMPT_PRE) + n_w0
+    # every chunk: kv_len rolled back to `reused`, the delta prefilled, last row stepped (qwen_asr.c:1823-1829)
+    pre = [e for e in eng.log if e[0] == "prefill"][-1]
+    assert pre[1] == r3["reused"] and pre[2] == r3["prefilled"] == r3["rows"] - 1 - r3["reused"]
+    sess.feed(audio[:64000])               # 4 s: windows 0, 1
+    r5 = sess.feed(audio[:80000])          # 5 s: still windows 0, 1 + tail
+    assert sorted(sess.win_rows) == [0, 1] and r5["reused"] >= len(st.PROMPT_PRE) + n_w0
+    sess.feed(np.concatenate([audio, audio[:16000]]))   # 6 s: window 2 completes -> window 0 evicted (max_windows=2)
+    assert sorted(sess.win_rows) == [1, 2]
+
+
+def test_common_prefix_rows_is_bitwise(pkg):
+    st = pkg.streaming
+    a = np.arange(12, dtype=np.float32).reshape(4, 3)
+    b = a.copy()
+    assert st.common_prefix_rows(a, b) == 4 and st.common_prefix_rows(a, None) == 0
+    b[2, 1] = np.nextafter(b[2, 1], np.float32(100))
+    assert st.common_prefix_rows(a, b) == 2
+    assert st.common_prefix_rows(a[:1], b) == 1
