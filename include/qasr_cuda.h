@@ -120,6 +120,15 @@ int qasr_cuda_generate(qasr_ctx_t *ctx, int first_token, int kv_len, int max_new
 int qasr_cuda_transcribe_ids(qasr_ctx_t *ctx, const float *samples, int n_samples, int max_new,
                              int *out_ids, int *out_n, double *timings_ms, int *out_enc_tokens);
 
+/* Independent units (the segments of -S mode, reference qwen_asr.c:941-1103, or separate utterances) decoded
+ * together: up to qasr_cuda_max_batch() sequences share every decode step (one pass over the weights serves all
+ * of them); front end, encoder and prefill run per unit.  samples[i] / n_samples[i] / max_new[i] describe unit i;
+ * unit i's ids go to out_ids + i*ids_stride (max_new[i] <= ids_stride), its count to out_n[i].  Ids are identical
+ * to qasr_cuda_transcribe_ids on the same unit.  timings_ms (nullable) = {mel, encoder, prefill, decode} totals. */
+int qasr_cuda_max_batch(const qasr_ctx_t *ctx);
+int qasr_cuda_transcribe_batch(qasr_ctx_t *ctx, const float *const *samples, const int *n_samples, int count,
+                               const int *max_new, int ids_stride, int *out_ids, int *out_n, double *timings_ms);
+
 /* Benchmark plumbing: keep a segment's samples resident in HBM and transcribe from there (no
  * per-call host->device copy), a CUDA-event stopwatch on the library's own stream (the stream
  * every kernel here is launched on), and the accumulated device time / step count of the greedy

@@ -46,6 +46,8 @@ SIGNATURES = {
     "qasr_cuda_step_logits": (ci, [vp, f32p, ci, f32p]),
     "qasr_cuda_generate": (ci, [vp, ci, ci, ci, i32p, ip, ip]),
     "qasr_cuda_transcribe_ids": (ci, [vp, f32p, ci, ci, i32p, ip, vp, ip]),
+    "qasr_cuda_max_batch": (ci, [vp]),
+    "qasr_cuda_transcribe_batch": (ci, [vp, vp, i32p, ci, i32p, ci, i32p, i32p, vp]),
     "qasr_cuda_stage_audio": (ci, [vp, f32p, ci]),
     "qasr_cuda_transcribe_staged": (ci, [vp, ci, i32p, ip, vp, ip]),
     "qasr_cuda_timer_start": (ci, [vp]),
@@ -246,6 +248,25 @@ class QasrCuda:
                                                    tm.ctypes.data_as(vp), C.byref(T)))
         return ids[:n.value].copy(), dict(mel_ms=tm[0], enc_ms=tm[1], prefill_ms=tm[2], decode_ms=tm[3],
                                           enc_tokens=T.value)
+
+    @property
+    def max_batch(self):
+        return int(self.lib.qasr_cuda_max_batch(self.ctx))
+
+    def transcribe_batch(self, units, max_new):
+        """Independent segments / utterances decoded together (up to `max_batch` per decode step).
+        units: list of f32 sample arrays; max_new: int or per-unit list.  Returns ([ids_i], timings dict)."""
+        units = [_f32(u) for u in units]
+        n = len(units)
+        caps = np.ascontiguousarray([max_new] * n if np.isscalar(max_new) else list(max_new), np.int32)
+        stride = int(caps.max()) if n else 1
+        ptrs = (C.c_void_p * max(n, 1))(*[u.ctypes.data for u in units])
+        lens = np.ascontiguousarray([len(u) for u in units], np.int32)
+        ids = np.zeros((max(n, 1), stride), np.int32)
+        cnt = np.zeros(max(n, 1), np.int32)
+        tm = np.zeros(4, np.float64)
+        self._ck(self.lib.qasr_cuda_transcribe_batch(self.ctx, C.cast(ptrs, vp), lens, n, caps, stride, ids, cnt, tm.ctypes.data_as(vp)))
+        return [ids[i, :cnt[i]].copy() for i in range(n)], dict(mel_ms=tm[0], enc_ms=tm[1], prefill_ms=tm[2], decode_ms=tm[3])
 
     # ---- benchmark plumbing
     def stage_audio(self, samples):

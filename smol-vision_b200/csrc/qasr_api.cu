@@ -95,7 +95,10 @@ struct qasr_ctx {
     float *rope_cos = nullptr, *rope_sin = nullptr;
     int rope_cap = 0;
     // KV cache f32 [layers][kv_max][kv_heads*hd]
-    float *kv_k = nullptr, *kv_v = nullptr;
+    float *kv_k = nullptr, *kv_v = nullptr; // cache of the CURRENT sequence (kv_ks[seq]); seq 0 = the single-sequence API
+    float *kv_ks[QASR_STREAM_MAX_SEQS] = {}, *kv_vs[QASR_STREAM_MAX_SEQS] = {}; // batched decode: one cache per sequence, same capacity
+    int kv_fill[QASR_STREAM_MAX_SEQS] = {};  // valid rows per sequence (what a growth has to preserve)
+    int seq = 0;
     int kv_max = 0;
     // decode-step state
     float *x = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *attn_part = nullptr, *logits = nullptr,
@@ -194,7 +197,8 @@ void qasr_cuda_free(qasr_ctx_t *c) {
     if (c->graph) cudaGraphDestroy(c->graph);
     for (auto &ge : c->graph_cache) cudaGraphExecDestroy(ge.exec);
     for (void *p : c->owned) cudaFree(p);
-    cudaFree(c->kv_k); cudaFree(c->kv_v); cudaFree(c->rope_cos); cudaFree(c->rope_sin);
+    for (int q = 0; q < QASR_STREAM_MAX_SEQS; q++) { cudaFree(c->kv_ks[q]); cudaFree(c->kv_vs[q]); }
+    cudaFree(c->rope_cos); cudaFree(c->rope_sin);
     if (c->h_tokens) cudaFreeHost(c->h_tokens);
     c->ws_samples.release(); c->ws_meltmp.release(); c->ws_mel.release(); c->ws_enc.release();
     c->ws_encout.release(); c->ws_pre.release(); c->ws_ids.release(); c->ws_geom.release();
@@ -390,26 +394,37 @@ static int ensure_rope(qasr_ctx_t *c, int need_pos) {
     return 0;
 }
 
-// KV cache growth keeps rows [0,keep) of every layer (reference kv_cache_grow, qwen_asr_decoder.c:179-206)
+// KV cache growth keeps rows [0,keep) of every layer (reference kv_cache_grow, qwen_asr_decoder.c:179-206).
+// All sequence caches share one capacity; a growth re-strides every allocated one (rows [0, kv_fill[q]) of the
+// others, rows [0, keep) of the current sequence).
+static void select_seq(qasr_ctx_t *c, int q) { c->seq = q; c->kv_k = c->kv_ks[q]; c->kv_v = c->kv_vs[q]; }
+
 static int ensure_kv(qasr_ctx_t *c, int need_pos, int keep) {
-    if (need_pos <= c->kv_max) return 0;
+    const size_t kvd = (size_t)c->kv_heads * c->hd;
+    if (need_pos <= c->kv_max && c->kv_ks[c->seq]) return 0;
     int cap = c->kv_max ? c->kv_max : 2048;
     while (cap < need_pos) cap *= 2;
-    const size_t kvd = (size_t)c->kv_heads * c->hd;
     const size_t bytes = (size_t)c->dec_layers * cap * kvd * 4;
-    float *nk = nullptr, *nv = nullptr;
     CK(cudaStreamSynchronize(c->stream));
-    if (cudaMalloc(&nk, bytes) != cudaSuccess || cudaMalloc(&nv, bytes) != cudaSuccess) {
-        cudaGetLastError(); cudaFree(nk);
-        return set_err(QASR_ERR_NOMEM, "KV cache allocation of %zu bytes failed", 2 * bytes);
-    }
-    if (c->kv_k && keep > 0)
-        for (int l = 0; l < c->dec_layers; l++) {
-            CK(cudaMemcpy(nk + (size_t)l * cap * kvd, c->kv_k + (size_t)l * c->kv_max * kvd, (size_t)keep * kvd * 4, cudaMemcpyDeviceToDevice));
-            CK(cudaMemcpy(nv + (size_t)l * cap * kvd, c->kv_v + (size_t)l * c->kv_max * kvd, (size_t)keep * kvd * 4, cudaMemcpyDeviceToDevice));
+    for (int q = 0; q < QASR_STREAM_MAX_SEQS; q++) {
+        if (!c->kv_ks[q] && q != c->seq) continue;
+        if (c->kv_ks[q] && cap == c->kv_max) continue;
+        float *nk = nullptr, *nv = nullptr;
+        if (cudaMalloc(&nk, bytes) != cudaSuccess || cudaMalloc(&nv, bytes) != cudaSuccess) {
+            cudaGetLastError(); cudaFree(nk);
+            return set_err(QASR_ERR_NOMEM, "KV cache allocation of %zu bytes failed", 2 * bytes);
         }
-    cudaFree(c->kv_k); cudaFree(c->kv_v);
-    c->kv_k = nk; c->kv_v = nv; c->kv_max = cap;
+        const int rows = q == c->seq ? keep : c->kv_fill[q];
+        if (c->kv_ks[q] && rows > 0)
+            for (int l = 0; l < c->dec_layers; l++) {
+                CK(cudaMemcpy(nk + (size_t)l * cap * kvd, c->kv_ks[q] + (size_t)l * c->kv_max * kvd, (size_t)rows * kvd * 4, cudaMemcpyDeviceToDevice));
+                CK(cudaMemcpy(nv + (size_t)l * cap * kvd, c->kv_vs[q] + (size_t)l * c->kv_max * kvd, (size_t)rows * kvd * 4, cudaMemcpyDeviceToDevice));
+            }
+        cudaFree(c->kv_ks[q]); cudaFree(c->kv_vs[q]);
+        c->kv_ks[q] = nk; c->kv_vs[q] = nv;
+    }
+    c->kv_max = cap;
+    select_seq(c, c->seq);
     c->ws_gen++;
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
     return 0;
@@ -524,14 +539,14 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
     // decode-step state
     auto dalloc = [&](size_t bytes) -> void * { void *p = dev_alloc(c, bytes); if (p) cudaMemset(p, 0, bytes); return p; };
     c->n_parts = argmax_num_parts(c->V);
-    c->x = (float *)dalloc((size_t)H * 4); c->pending = (float *)dalloc((size_t)H * 4);
+    c->x = (float *)dalloc((size_t)QASR_STREAM_MAX_SEQS * H * 4); c->pending = (float *)dalloc((size_t)H * 4);
     c->qkv = (float *)dalloc(4096 * 4); c->attn = (float *)dalloc(2048 * 4); c->act = (float *)dalloc((size_t)I * 4);
     c->attn_part = (float *)dalloc((size_t)8 * QASR_ATTN_SPLITS * 2 * QASR_ATTN_PART_STRIDE * 4);
     c->logits = (float *)dalloc((size_t)c->V * 4);
     c->part_val = (float *)dalloc((size_t)c->n_parts * 4); c->part_idx = (int *)dalloc((size_t)c->n_parts * 4);
     c->counters = (unsigned *)dalloc(8 * 4);
-    c->d_pos = (int *)dalloc(4); c->d_done = (int *)dalloc(4); c->d_step = (int *)dalloc(4);
-    c->d_tokens = (int *)dalloc((size_t)c->max_steps * 4);
+    c->d_pos = (int *)dalloc(4 * QASR_STREAM_MAX_SEQS); c->d_done = (int *)dalloc(4); c->d_step = (int *)dalloc(4);
+    c->d_tokens = (int *)dalloc((size_t)c->max_steps * QASR_STREAM_MAX_SEQS * 4);
     c->d_gmax = (int *)dalloc(4);
     c->head_val = (float *)dalloc(1024 * 4); c->head_idx = (int *)dalloc(1024 * 4);
     c->grid_bar = (unsigned *)dalloc(64 * 4);
@@ -569,14 +584,15 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
         if (stream_build_image(c->stream, c->dec_layers, H, I, c->V, mats.data(), c->emb, c->sk_cta_off, c->sk_image) != 0)
             return set_err(QASR_ERR_CUDA, "%s", stream_error());
         CK(cudaStreamSynchronize(c->stream));
-        c->ll_qkv = (unsigned long long *)dalloc(4096 * 8); c->ll_att = (unsigned long long *)dalloc((size_t)QASR_STREAM_ATT_WORDS * 8);
-        c->ll_xwo = (unsigned long long *)dalloc((size_t)H * 8); c->ll_act = (unsigned long long *)dalloc((size_t)I * 8);
-        c->ll_xdn = (unsigned long long *)dalloc((size_t)H * 8); c->ll_head = (unsigned long long *)dalloc((size_t)2 * 1024 * 8);
+        const size_t NS = QASR_STREAM_MAX_SEQS;
+        c->ll_qkv = (unsigned long long *)dalloc(NS * 4096 * 8); c->ll_att = (unsigned long long *)dalloc(NS * QASR_STREAM_ATT_WORDS * 8);
+        c->ll_xwo = (unsigned long long *)dalloc(NS * H * 8); c->ll_act = (unsigned long long *)dalloc(NS * I * 8);
+        c->ll_xdn = (unsigned long long *)dalloc(NS * H * 8); c->ll_head = (unsigned long long *)dalloc(NS * 2048 * 8);
         if (!c->ll_head) return set_err(QASR_ERR_NOMEM, "exchange buffers");
     }
     if (getenv("QASR_MEGA_PROF")) c->mega_prof = (long long *)dalloc(3 * 4096 * 8);
     if (!c->x || !c->logits || !c->d_gmax) return set_err(QASR_ERR_NOMEM, "state allocation failed");
-    CK(cudaHostAlloc((void **)&c->h_tokens, (size_t)c->max_steps * 4, cudaHostAllocMapped));
+    CK(cudaHostAlloc((void **)&c->h_tokens, (size_t)c->max_steps * QASR_STREAM_MAX_SEQS * 4, cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void **)&c->dh_tokens, c->h_tokens, 0));
     CKR(ensure_kv(c, 2048, 0));
     CKR(ensure_rope(c, 4096));
@@ -821,7 +837,8 @@ static int prefill_device(qasr_ctx_t *c, int P, int kv_len) {
     }
     return 0;
     };
-    CKR(run_cached_graph(c, 2, P, (long long)kv_len * 8 + c->nsplit, enqueue));
+    CKR(run_cached_graph(c, 2, P, (long long)kv_len * 8 + c->nsplit + ((long long)c->seq << 48), enqueue));
+    c->kv_fill[c->seq] = kv_len + P;
     CK(cudaGetLastError());
     return 0;
 }
@@ -914,7 +931,8 @@ static int ensure_graph(qasr_ctx_t *c) {
 }
 
 // Enqueue n greedy steps (each consumes c->x, leaves the next embedding in c->x).
-static int enqueue_steps(qasr_ctx_t *c, int n) {
+static int enqueue_steps(qasr_ctx_t *c, int n, int nseq = 1) {
+    if (nseq != 1 && !c->use_stream) return set_err(QASR_ERR_STATE, "batched decode needs the stream kernel (unset QASR_DECODE)");
     if (c->use_stream) { // one persistent cooperative launch runs all n steps (stops itself after an EOS token)
         StreamParams p;
         p.image = c->sk_image; p.cta_off = c->sk_cta_off;
@@ -925,14 +943,17 @@ static int enqueue_steps(qasr_ctx_t *c, int n) {
             p.in_norm[l] = L.in_norm; p.post_norm[l] = L.post_norm; p.qn[l] = L.qn; p.kn[l] = L.kn;
         }
         p.x_io = c->x;
-        p.kv_k = c->kv_k; p.kv_v = c->kv_v; p.kv_layer_stride = (size_t)c->kv_max * c->kv_heads * c->hd;
+        p.nseq = nseq;
+        for (int q = 0; q < QASR_STREAM_MAX_SEQS; q++) { p.kv_k[q] = nseq == 1 ? c->kv_k : c->kv_ks[q]; p.kv_v[q] = nseq == 1 ? c->kv_v : c->kv_vs[q]; }
+        p.kv_layer_stride = (size_t)c->kv_max * c->kv_heads * c->hd;
         p.rope_cos = c->rope_cos; p.rope_sin = c->rope_sin;
         p.ll_qkv = c->ll_qkv; p.ll_att = c->ll_att; p.ll_xwo = c->ll_xwo; p.ll_act = c->ll_act; p.ll_xdn = c->ll_xdn; p.ll_head = c->ll_head;
         const unsigned span = (unsigned)n * (unsigned)(c->dec_layers + 1) + 1;
         if (c->sk_tag > 0xF0000000u) { // tag space exhausted: clear the exchange buffers and start over
-            CK(cudaMemsetAsync(c->ll_qkv, 0, 4096 * 8, c->stream)); CK(cudaMemsetAsync(c->ll_att, 0, (size_t)QASR_STREAM_ATT_WORDS * 8, c->stream));
-            CK(cudaMemsetAsync(c->ll_xwo, 0, (size_t)c->H * 8, c->stream)); CK(cudaMemsetAsync(c->ll_act, 0, (size_t)c->I * 8, c->stream));
-            CK(cudaMemsetAsync(c->ll_xdn, 0, (size_t)c->H * 8, c->stream)); CK(cudaMemsetAsync(c->ll_head, 0, (size_t)2 * 1024 * 8, c->stream));
+            const size_t NS = QASR_STREAM_MAX_SEQS;
+            CK(cudaMemsetAsync(c->ll_qkv, 0, NS * 4096 * 8, c->stream)); CK(cudaMemsetAsync(c->ll_att, 0, NS * QASR_STREAM_ATT_WORDS * 8, c->stream));
+            CK(cudaMemsetAsync(c->ll_xwo, 0, NS * c->H * 8, c->stream)); CK(cudaMemsetAsync(c->ll_act, 0, NS * c->I * 8, c->stream));
+            CK(cudaMemsetAsync(c->ll_xdn, 0, NS * c->H * 8, c->stream)); CK(cudaMemsetAsync(c->ll_head, 0, NS * 2048 * 8, c->stream));
             c->sk_tag = 1;
         }
         p.tag_base = c->sk_tag;
@@ -1151,6 +1172,107 @@ int qasr_cuda_transcribe_ids(qasr_ctx_t *c, const float *samples, int n_samples,
                              double *timings_ms, int *out_enc_tokens) {
     if (!samples) return set_err(QASR_ERR_ARG, "null samples");
     return transcribe_impl(c, samples, n_samples, max_new, out_ids, out_n, timings_ms, out_enc_tokens);
+}
+
+// ------------------------------------------------------------------ batched segments / utterances
+// Independent units (reference: the segments of -S mode, qwen_asr.c:941-1103, or separate files) are decoded
+// B at a time by one decode_stream_kernel launch: sequence s rides in MMA columns 2s, 2s+1, so B greedy tokens
+// cost the weight traffic of one.  Front end, encoder and prefill still run per unit into that unit's KV cache.
+int qasr_cuda_max_batch(const qasr_ctx_t *c) {
+    if (!c || !c->loaded) return 0;
+    return c->use_stream ? stream_max_seqs(c->H, c->I) : 1;
+}
+
+static int transcribe_group(qasr_ctx_t *c, const float *const *samples, const int *n_samples, int B, const int *max_new, int ids_stride,
+                            int *out_ids, int *out_n, double *tm) {
+    static const int PRE[] = {151644, 8948, 198, 151645, 198, 151644, 872, 198, 151669}; // qwen_asr.c:388-393
+    static const int SUF[] = {151670, 151645, 198, 151644, 77091, 198};                  // qwen_asr.c:394-396
+    int kv0[QASR_STREAM_MAX_SEQS] = {}, n[QASR_STREAM_MAX_SEQS] = {};
+    bool done[QASR_STREAM_MAX_SEQS] = {};
+    int cap_new = 0;
+    for (int q = 0; q < B; q++) {
+        select_seq(c, q);
+        c->kv_fill[q] = 0;
+        int frames = 0, T = 0;
+        CK(cudaEventRecord(c->ev[0], c->stream));
+        CKR(mel_device(c, samples[q], n_samples[q], &frames));
+        CK(cudaEventRecord(c->ev[2], c->stream));
+        CKR(encode_device(c, c->ws_mel.as<float>(), frames, &T));
+        CK(cudaEventRecord(c->ev[3], c->stream));
+        CKR(prefill_prompt_device(c, PRE, 9, T, SUF, 6, 0));
+        CK(cudaMemcpyAsync(c->x + (size_t)q * c->H, c->pending, (size_t)c->H * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaEventRecord(c->ev[4], c->stream));
+        CK(cudaEventSynchronize(c->ev[4]));
+        c->has_pending = false;
+        if (tm) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, c->ev[0], c->ev[2]); cudaEventElapsedTime(&b, c->ev[2], c->ev[3]); cudaEventElapsedTime(&d, c->ev[3], c->ev[4]);
+            tm[0] += a; tm[1] += b; tm[2] += d;
+        }
+        kv0[q] = 9 + T + 6 - 1;
+        if (max_new[q] > cap_new) cap_new = max_new[q];
+    }
+    int cap = 0;
+    for (int q = 0; q < B; q++) if (kv0[q] > cap) cap = kv0[q];
+    cap += cap_new + 34; // finished sequences keep stepping until the whole group is done
+    for (int q = 0; q < B; q++) { select_seq(c, q); CKR(ensure_kv(c, cap, kv0[q])); }
+    CKR(ensure_rope(c, cap));
+    select_seq(c, 0);
+    launch_set_state(c->stream, c->d_pos, kv0[0], c->d_done, 0, c->d_step, 0);
+    CK(cudaMemcpyAsync(c->d_pos, kv0, sizeof(int) * B, cudaMemcpyHostToDevice, c->stream));
+    c->launches += 1;
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    long long ksteps = 0;
+    bool first = true;
+    for (;;) {
+        int chunk = 0;
+        for (int q = 0; q < B; q++) if (!done[q] && max_new[q] - n[q] > chunk) chunk = max_new[q] - n[q];
+        if (chunk <= 0) break;
+        if (first) chunk = 1; // the step on the pending prompt row (reference qwen_asr.c:769)
+        if (chunk > 16) chunk = 16;
+        if (!first) { launch_set_state(c->stream, c->d_step, 0, c->d_done, 0, c->d_step, 0); c->launches += 1; }
+        CKR(enqueue_steps(c, chunk, B));
+        CK(cudaStreamSynchronize(c->stream));
+        ksteps += chunk;
+        for (int i = 0; i < chunk; i++)
+            for (int q = 0; q < B; q++) {
+                if (done[q]) continue;
+                const int tok = c->h_tokens[i * B + q];
+                out_ids[(size_t)q * ids_stride + n[q]++] = tok;
+                if (tok == QASR_TOKEN_ENDOFTEXT || tok == QASR_TOKEN_IM_END || n[q] >= max_new[q]) done[q] = true;
+            }
+        first = false;
+    }
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->last_decode_ms = ms;
+    c->decode_ms_total += ms;
+    c->decode_steps_total += ksteps;
+    if (tm) tm[3] += ms;
+    for (int q = 0; q < B; q++) { out_n[q] = n[q]; c->kv_fill[q] = 0; }
+    c->x_token = -1;
+    return 0;
+}
+
+int qasr_cuda_transcribe_batch(qasr_ctx_t *c, const float *const *samples, const int *n_samples, int count, const int *max_new,
+                               int ids_stride, int *out_ids, int *out_n, double *timings_ms) {
+    if (!c || !samples || !n_samples || !max_new || !out_ids || !out_n || count < 0) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
+    for (int i = 0; i < count; i++)
+        if (!samples[i] || max_new[i] < 1 || max_new[i] > ids_stride) return set_err(QASR_ERR_ARG, "unit %d: null samples or max_new outside [1, ids_stride]", i);
+    CK(cudaSetDevice(c->device));
+    if (timings_ms) timings_ms[0] = timings_ms[1] = timings_ms[2] = timings_ms[3] = 0.0;
+    const int maxb = qasr_cuda_max_batch(c);
+    int i = 0;
+    while (i < count) {
+        int B = count - i >= 4 && maxb >= 4 ? 4 : (count - i >= 2 && maxb >= 2 ? 2 : 1);
+        CKR(transcribe_group(c, samples + i, n_samples + i, B, max_new + i, ids_stride, out_ids + (size_t)i * ids_stride, out_n + i, timings_ms));
+        i += B;
+    }
+    select_seq(c, 0);
+    return 0;
 }
 
 int qasr_cuda_stage_audio(qasr_ctx_t *c, const float *samples, int n_samples) {

@@ -78,14 +78,15 @@ struct StreamParams {
     const bf16_t *emb;                     // row-major tied embedding (next-input gather)
     const float *in_norm[28], *post_norm[28], *qn[28], *kn[28];
     const float *final_norm;
-    float *x_io;                           // [H] input row in / last gathered row out
-    float *kv_k, *kv_v;
+    int nseq;                              // sequences decoded together (1, 2 or 4): sequence s = MMA columns 2s, 2s+1
+    float *x_io;                           // [nseq][H] input rows in / last gathered rows out
+    float *kv_k[4], *kv_v[4];              // per-sequence KV caches
     size_t kv_layer_stride;
     const float *rope_cos, *rope_sin;      // [pos][64]
-    unsigned long long *ll_qkv, *ll_att, *ll_xwo, *ll_act, *ll_xdn, *ll_head; // {f32, tag} exchange buffers
+    unsigned long long *ll_qkv, *ll_att, *ll_xwo, *ll_act, *ll_xdn, *ll_head; // {f32, tag} exchange buffers, [nseq][...]
     unsigned tag_base;                     // tags of this launch: tag_base + step*(L+1) + layer + 1
-    int *d_pos, *d_step, *d_tokens;
-    volatile int *h_tokens;                // mapped pinned ring (may be NULL)
+    int *d_pos, *d_step, *d_tokens;        // d_pos[nseq]; d_tokens[step][nseq]
+    volatile int *h_tokens;                // mapped pinned ring [step][nseq] (may be NULL)
     long long *prof;                       // optional clock64 stamps [2][prof_cap] (CTA 0, last CTA) or NULL
     int prof_cap;
     int debug;
@@ -94,12 +95,14 @@ struct StreamParams {
 };
 int stream_init(void);
 int stream_grid(void);
+int stream_max_seqs(int H, int I);
 size_t stream_image_layout(int L, int H, int I, int V, unsigned long long *cta_off_host /* [grid+1] */);
 int stream_build_image(cudaStream_t s, int L, int H, int I, int V, const bf16_t *const *layer_mats /* [L*4] */, const bf16_t *emb,
                        const unsigned long long *d_cta_off, uint8_t *image);
 int launch_decode_stream(cudaStream_t s, const StreamParams &p);
 const char *stream_error(void);
-#define QASR_STREAM_ATT_WORDS (16 * 9 * 130) /* room for up to 9 key splits per head */
+#define QASR_STREAM_MAX_SEQS 4
+#define QASR_STREAM_ATT_WORDS (16 * 4 * 130) /* per sequence: 16 heads x SK_ATT_MAXS splits x (128 acc + m + l) */
 
 // ---- row-wise / prefill / encoder kernels (qasr_rows.cu)
 void launch_rmsnorm(cudaStream_t s, const float *x, const float *gamma, float eps, int M, int H, float *out_f32,

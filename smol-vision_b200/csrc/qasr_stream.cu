@@ -61,16 +61,6 @@
 
 typedef unsigned long long u64;
 
-struct SkSmem {
-    uint8_t ring[SK_WARPS][SK_SLOTS][SK_UNIT];            // 163840 B
-    uint32_t xf[SK_MAX_K];                                 // phase input, B-fragment order: [kb][8 lanes][2] (24576 B); attention scratch
-    float x[SK_MAX_H];                                     // residual stream (replicated in every CTA)
-    float partial[2][SK_CHUNK_GROUPS * 16][SK_PSTRIDE];    // [buffer][row in chunk][warp]
-    float red[64];
-    float ssq[SK_WARPS];                                   // per-warp sums of squares of the last normalised input
-    int redi[SK_WARPS];
-};
-
 // ---- static schedule, shared by the re-tiling kernel and the decode kernel ---------------------
 struct SkDims { int L, H, I, V, G; };
 __host__ __device__ __forceinline__ void sk_phase_shape(const SkDims &d, int wp, int &N, int &K) {
@@ -187,13 +177,6 @@ __device__ __forceinline__ uint32_t sk_pack_bf16(float a, float b) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(a, b); // .x = a (low half)
     return *reinterpret_cast<const uint32_t *>(&v);
 }
-// elements (2p, 2p+1) of the phase input -> hi / lo words of the B-fragment image
-__device__ __forceinline__ void sk_put_pair(uint32_t *xf, int p, float v0, float v1) {
-    const float h0 = __bfloat162float(__float2bfloat16_rn(v0)), h1 = __bfloat162float(__float2bfloat16_rn(v1));
-    const int kb = p >> 3, jj = p & 7, tig = jj & 3, reg = jj >> 2;
-    xf[kb * 16 + tig * 2 + reg] = sk_pack_bf16(v0, v1);               // lanes 0-3  (column 0: x_hi)
-    xf[kb * 16 + 8 + tig * 2 + reg] = sk_pack_bf16(v0 - h0, v1 - h1); // lanes 4-7  (column 1: x_lo)
-}
 __device__ __forceinline__ bool sk_better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
 
 __device__ __forceinline__ float sk_block_sum(float v, float *red, int tid) {
@@ -207,27 +190,63 @@ __device__ __forceinline__ float sk_block_sum(float v, float *red, int tid) {
     return t;
 }
 
+// Shared-memory carve-up (dynamic): ring | xf | x | partial | small.  NSEQ sequences share one launch: sequence s
+// occupies MMA columns 2s (x_hi) and 2s+1 (x_lo) of the m16n8k16 B operand, so up to 4 independent segments /
+// utterances are decoded for the weight traffic of one (the 6 columns a single sequence leaves idle are free).
+template <int NSEQ, int SLOTS>
+struct SkLayout {
+    static constexpr int CH_GROUPS = SK_CHUNK_GROUPS / NSEQ;   // 16-row groups reduced together
+    static constexpr int CH_ROWS = CH_GROUPS * 16;             // x NSEQ sequences = 128 epilogue threads
+    static constexpr size_t ring_bytes = (size_t)SK_WARPS * SLOTS * SK_UNIT;
+    static __host__ __device__ size_t xf_bytes(int kmax) { return (size_t)kmax * 4 * NSEQ; }            // [kb][8*NSEQ lanes][2] u32
+    static __host__ __device__ size_t x_bytes(int H) { return (size_t)NSEQ * H * 4; }
+    static constexpr size_t partial_bytes = (size_t)2 * 128 * SK_PSTRIDE * 4;
+    static constexpr size_t small_bytes = (64 + NSEQ * SK_WARPS + SK_WARPS) * 4;
+    static __host__ __device__ size_t total(int kmax, int H) { return ring_bytes + xf_bytes(kmax) + x_bytes(H) + partial_bytes + small_bytes + 1024; }
+};
+
+// elements (2p, 2p+1) of sequence s -> hi / lo words of the B-fragment image ([kb][lane = column*4 + tig][2 regs])
+template <int NSEQ>
+__device__ __forceinline__ void sk_put_pair(uint32_t *xf, int s, int p, float v0, float v1) {
+    const float h0 = __bfloat162float(__float2bfloat16_rn(v0)), h1 = __bfloat162float(__float2bfloat16_rn(v1));
+    const int kb = p >> 3, jj = p & 7, tig = jj & 3, reg = jj >> 2;
+    uint32_t *q = xf + kb * (16 * NSEQ) + 16 * s + tig * 2 + reg;
+    q[0] = sk_pack_bf16(v0, v1);            // column 2s   : x_hi
+    q[8] = sk_pack_bf16(v0 - h0, v1 - h1);  // column 2s+1 : x_lo
+}
+
+template <int NSEQ, int SLOTS>
 __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const StreamParams p) {
+    using LY = SkLayout<NSEQ, SLOTS>;
+    constexpr int CH_GROUPS = LY::CH_GROUPS, CH_ROWS = LY::CH_ROWS;
     extern __shared__ __align__(1024) uint8_t sk_raw[];
-    SkSmem &sm = *reinterpret_cast<SkSmem *>((reinterpret_cast<uintptr_t>(sk_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gid = lane >> 2, tig = lane & 3;
     const int b = blockIdx.x, G = gridDim.x;
     const int L = p.n_layers, H = p.H, I = p.I;
+    const int kmax = max(max(H, I), 2048);
+    uint8_t *sm0 = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sk_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sm_ring = sm0;
+    uint32_t *sm_xf = reinterpret_cast<uint32_t *>(sm0 + LY::ring_bytes);
+    float *sm_x = reinterpret_cast<float *>(sm0 + LY::ring_bytes + LY::xf_bytes(kmax));                  // [NSEQ][H] residual streams
+    float(*sm_partial)[128][SK_PSTRIDE] = reinterpret_cast<float(*)[128][SK_PSTRIDE]>(sm0 + LY::ring_bytes + LY::xf_bytes(kmax) + LY::x_bytes(H));
+    float *sm_red = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(sm_partial) + LY::partial_bytes); // [64]
+    float *sm_ssq = sm_red + 64;                                                                            // [NSEQ][16]
+    int *sm_redi = reinterpret_cast<int *>(sm_ssq + NSEQ * SK_WARPS);                                       // [16]
 
-    for (int e = tid; e < H; e += SK_THREADS) sm.x[e] = p.x_io[e];
+    for (int e = tid; e < NSEQ * H; e += SK_THREADS) sm_x[e] = p.x_io[e];
     __syncthreads();
 
     // ---- per-warp weight stream (contiguous, cyclic).  Every lane copies its own 4 x 16 B of each unit with
-    // cp.async (LDGSTS, L1 bypass, L2 evict-first) into its private bytes of the warp's SK_SLOTS-deep ring and
+    // cp.async (LDGSTS, L1 bypass, L2 evict-first) into its private bytes of the warp's SLOTS-deep ring and
     // later reads back exactly those bytes as its A fragments: a per-lane FIFO, so completion is tracked by the
-    // per-thread cp.async group counter alone (one group per unit, always SK_SLOTS groups outstanding).
+    // per-thread cp.async group counter alone (one group per unit, always SLOTS groups outstanding).
     const u64 coff = p.cta_off[b];
     const uint32_t slen = (uint32_t)((p.cta_off[b + 1] - coff) / SK_WARPS);
     const uint8_t *wbase = p.image + coff + (u64)warp * slen;
     const uint8_t *sbase = wbase + lane * 16;
     // Second-level prefetch, driven by the exchange waits: while a warp polls, it pulls the units that follow its
-    // ring (up to `l2_window` of them) into L2, so HBM keeps streaming during the stalls the 160 KB ring cannot
+    // ring (up to `l2_window` of them) into L2, so HBM keeps streaming during the stalls the ring cannot
     // cover; the later cp.async fetches then hit L2.  Nothing is issued while the consumer is HBM-bound.
     const unsigned l2_window = (unsigned)p.l2_ahead_units;
     unsigned fpos = 0, lpos = 0;
@@ -237,7 +256,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
     unsigned consumed = 0;
     u64 pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    const uint32_t ring0 = sk_smem_u32(sm.ring[warp][0]) + lane * 16;
+    const uint32_t ring0 = sk_smem_u32(sm_ring) + warp * (SLOTS * SK_UNIT) + lane * 16;
     auto fetch_into = [&](unsigned slot) { // next unit of the stream -> ring slot; always commits one group
         if (fsteps < p.n_steps) {
             const uint8_t *src = sbase + foff;
@@ -253,7 +272,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 #pragma unroll
-    for (int i = 0; i < SK_SLOTS; i++) fetch_into(i);
+    for (int i = 0; i < SLOTS; i++) fetch_into(i);
     auto top_up = [&]() { // service hook of every poll loop (runs converged: the loops are warp-uniform)
         if (lpos - fpos < l2_window) {
             if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + loff + lane * 128) : "memory");
@@ -263,132 +282,121 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
         }
     };
 
-    // ---- one weighted phase: y[row] = W[row,:] . x for the CTA's rows, handed to epi(row, r, rowsum)
-    // in chunks of <= 128 rows; `rowsum(r)` adds the 16 per-warp partials of chunk row r in fixed order.
+    // ---- one weighted phase: y[s][row] = W[row,:] . x_s for the CTA's rows, handed to epi(s, row, r, rowsum) in
+    // chunks of <= CH_ROWS rows; `rowsum(r)` adds the 16 per-warp partials of (sequence s, chunk row r) in fixed order.
     int pbuf = 0;
     auto run_phase = [&](int N, int K, auto &&epi) {
         const int g0 = sk_g0(N >> 4, b, G), g1 = sk_g0(N >> 4, b + 1, G), nj = K >> 10;
-        for (int cg0 = g0; cg0 < g1; cg0 += SK_CHUNK_GROUPS) {
-            const int cg1 = min(cg0 + SK_CHUNK_GROUPS, g1);
-            float(*part)[SK_PSTRIDE] = sm.partial[pbuf];
+        for (int cg0 = g0; cg0 < g1; cg0 += CH_GROUPS) {
+            const int cg1 = min(cg0 + CH_GROUPS, g1);
+            float(*part)[SK_PSTRIDE] = sm_partial[pbuf];
             for (int grp = cg0; grp < cg1; grp++) {
                 float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
                 for (int j = 0; j < nj; j++) {
                     const bool tr = (p.debug & 64) && p.prof && b == p.trace_cta && tid == 0 && consumed < 1300;
                     if (tr) p.prof[2 * p.prof_cap + 3 * consumed] = clock64();
-                    const uint2 *xb = reinterpret_cast<const uint2 *>(sm.xf) + (size_t)(warp + 16 * j) * 32 + (lane & 7);
+                    const uint2 *xb = reinterpret_cast<const uint2 *>(sm_xf) + (size_t)(warp + 16 * j) * (32 * NSEQ) + (lane & (8 * NSEQ - 1));
                     uint2 bb[4];
 #pragma unroll
                     for (int kb = 0; kb < 4; kb++) {
-                        bb[kb] = xb[kb * 8];
-                        if (lane >= 8) bb[kb] = make_uint2(0u, 0u);
+                        bb[kb] = xb[kb * (8 * NSEQ)];
+                        if (NSEQ < 4 && lane >= 8 * NSEQ) bb[kb] = make_uint2(0u, 0u);
                     }
-                    auto mma4 = [&](uint4 (&a)[4]) {
-                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(a[0].x), "r"(a[0].y), "r"(a[0].z), "r"(a[0].w), "r"(bb[0].x), "r"(bb[0].y));
-                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                     : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a[1].x), "r"(a[1].y), "r"(a[1].z), "r"(a[1].w), "r"(bb[1].x), "r"(bb[1].y));
-                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                     : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(a[2].x), "r"(a[2].y), "r"(a[2].z), "r"(a[2].w), "r"(bb[2].x), "r"(bb[2].y));
-                        asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                     : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a[3].x), "r"(a[3].y), "r"(a[3].z), "r"(a[3].w), "r"(bb[3].x), "r"(bb[3].y));
-                    };
-                    const unsigned slot = consumed % SK_SLOTS;
-                    asm volatile("cp.async.wait_group %0;" ::"n"(SK_SLOTS - 1) : "memory"); // this lane's bytes of the oldest unit have landed
+                    const unsigned slot = consumed % SLOTS;
+                    asm volatile("cp.async.wait_group %0;" ::"n"(SLOTS - 1) : "memory"); // this lane's bytes of the oldest unit have landed
                     if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 1] = clock64();
-                    const uint4 *tile = reinterpret_cast<const uint4 *>(sm.ring[warp][slot]) + lane;
+                    const uint4 *tile = reinterpret_cast<const uint4 *>(sm_ring + (size_t)(warp * SLOTS + slot) * SK_UNIT) + lane;
                     uint4 a[4];
 #pragma unroll
                     for (int kb = 0; kb < 4; kb++) a[kb] = tile[kb * 32];
-                    mma4(a);
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(a[0].x), "r"(a[0].y), "r"(a[0].z), "r"(a[0].w), "r"(bb[0].x), "r"(bb[0].y));
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a[1].x), "r"(a[1].y), "r"(a[1].z), "r"(a[1].w), "r"(bb[1].x), "r"(bb[1].y));
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3) : "r"(a[2].x), "r"(a[2].y), "r"(a[2].z), "r"(a[2].w), "r"(bb[2].x), "r"(bb[2].y));
+                    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3) : "r"(a[3].x), "r"(a[3].y), "r"(a[3].z), "r"(a[3].w), "r"(bb[3].x), "r"(bb[3].y));
                     if (tr) p.prof[2 * p.prof_cap + 3 * consumed + 2] = clock64();
                     consumed++;
                     fetch_into(slot); // the freed slot immediately takes the next unit (possibly of a later phase / token)
                 }
-                if (tig == 0) { // column 0 = x_hi sums, column 1 = x_lo sums; rows gid and gid+8
-                    const int r = (grp - cg0) * 16 + gid;
+                if (tig < NSEQ) { // D columns (2 tig, 2 tig + 1) = x_hi / x_lo sums of sequence tig; rows gid and gid+8
+                    const int r = tig * CH_ROWS + (grp - cg0) * 16 + gid;
                     part[r][warp] = (c0 + d0) + (c1 + d1);
                     part[r + 8][warp] = (c2 + d2) + (c3 + d3);
                 }
             }
             sk_csync();
             const int rows = (cg1 - cg0) * 16;
-            if (tid < rows) {
+            const int es = tid / CH_ROWS, er = tid - es * CH_ROWS; // epilogue thread <-> (sequence, chunk row)
+            if (tid < NSEQ * CH_ROWS && er < rows) {
                 auto rowsum = [&](int r) {
                     float y = 0.0f;
 #pragma unroll
-                    for (int i = 0; i < SK_WARPS; i++) y += part[r][i];
+                    for (int i = 0; i < SK_WARPS; i++) y += part[es * CH_ROWS + r][i];
                     return y;
                 };
-                epi(cg0 * 16 + tid, tid, rowsum);
+                epi(es, cg0 * 16 + er, er, rowsum);
             }
             pbuf ^= 1; // the next chunk / phase writes the other buffer: one bar.sync per chunk is enough
         }
     };
 
-    // x (shared, or gathered from an exchange buffer first) -> RMSNorm -> B-fragment image
-    // Sentinel pre-poll: one word per producer CTA (the last row it writes) before the batch load, so the lines
-    // being written are not hammered by 148 x 512 polling threads (tools/microbench/ll_exchange.cu: 1.1 vs 1.7 us).
-    auto wait_producers = [&](const u64 *buf, int NG, int rows_per_word_shift, unsigned tag) {
-        if (!(p.debug & 2)) return;
-        bool ok = true;
-        const u64 *w = buf;
-        if (tid < G) {
-            const int g0 = sk_g0(NG, tid, G), g1 = sk_g0(NG, tid + 1, G);
-            ok = g1 <= g0;
-            w = buf + ((g1 * 16) >> rows_per_word_shift) - 1;
-        }
-        for (;;) {
-            if (!ok) ok = (unsigned)(ll_load1(w) >> 32) == tag;
-            if (__all_sync(QASR_FULL, ok)) break;
-        }
-        sk_csync();
-    };
     // x (shared, or gathered from an exchange buffer first) -> x * gamma -> B-fragment image.  The RMSNorm scale
     // 1/sqrt(mean(x^2)+eps) is a scalar, so it is applied to the phase OUTPUT (norm_scale() in the epilogue):
     // the block reduction of the squares leaves the critical path between the gather and the first MMA.
-    auto stage_norm = [&](const u64 *src, unsigned tag, const float2 (&gm)[2]) {
-        float v[2][2];
-        const int npairs = H >> 1;
+    // All NSEQ vectors are gathered as one long vector (pair q = s * H/2 + pr), every load in flight before the first check.
+    constexpr int NPX = NSEQ == 4 ? 4 : 2 * NSEQ; // 512 threads x NPX pairs cover NSEQ x H/2 (NSEQ = 4 only with H = 1024)
+    auto stage_norm = [&](const u64 *src, unsigned tag, const float *gamma) {
+        float v[NPX][2];
+        const int hp = H >> 1, npairs = NSEQ * hp;
         if (src) {
-            wait_producers(src, H >> 4, 0, tag);
-            ll_gather_pairs<2>(src, npairs, tag, tid, v, top_up);
+            ll_gather_pairs<NPX>(src, npairs, tag, tid, v, top_up);
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const int pr = tid + i * SK_THREADS;
-                if (pr < npairs) *reinterpret_cast<float2 *>(sm.x + 2 * pr) = make_float2(v[i][0], v[i][1]);
+            for (int i = 0; i < NPX; i++) {
+                const int q = tid + i * SK_THREADS;
+                if (q < npairs) *reinterpret_cast<float2 *>(sm_x + 2 * q) = make_float2(v[i][0], v[i][1]);
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const int pr = tid + i * SK_THREADS;
-                const float2 t = pr < npairs ? *reinterpret_cast<const float2 *>(sm.x + 2 * pr) : make_float2(0.f, 0.f);
+            for (int i = 0; i < NPX; i++) {
+                const int q = tid + i * SK_THREADS;
+                const float2 t = q < npairs ? *reinterpret_cast<const float2 *>(sm_x + 2 * q) : make_float2(0.f, 0.f);
                 v[i][0] = t.x; v[i][1] = t.y;
             }
         }
-        float ss = 0.0f;
+        // pair q belongs to sequence q / hp; with hp a multiple of 512 (H = 1024, 2048) each i maps to ONE sequence per thread
+        float ss[NSEQ];
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int pr = tid + i * SK_THREADS;
-            ss = fmaf(v[i][0], v[i][0], fmaf(v[i][1], v[i][1], ss));
-            if (pr < npairs) sk_put_pair(sm.xf, pr, v[i][0] * gm[i].x, v[i][1] * gm[i].y);
+        for (int s = 0; s < NSEQ; s++) ss[s] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NPX; i++) {
+            const int q = tid + i * SK_THREADS;
+            if (q < npairs) {
+                const int s = q / hp, pr = q - s * hp;
+                const float2 gm = __ldg(reinterpret_cast<const float2 *>(gamma) + pr);
+                const float sq = fmaf(v[i][0], v[i][0], v[i][1] * v[i][1]);
+#pragma unroll
+                for (int t = 0; t < NSEQ; t++) if (t == s) ss[t] += sq;
+                sk_put_pair<NSEQ>(sm_xf, s, pr, v[i][0] * gm.x, v[i][1] * gm.y);
+            }
         }
-        ss = warp_sum(ss);
-        if (lane == 0) sm.ssq[warp] = ss;
+#pragma unroll
+        for (int s = 0; s < NSEQ; s++) {
+            const float t = warp_sum(ss[s]);
+            if (lane == 0) sm_ssq[s * SK_WARPS + warp] = t;
+        }
         sk_csync();
     };
-    auto norm_scale = [&]() {
+    auto norm_scale = [&](int s) {
         float t = 0.0f;
 #pragma unroll
-        for (int w = 0; w < SK_WARPS; w++) t += sm.ssq[w];
+        for (int w = 0; w < SK_WARPS; w++) t += sm_ssq[s * SK_WARPS + w];
         return 1.0f / sqrtf(t / (float)H + p.eps);
     };
-    auto load_gamma = [&](const float *g, float2 (&gm)[2]) {
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-            const int pr = tid + i * SK_THREADS;
-            gm[i] = pr < (H >> 1) ? __ldg(reinterpret_cast<const float2 *>(g) + pr) : make_float2(0.f, 0.f);
-        }
+    auto warm_gamma = [&](const float *g) { // pull the norm weights towards L1/L2 before the exchange wait
+        if (tid < (H >> 5)) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + tid * 32) : "memory");
     };
 
     long long *prof = (p.prof && (b == 0 || b == G - 1) && tid == 0) ? p.prof + (b == 0 ? 0 : p.prof_cap) : nullptr;
@@ -397,63 +405,72 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
 
     const size_t kvd = 1024;
     const float scale = 0.08838834764831845f; // 1/sqrtf(128)
-    int pos = *p.d_pos;
+    int pos[NSEQ];
+#pragma unroll
+    for (int s = 0; s < NSEQ; s++) pos[s] = p.d_pos[s];
+    unsigned done_mask = 0; // sequences that have produced an EOS token (they keep running; the host cuts their ids)
     int step = 0;
     bool stop = false;
+    const size_t att_words = (size_t)16 * SK_ATT_MAXS * SK_ATT_STRIDE;
 
     for (; step < p.n_steps && !stop; step++) {
-        const float4 rope_c = __ldg(reinterpret_cast<const float4 *>(p.rope_cos + (size_t)pos * 64) + (lane & 15));
-        const float4 rope_s = __ldg(reinterpret_cast<const float4 *>(p.rope_sin + (size_t)pos * 64) + (lane & 15));
+        // attention role of this CTA for the whole step: (sequence sa, q head hq, key split sp of S)
+        int maxkeys = 0;
+#pragma unroll
+        for (int s = 0; s < NSEQ; s++) maxkeys = max(maxkeys, pos[s] + 1);
+        int S = (maxkeys + SK_ATT_BATCH * SK_WARPS - 1) / (SK_ATT_BATCH * SK_WARPS);
+        S = min(S, min(SK_ATT_MAXS, G / (16 * NSEQ)));
+        const bool att = b < NSEQ * 16 * S;
+        const int sa = att ? b / (16 * S) : 0, hq = (b - sa * 16 * S) / S, sp = b - sa * 16 * S - hq * S, hkv = hq >> 1;
+        int apos = pos[0];
+#pragma unroll
+        for (int s = 1; s < NSEQ; s++) if (s == sa) apos = pos[s];
+        const int n_keys = apos + 1;
+        const int per = (n_keys + S - 1) / S;
+        const int k0 = sp * per, k1 = min(n_keys, k0 + per);
+        const float4 rope_c = __ldg(reinterpret_cast<const float4 *>(p.rope_cos + (size_t)apos * 64) + (lane & 15));
+        const float4 rope_s = __ldg(reinterpret_cast<const float4 *>(p.rope_sin + (size_t)apos * 64) + (lane & 15));
         for (int l = 0; l < L; l++) {
             const unsigned tag = p.tag_base + (unsigned)(step * (L + 1) + l + 1);
-            float *kc = p.kv_k + (size_t)l * p.kv_layer_stride, *vc = p.kv_v + (size_t)l * p.kv_layer_stride;
-            // attention role of this CTA: q head hq, key split sp of S
-            const int n_keys = pos + 1;
-            int S = (n_keys + SK_ATT_BATCH * SK_WARPS - 1) / (SK_ATT_BATCH * SK_WARPS);
-            S = S > SK_ATT_MAXS ? SK_ATT_MAXS : S;
-            const bool att = b < 16 * S;
-            const int hq = b / S, sp = b - hq * S, hkv = hq >> 1;
-            const int per = (n_keys + S - 1) / S;
-            const int k0 = sp * per, k1 = min(n_keys, k0 + per);
+            float *kc = p.kv_k[sa] + (size_t)l * p.kv_layer_stride, *vc = p.kv_v[sa] + (size_t)l * p.kv_layer_stride;
             if (att) // K/V rows of this split -> L2 while the QKV phase runs
-                if (!(p.debug & 8))
-                    for (int j = k0 * 8 + tid; j < k1 * 8 && j < pos * 8; j += SK_THREADS) { // 8 lines of 128 B per key (K row + V row)
-                        const float *row = ((j & 4) ? vc : kc) + (size_t)(j >> 3) * kvd + hkv * 128 + (j & 3) * 32;
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row) : "memory");
-                    }
+                for (int j = k0 * 8 + tid; j < k1 * 8 && j < apos * 8; j += SK_THREADS) { // 8 lines of 128 B per key (K row + V row)
+                    const float *row = ((j & 4) ? vc : kc) + (size_t)(j >> 3) * kvd + hkv * 128 + (j & 3) * 32;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row) : "memory");
+                }
             // small per-layer parameters: issue the loads now, use them after the exchange waits
-            float2 g_in[2], g_post[2];
-            load_gamma(p.in_norm[l], g_in);
-            load_gamma(p.post_norm[l], g_post);
+            warm_gamma(p.in_norm[l]);
+            warm_gamma(p.post_norm[l]);
             const float4 qn4 = __ldg(reinterpret_cast<const float4 *>(p.qn[l]) + lane), kn4 = __ldg(reinterpret_cast<const float4 *>(p.kn[l]) + lane);
             mark();
             // ---------------- QKV
-            stage_norm(l > 0 ? p.ll_xdn : nullptr, tag - 1, g_in);
+            stage_norm(l > 0 ? p.ll_xdn : nullptr, tag - 1, p.in_norm[l]);
             mark();
-            run_phase(4096, H, [&](int row, int r, auto &&rowsum) { ll_store(p.ll_qkv + row, rowsum(r) * norm_scale(), tag); });
+            run_phase(4096, H, [&](int s, int row, int r, auto &&rowsum) { ll_store(p.ll_qkv + s * 4096 + row, rowsum(r) * norm_scale(s), tag); });
             mark();
             // ---------------- ATTN (attention CTAs only): everything up to the final merge is warp-local.
             // Every warp gathers q of the head itself (4 dims per lane), RMS-normalises and ropes it with shuffles;
             // the warp that owns the new key does the same for k and appends k/v to the cache.  The K/V rows of the
             // cached keys do not depend on this layer's output: their loads are issued BEFORE the q words are polled.
             if (att) {
-                float *sc = reinterpret_cast<float *>(sm.xf); // the QKV input image is dead: attention scratch
+                float *sc = reinterpret_cast<float *>(sm_xf); // the QKV input image is dead: attention scratch
                 float *wacc = sc, *wml = sc + SK_WARPS * 128;
                 const bool has_new = (k1 == n_keys) && (k0 < k1);
-                const int w_new = has_new ? ((pos - k0) & (SK_WARPS - 1)) : -1; // warp whose key list contains `pos`
+                const int w_new = has_new ? ((apos - k0) & (SK_WARPS - 1)) : -1; // warp whose key list contains `apos`
                 const size_t hoff = (size_t)hkv * 128 + lane * 4;
                 float4 kr[SK_ATT_BATCH], vr[SK_ATT_BATCH];
 #pragma unroll
                 for (int i = 0; i < SK_ATT_BATCH; i++) {
                     const int j = k0 + warp + SK_WARPS * i;
-                    if (j < k1 && j != pos) {
+                    if (j < k1 && j != apos) {
                         kr[i] = __ldcg(reinterpret_cast<const float4 *>(kc + (size_t)j * kvd + hoff));
                         vr[i] = __ldcg(reinterpret_cast<const float4 *>(vc + (size_t)j * kvd + hoff));
                     }
                 }
                 // q (all warps), k and v (owning warp): 4 consecutive words per lane
                 u64 wq[4], wk[4], wv[4];
-                const u64 *pq = p.ll_qkv + hq * 128 + lane * 4, *pk = p.ll_qkv + 2048 + hkv * 128 + lane * 4, *pv = pk + 1024;
+                const u64 *qkv = p.ll_qkv + sa * 4096;
+                const u64 *pq = qkv + hq * 128 + lane * 4, *pk = qkv + 2048 + hkv * 128 + lane * 4, *pv = pk + 1024;
                 const bool own = warp == w_new;
                 ll_load2(pq, wq[0], wq[1]); ll_load2(pq + 2, wq[2], wq[3]);
                 if (own) { ll_load2(pk, wk[0], wk[1]); ll_load2(pk + 2, wk[2], wk[3]); ll_load2(pv, wv[0], wv[1]); ll_load2(pv + 2, wv[2], wv[3]); }
@@ -497,10 +514,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                     v_new = make_float4(__uint_as_float((unsigned)wv[0]), __uint_as_float((unsigned)wv[1]), __uint_as_float((unsigned)wv[2]), __uint_as_float((unsigned)wv[3]));
                     if (own) {
 #pragma unroll
-                        for (int i = 0; i < SK_ATT_BATCH; i++) if (k0 + warp + SK_WARPS * i == pos) { kr[i] = k_new; vr[i] = v_new; }
+                        for (int i = 0; i < SK_ATT_BATCH; i++) if (k0 + warp + SK_WARPS * i == apos) { kr[i] = k_new; vr[i] = v_new; }
                         if (!(hq & 1)) { // one writer per kv head appends the new row (reference qwen_asr_decoder.c:640-646)
-                            *reinterpret_cast<float4 *>(kc + (size_t)pos * kvd + hoff) = k_new;
-                            *reinterpret_cast<float4 *>(vc + (size_t)pos * kvd + hoff) = v_new;
+                            *reinterpret_cast<float4 *>(kc + (size_t)apos * kvd + hoff) = k_new;
+                            *reinterpret_cast<float4 *>(vc + (size_t)apos * kvd + hoff) = v_new;
                         }
                     }
                 }
@@ -508,12 +525,12 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                 float m = -1e30f, lsum = 0.0f;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int base = k0; base < k1; base += SK_ATT_BATCH * SK_WARPS) {
-                    if (base != k0) { // later batches (only when a split holds more than 64 keys)
+                    if (base != k0) { // later batches (only when a split holds more than SK_ATT_BATCH * 16 keys)
 #pragma unroll
                         for (int i = 0; i < SK_ATT_BATCH; i++) {
                             const int j = base + warp + SK_WARPS * i;
                             if (j < k1) {
-                                if (j == pos) { kr[i] = k_new; vr[i] = v_new; } // never read the row being appended from the cache
+                                if (j == apos) { kr[i] = k_new; vr[i] = v_new; } // never read the row being appended from the cache
                                 else {
                                     kr[i] = __ldcg(reinterpret_cast<const float4 *>(kc + (size_t)j * kvd + hoff));
                                     vr[i] = __ldcg(reinterpret_cast<const float4 *>(vc + (size_t)j * kvd + hoff));
@@ -562,7 +579,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                         Ls += wml[w * 2 + 1] * e;
                         A += wacc[w * 128 + tid] * e;
                     }
-                    u64 *pb = p.ll_att + (size_t)(hq * SK_ATT_MAXS + sp) * SK_ATT_STRIDE;
+                    u64 *pb = p.ll_att + sa * att_words + (size_t)(hq * SK_ATT_MAXS + sp) * SK_ATT_STRIDE;
                     ll_store(pb + tid, A, tag);
                     if (tid == 0) { ll_store(pb + 128, M, tag); ll_store(pb + 129, Ls, tag); }
                 }
@@ -571,91 +588,95 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             mark();
             // ---------------- WO: input = attention output merged over the S key splits
             {
-                auto merge_splits = [&](auto ns_c) { // NS = compile-time bound on S (1 for contexts of <= 64 keys)
+                auto merge_splits = [&](auto ns_c) { // NS = compile-time bound on S (1 for contexts of <= 32 keys)
                     constexpr int NS = decltype(ns_c)::value;
 #pragma unroll 1
-                    for (int i = 0; i < 2; i++) {
-                        const int pr = tid + i * SK_THREADS; // elements 2pr, 2pr+1 of the 2048-wide head-major vector
+                    for (int i = 0; i < 2 * NSEQ; i++) {
+                        const int q = tid + i * SK_THREADS;   // pair q = s * 1024 + pr: elements 2pr, 2pr+1 of sequence s' head-major vector
+                        const int s = q >> 10, pr = q & 1023;
                         const int hh = pr >> 6, dd = (pr & 63) * 2;
-                        const u64 *pb = p.ll_att + (size_t)(hh * SK_ATT_MAXS) * SK_ATT_STRIDE;
+                        const u64 *pb = p.ll_att + s * att_words + (size_t)(hh * SK_ATT_MAXS) * SK_ATT_STRIDE;
                         u64 w[NS][4];
 #pragma unroll
-                        for (int s = 0; s < NS; s++) {
-                            if (s < S) {
-                                ll_load2(pb + s * SK_ATT_STRIDE + dd, w[s][0], w[s][1]);
-                                ll_load2(pb + s * SK_ATT_STRIDE + 128, w[s][2], w[s][3]);
-                            } else w[s][0] = w[s][1] = w[s][2] = w[s][3] = (u64)tag << 32;
+                        for (int t = 0; t < NS; t++) {
+                            if (t < S) {
+                                ll_load2(pb + t * SK_ATT_STRIDE + dd, w[t][0], w[t][1]);
+                                ll_load2(pb + t * SK_ATT_STRIDE + 128, w[t][2], w[t][3]);
+                            } else w[t][0] = w[t][1] = w[t][2] = w[t][3] = (u64)tag << 32;
                         }
                         for (;;) {
                             bool ok = true;
 #pragma unroll
-                            for (int s = 0; s < NS; s++)
-                                ok = ok && (unsigned)(w[s][0] >> 32) == tag && (unsigned)(w[s][1] >> 32) == tag && (unsigned)(w[s][2] >> 32) == tag && (unsigned)(w[s][3] >> 32) == tag;
+                            for (int t = 0; t < NS; t++)
+                                ok = ok && (unsigned)(w[t][0] >> 32) == tag && (unsigned)(w[t][1] >> 32) == tag && (unsigned)(w[t][2] >> 32) == tag && (unsigned)(w[t][3] >> 32) == tag;
                             if (__all_sync(QASR_FULL, ok)) break;
                             top_up();
 #pragma unroll
-                            for (int s = 0; s < NS; s++) {
-                                if ((unsigned)(w[s][0] >> 32) != tag || (unsigned)(w[s][1] >> 32) != tag) ll_load2(pb + s * SK_ATT_STRIDE + dd, w[s][0], w[s][1]);
-                                if ((unsigned)(w[s][2] >> 32) != tag || (unsigned)(w[s][3] >> 32) != tag) ll_load2(pb + s * SK_ATT_STRIDE + 128, w[s][2], w[s][3]);
+                            for (int t = 0; t < NS; t++) {
+                                if ((unsigned)(w[t][0] >> 32) != tag || (unsigned)(w[t][1] >> 32) != tag) ll_load2(pb + t * SK_ATT_STRIDE + dd, w[t][0], w[t][1]);
+                                if ((unsigned)(w[t][2] >> 32) != tag || (unsigned)(w[t][3] >> 32) != tag) ll_load2(pb + t * SK_ATT_STRIDE + 128, w[t][2], w[t][3]);
                             }
                         }
                         float M = -1e30f, Ls = 0.f, o0 = 0.f, o1 = 0.f;
 #pragma unroll
-                        for (int s = 0; s < NS; s++)
-                            if (s < S) M = fmaxf(M, __uint_as_float((unsigned)w[s][2]));
+                        for (int t = 0; t < NS; t++)
+                            if (t < S) M = fmaxf(M, __uint_as_float((unsigned)w[t][2]));
 #pragma unroll
-                        for (int s = 0; s < NS; s++)
-                            if (s < S) {
-                                const float e = expf(__uint_as_float((unsigned)w[s][2]) - M);
-                                Ls += __uint_as_float((unsigned)w[s][3]) * e;
-                                o0 += __uint_as_float((unsigned)w[s][0]) * e;
-                                o1 += __uint_as_float((unsigned)w[s][1]) * e;
+                        for (int t = 0; t < NS; t++)
+                            if (t < S) {
+                                const float e = expf(__uint_as_float((unsigned)w[t][2]) - M);
+                                Ls += __uint_as_float((unsigned)w[t][3]) * e;
+                                o0 += __uint_as_float((unsigned)w[t][0]) * e;
+                                o1 += __uint_as_float((unsigned)w[t][1]) * e;
                             }
                         const float invL = Ls > 0.0f ? 1.0f / Ls : 0.0f;
-                        sk_put_pair(sm.xf, pr, o0 * invL, o1 * invL);
+                        sk_put_pair<NSEQ>(sm_xf, s, pr, o0 * invL, o1 * invL);
                     }
                 };
                 if (S == 1) merge_splits(std::integral_constant<int, 1>{});
                 else merge_splits(std::integral_constant<int, SK_ATT_MAXS>{});
                 sk_csync();
                 mark();
-                run_phase(H, 2048, [&](int row, int r, auto &&rowsum) { ll_store(p.ll_xwo + row, sm.x[row] + rowsum(r), tag); });
+                run_phase(H, 2048, [&](int s, int row, int r, auto &&rowsum) { ll_store(p.ll_xwo + s * H + row, sm_x[s * H + row] + rowsum(r), tag); });
             }
             mark();
             // ---------------- GU + SwiGLU: rows (2j, 2j+1) = (gate_j, up_j) are neighbours in a chunk
-            stage_norm(p.ll_xwo, tag, g_post);
+            stage_norm(p.ll_xwo, tag, p.post_norm[l]);
             mark();
-            run_phase(2 * I, H, [&](int row, int r, auto &&rowsum) {
+            run_phase(2 * I, H, [&](int s, int row, int r, auto &&rowsum) {
                 if (!(row & 1)) {
-                    const float inv = norm_scale();
-                    ll_store(p.ll_act + (row >> 1), silu(rowsum(r) * inv) * (rowsum(r + 1) * inv), tag);
+                    const float inv = norm_scale(s);
+                    ll_store(p.ll_act + s * I + (row >> 1), silu(rowsum(r) * inv) * (rowsum(r + 1) * inv), tag);
                 }
             });
             mark();
             // ---------------- DOWN
             {
-                float v[6][2];
-                wait_producers(p.ll_act, (2 * I) >> 4, 1, tag);
-                ll_gather_pairs<6>(p.ll_act, I >> 1, tag, tid, v, top_up);
+                const int ip = I >> 1;
+#pragma unroll 1
+                for (int s = 0; s < NSEQ; s++) { // one sequence per pass (6 pairs per thread in flight)
+                    float v[6][2];
+                    ll_gather_pairs<6>(p.ll_act + (size_t)s * I, ip, tag, tid, v, top_up);
 #pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    const int pr = tid + i * SK_THREADS;
-                    if (pr < (I >> 1)) sk_put_pair(sm.xf, pr, v[i][0], v[i][1]);
+                    for (int i = 0; i < 6; i++) {
+                        const int pr = tid + i * SK_THREADS;
+                        if (pr < ip) sk_put_pair<NSEQ>(sm_xf, s, pr, v[i][0], v[i][1]);
+                    }
                 }
                 sk_csync();
                 mark();
-                run_phase(H, I, [&](int row, int r, auto &&rowsum) { ll_store(p.ll_xdn + row, sm.x[row] + rowsum(r), tag); });
+                run_phase(H, I, [&](int s, int row, int r, auto &&rowsum) { ll_store(p.ll_xdn + s * H + row, sm_x[s * H + row] + rowsum(r), tag); });
             }
             mark();
         }
-        // ---------------- HEAD: greedy argmax over this CTA's vocab rows of the tied embedding
+        // ---------------- HEAD: greedy argmax over this CTA's vocab rows of the tied embedding, per sequence
         const unsigned htag = p.tag_base + (unsigned)(step * (L + 1) + L + 1);
-        float2 g_fin[2];
-        load_gamma(p.final_norm, g_fin);
-        stage_norm(p.ll_xdn, htag - 1, g_fin); // argmax is invariant under the positive RMSNorm scale: not applied
+        warm_gamma(p.final_norm);
+        stage_norm(p.ll_xdn, htag - 1, p.final_norm); // argmax is invariant under the positive RMSNorm scale: not applied
         float bv = -1e30f;
         int bi = 0x7fffffff;
-        run_phase(p.V, H, [&](int row, int r, auto &&rowsum) { const float y = rowsum(r); if (sk_better(y, row, bv, bi)) { bv = y; bi = row; } });
+        run_phase(p.V, H, [&](int s, int row, int r, auto &&rowsum) { const float y = rowsum(r); if (sk_better(y, row, bv, bi)) { bv = y; bi = row; } });
+        // epilogue thread t holds the winner of sequence t / CH_ROWS over rows == t (mod CH_ROWS): reduce per sequence
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float ov = __shfl_xor_sync(QASR_FULL, bv, o);
@@ -663,28 +684,34 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             if (sk_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
         }
         sk_csync();
-        if (lane == 0) { sm.red[warp] = bv; sm.redi[warp] = bi; }
+        if (lane == 0) { sm_red[warp] = bv; sm_redi[warp] = bi; }
         sk_csync();
         __threadfence(); // KV rows appended this step become visible device-wide before the token exchange
-        if (tid == 0) {
+        if (tid < NSEQ) {
+            constexpr int WPS = CH_ROWS / 32; // epilogue warps per sequence (4, 2, 1)
+            float v = sm_red[tid * WPS];
+            int ix = sm_redi[tid * WPS];
 #pragma unroll
-            for (int w = 1; w < SK_WARPS; w++)
-                if (sk_better(sm.red[w], sm.redi[w], bv, bi)) { bv = sm.red[w]; bi = sm.redi[w]; }
-            ll_store(p.ll_head + 2 * b, bv, htag);
-            ll_store_u32(p.ll_head + 2 * b + 1, (unsigned)bi, htag);
+            for (int w = 1; w < WPS; w++)
+                if (sk_better(sm_red[tid * WPS + w], sm_redi[tid * WPS + w], v, ix)) { v = sm_red[tid * WPS + w]; ix = sm_redi[tid * WPS + w]; }
+            ll_store(p.ll_head + (size_t)tid * 2048 + 2 * b, v, htag);
+            ll_store_u32(p.ll_head + (size_t)tid * 2048 + 2 * b + 1, (unsigned)ix, htag);
         }
-        { // every CTA reduces the G winners identically
+        int toks[NSEQ];
+#pragma unroll 1
+        for (int s = 0; s < NSEQ; s++) { // every CTA reduces the G winners of every sequence identically
             float wv = -1e30f;
             int wi = 0x7fffffff;
             {
                 const bool active = tid < G;
+                const u64 *hp2 = p.ll_head + (size_t)s * 2048 + 2 * tid;
                 u64 w0 = (u64)htag << 32, w1 = (u64)htag << 32;
-                if (active) ll_load2(p.ll_head + 2 * tid, w0, w1);
+                if (active) ll_load2(hp2, w0, w1);
                 for (;;) {
                     const bool ok = (unsigned)(w0 >> 32) == htag && (unsigned)(w1 >> 32) == htag;
                     if (__all_sync(QASR_FULL, ok)) break;
                     top_up();
-                    if (!ok) ll_load2(p.ll_head + 2 * tid, w0, w1);
+                    if (!ok) ll_load2(hp2, w0, w1);
                 }
                 if (active) { wv = __uint_as_float((unsigned)w0); wi = (int)(unsigned)w1; }
             }
@@ -695,29 +722,39 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                 if (sk_better(ov, oi, wv, wi)) { wv = ov; wi = oi; }
             }
             sk_csync();
-            if (lane == 0) { sm.red[warp] = wv; sm.redi[warp] = wi; }
+            if (lane == 0) { sm_red[warp] = wv; sm_redi[warp] = wi; }
             sk_csync();
-            wv = sm.red[0]; wi = sm.redi[0];
+            wv = sm_red[0]; wi = sm_redi[0];
 #pragma unroll
             for (int w = 1; w < SK_WARPS; w++)
-                if (sk_better(sm.red[w], sm.redi[w], wv, wi)) { wv = sm.red[w]; wi = sm.redi[w]; }
-            const int tok = wi;
-            __threadfence();
-            pos++;
-            // next input row: exact bf16 -> f32 upcast of the embedding (reference qwen_asr.c:412-419,816)
-            for (int e = tid; e < H; e += SK_THREADS) sm.x[e] = __uint_as_float(((uint32_t)p.emb[(size_t)tok * H + e]) << 16);
-            if (b == 0 && tid == 0) {
-                p.d_tokens[step] = tok;
-                if (p.h_tokens) p.h_tokens[step] = tok;
-            }
-            stop = (tok == 151643 || tok == 151645); // reference qwen_asr.c:792
-            sk_csync();
+                if (sk_better(sm_red[w], sm_redi[w], wv, wi)) { wv = sm_red[w]; wi = sm_redi[w]; }
+#pragma unroll
+            for (int t = 0; t < NSEQ; t++) if (t == s) toks[t] = wi;
         }
+        __threadfence();
+#pragma unroll
+        for (int s = 0; s < NSEQ; s++) {
+            const int tok = toks[s];
+            pos[s]++;
+            // next input row: exact bf16 -> f32 upcast of the embedding (reference qwen_asr.c:412-419,816)
+            for (int e = tid; e < H; e += SK_THREADS) sm_x[s * H + e] = __uint_as_float(((uint32_t)p.emb[(size_t)tok * H + e]) << 16);
+            if (b == 0 && tid == 0) {
+                p.d_tokens[step * NSEQ + s] = tok;
+                if (p.h_tokens) p.h_tokens[step * NSEQ + s] = tok;
+            }
+            if (tok == 151643 || tok == 151645) done_mask |= 1u << s; // reference qwen_asr.c:792
+        }
+        stop = done_mask == (1u << NSEQ) - 1u;
+        sk_csync();
         mark();
     }
     if (b == 0) {
-        for (int e = tid; e < H; e += SK_THREADS) p.x_io[e] = sm.x[e];
-        if (tid == 0) { *p.d_pos = pos; *p.d_step = step; }
+        for (int e = tid; e < NSEQ * H; e += SK_THREADS) p.x_io[e] = sm_x[e];
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < NSEQ; s++) p.d_pos[s] = pos[s];
+            *p.d_step = step;
+        }
     }
     // drain copies that were prefetched past an early stop before the CTA's shared memory goes away
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -728,17 +765,26 @@ static char g_sk_err[256] = "";
 const char *stream_error(void) { return g_sk_err; }
 static int g_sk_grid = 0;
 
+template <int NSEQ, int SLOTS>
+static cudaError_t sk_prepare_variant(int *per_sm, int kmax, int hmax) {
+    const size_t smem = SkLayout<NSEQ, SLOTS>::total(kmax, hmax);
+    cudaError_t e = cudaFuncSetAttribute(decode_stream_kernel<NSEQ, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, decode_stream_kernel<NSEQ, SLOTS>, SK_THREADS, smem);
+    return e;
+}
+
 int stream_init(void) {
     if (g_sk_grid) return 0;
     int dev = 0, sms = 0, coop = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    cudaError_t e = cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SkSmem) + 1024);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_stream_kernel, SK_THREADS, sizeof(SkSmem) + 1024);
-    if (e != cudaSuccess || !coop || per_sm < 1 || sms < 1) {
-        snprintf(g_sk_err, sizeof g_sk_err, "decode stream kernel unavailable: %s (coop=%d, blocks/SM=%d, smem=%zu)",
-                 cudaGetErrorString(e), coop, per_sm, sizeof(SkSmem));
+    cudaError_t e = sk_prepare_variant<1, 5>(&per_sm, SK_MAX_K, SK_MAX_H);
+    int p2 = 0;
+    if (e == cudaSuccess && per_sm >= 1) e = sk_prepare_variant<2, 4>(&p2, SK_MAX_K, SK_MAX_H);
+    if (e == cudaSuccess && per_sm >= 1) e = sk_prepare_variant<4, 4>(&p2, 3072, 1024); // 4 sequences only fit for the 0.6B dims
+    if (e != cudaSuccess || !coop || per_sm < 1 || p2 < 1 || sms < 1) {
+        snprintf(g_sk_err, sizeof g_sk_err, "decode stream kernel unavailable: %s (coop=%d, blocks/SM=%d/%d)", cudaGetErrorString(e), coop, per_sm, p2);
         cudaGetLastError();
         return -1;
     }
@@ -780,15 +826,25 @@ int stream_build_image(cudaStream_t s, int L, int H, int I, int V, const bf16_t 
     return 0;
 }
 
+// Largest number of sequences one launch can carry for these dims (shared memory: the DOWN input image is K x 4 B per sequence)
+int stream_max_seqs(int H, int I) { return (H <= 1024 && I <= 3072) ? 4 : 2; }
+
 int launch_decode_stream(cudaStream_t s, const StreamParams &p) {
     if (stream_init() != 0) return -1;
-    if (!sk_dims_ok(p.n_layers, p.H, p.I, p.V) || p.n_steps > 64 || p.n_steps < 1) {
-        snprintf(g_sk_err, sizeof g_sk_err, "decode stream kernel: unsupported dims H=%d I=%d V=%d steps=%d", p.H, p.I, p.V, p.n_steps);
+    if (!sk_dims_ok(p.n_layers, p.H, p.I, p.V) || p.n_steps > 64 || p.n_steps < 1 || (p.nseq != 1 && p.nseq != 2 && p.nseq != 4) ||
+        p.nseq > stream_max_seqs(p.H, p.I)) {
+        snprintf(g_sk_err, sizeof g_sk_err, "decode stream kernel: unsupported dims H=%d I=%d V=%d steps=%d seqs=%d", p.H, p.I, p.V, p.n_steps, p.nseq);
         return -1;
     }
     void *args[] = {(void *)&p};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)decode_stream_kernel, dim3(g_sk_grid), dim3(SK_THREADS), args,
-                                                sizeof(SkSmem) + 1024, s);
+    const int kmax = p.I > 2048 ? p.I : 2048;
+    cudaError_t e;
+    if (p.nseq == 1)
+        e = cudaLaunchCooperativeKernel((const void *)decode_stream_kernel<1, 5>, dim3(g_sk_grid), dim3(SK_THREADS), args, SkLayout<1, 5>::total(kmax, p.H), s);
+    else if (p.nseq == 2)
+        e = cudaLaunchCooperativeKernel((const void *)decode_stream_kernel<2, 4>, dim3(g_sk_grid), dim3(SK_THREADS), args, SkLayout<2, 4>::total(kmax, p.H), s);
+    else
+        e = cudaLaunchCooperativeKernel((const void *)decode_stream_kernel<4, 4>, dim3(g_sk_grid), dim3(SK_THREADS), args, SkLayout<4, 4>::total(kmax, p.H), s);
     if (e != cudaSuccess) {
         snprintf(g_sk_err, sizeof g_sk_err, "decode stream kernel launch: %s", cudaGetErrorString(e));
         return -1;

@@ -1,7 +1,7 @@
 """Host-side streaming session: the device-visible part of the reference's `stream_impl`
-(qwen_asr.c:1273-1900) for `--stream` mode, written against the duck-typed engine interface that
-`QasrCuda`, `OracleLib` and `RefLib` share (mel / encode / embed / prefill / step / kv_len), so the same
-driver runs the B200 path and the CPU checkers.
+(qwen_asr.c:1273-1900) for `--stream` mode, written against a duck-typed engine interface
+(mel / encode / embed / prefill / step / kv_len, optionally generate): `QasrCuda` implements it, and so do the
+CPU checkers the tests drive through the very same session.
 
 Per chunk of new audio (reference line numbers):
   * every newly completed `window_sec` (8 s) span is mel-normalised on its own span and encoded ONCE,

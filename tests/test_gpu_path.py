@@ -216,3 +216,31 @@ def test_long_context_decode_matches_oracle(gpu06, oracle06):
     assert ids[0] == ids[1]
     gpu06.kv_len = 540
     assert list(gpu06.generate(ids[0][0], 6)) == ids[0]      # device greedy loop from the same state
+
+
+def test_batched_decode_ids_equal_single_sequence(gpu06, pkg):
+    """qasr_cuda_transcribe_batch: 4 (0.6B) sequences share every decode step in separate MMA columns; each
+    unit's ids must be exactly those of qasr_cuda_transcribe_ids on that unit alone (7 units = 4 + 2 + 1,
+    different lengths and token caps)."""
+    assert gpu06.max_batch == 4
+    secs = [1.3, 2.6, 0.9, 3.4, 1.9, 2.2, 1.1]
+    caps = [9, 12, 6, 17, 8, 11, 5]
+    units = [pkg.synth_audio(s, seed=40 + i) for i, s in enumerate(secs)]
+    single = [gpu06.transcribe_ids(u, c)[0].tolist() for u, c in zip(units, caps)]
+    batched, tm = gpu06.transcribe_batch(units, caps)
+    assert [b.tolist() for b in batched] == single
+    assert tm["decode_ms"] > 0
+    # and the single-sequence path still works after a batch (sequence 0's cache is the default again)
+    assert gpu06.transcribe_ids(units[1], caps[1])[0].tolist() == single[1]
+
+
+def test_batched_decode_1p7b_pairs(pkg, model17):
+    eng = pkg.QasrCuda(0).load(model17)
+    try:
+        assert eng.max_batch == 2
+        units = [pkg.synth_audio(s, seed=60 + i) for i, s in enumerate([2.0, 3.1, 1.2])]
+        single = [eng.transcribe_ids(u, 10)[0].tolist() for u in units]
+        batched, _ = eng.transcribe_batch(units, 10)
+        assert [b.tolist() for b in batched] == single
+    finally:
+        eng.close()
