@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
     const int b = blockIdx.x, G = gridDim.x;
     const int L = p.n_layers, H = p.H, I = p.I;
     const int kmax = max(max(H, I), 2048);
-    uint8_t *sm0 = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(sk_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sm0 = sk_raw; // used as is (16-byte alignment suffices): keeps the shared address space visible to the compiler (LDS/STS instead of generic LD/ST)
     uint8_t *sm_ring = sm0;
     uint32_t *sm_xf = reinterpret_cast<uint32_t *>(sm0 + LY::ring_bytes);
     float *sm_x = reinterpret_cast<float *>(sm0 + LY::ring_bytes + LY::xf_bytes(kmax));                  // [NSEQ][H] residual streams
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
     __syncthreads();
 
     // ---- per-warp weight stream (contiguous, cyclic).  Every lane copies its own 4 x 16 B of each unit with
-    // cp.async (LDGSTS, L1 bypass, L2 evict-first) into its private bytes of the warp's SLOTS-deep ring and
+    // cp.async (LDGSTS, L1 bypass) into its private bytes of the warp's SLOTS-deep ring and
     // later reads back exactly those bytes as its A fragments: a per-lane FIFO, so completion is tracked by the
     // per-thread cp.async group counter alone (one group per unit, always SLOTS groups outstanding).
     const u64 coff = p.cta_off[b];
@@ -254,16 +254,25 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
     uint32_t foff = 0;
     int fsteps = 0;
     unsigned consumed = 0;
+    // L2 evict-first for the weight stream (read once per token) so KV rows, exchange words and L2-prefetched units stay resident
     u64 pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     const uint32_t ring0 = sk_smem_u32(sm_ring) + warp * (SLOTS * SK_UNIT) + lane * 16;
     auto fetch_into = [&](unsigned slot) { // next unit of the stream -> ring slot; always commits one group
         if (fsteps < p.n_steps) {
             const uint8_t *src = sbase + foff;
-            const uint32_t dst = ring0 + slot * SK_UNIT;
+            uint32_t dst = ring0 + slot * SK_UNIT;
+            // keep the shared address in ONE general register: when ptxas 12.9 splits it into a uniform base plus an offset
+            // ([R+UR]) the cache-hinted LDGSTS is mis-assembled with undefined descriptor registers (CUDA_EXCEPTION_4,
+            // "Warp Illegal Instruction", located with cuda-gdb); tests/test_abi.py checks the SASS for that form
+            asm volatile("mov.u32 %0, %0;" : "+r"(dst));
 #pragma unroll
-            for (int kb = 0; kb < 4; kb++)
-                asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + kb * 512), "l"(src + kb * 512), "l"(pol) : "memory");
+            for (int kb = 0; kb < 4; kb++) {
+                if constexpr (NSEQ == 1) // hinted copies only where the generated SASS is clean (see above); the batched variants use the default policy
+                    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + kb * 512), "l"(src + kb * 512), "l"(pol) : "memory");
+                else
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + kb * 512), "l"(src + kb * 512) : "memory");
+            }
             foff += SK_UNIT;
             if (foff == slen) { foff = 0; fsteps++; }
             fpos++;
@@ -275,7 +284,10 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
     for (int i = 0; i < SLOTS; i++) fetch_into(i);
     auto top_up = [&]() { // service hook of every poll loop (runs converged: the loops are warp-uniform)
         if (lpos - fpos < l2_window) {
-            if (lane < 16) asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + loff + lane * 128) : "memory");
+            if (lane < 16) {
+                if (p.debug & 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + loff + lane * 128) : "memory");
+                else asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(wbase + loff + lane * 128) : "memory");
+            }
             lpos++;
             loff += SK_UNIT;
             if (loff == slen) loff = 0;
@@ -348,7 +360,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
     // the block reduction of the squares leaves the critical path between the gather and the first MMA.
     // All NSEQ vectors are gathered as one long vector (pair q = s * H/2 + pr), every load in flight before the first check.
     constexpr int NPX = NSEQ == 4 ? 4 : 2 * NSEQ; // 512 threads x NPX pairs cover NSEQ x H/2 (NSEQ = 4 only with H = 1024)
-    auto stage_norm = [&](const u64 *src, unsigned tag, const float *gamma) {
+    auto stage_norm = [&](const u64 *src, unsigned tag, const float2 (&gm2)[2]) {
         float v[NPX][2];
         const int hp = H >> 1, npairs = NSEQ * hp;
         if (src) {
@@ -374,8 +386,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
         for (int i = 0; i < NPX; i++) {
             const int q = tid + i * SK_THREADS;
             if (q < npairs) {
-                const int s = q / hp, pr = q - s * hp;
-                const float2 gm = __ldg(reinterpret_cast<const float2 *>(gamma) + pr);
+                const int s = NSEQ == 1 ? 0 : q / hp, pr = q - s * hp;
+                const float2 gm = (hp > SK_THREADS && (i & 1)) ? gm2[1] : gm2[0]; // pr = tid + 512 * (i mod hp/512)
                 const float sq = fmaf(v[i][0], v[i][0], v[i][1] * v[i][1]);
 #pragma unroll
                 for (int t = 0; t < NSEQ; t++) if (t == s) ss[t] += sq;
@@ -395,8 +407,12 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
         for (int w = 0; w < SK_WARPS; w++) t += sm_ssq[s * SK_WARPS + w];
         return 1.0f / sqrtf(t / (float)H + p.eps);
     };
-    auto warm_gamma = [&](const float *g) { // pull the norm weights towards L1/L2 before the exchange wait
-        if (tid < (H >> 5)) asm volatile("prefetch.global.L2 [%0];" ::"l"(g + tid * 32) : "memory");
+    auto load_gamma = [&](const float *g, float2 (&gm2)[2]) { // this thread's norm weights (pairs tid, tid + 512), loaded before the exchange waits
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int pr = tid + j * SK_THREADS;
+            gm2[j] = pr < (H >> 1) ? __ldg(reinterpret_cast<const float2 *>(g) + pr) : make_float2(0.f, 0.f);
+        }
     };
 
     long long *prof = (p.prof && (b == 0 || b == G - 1) && tid == 0) ? p.prof + (b == 0 ? 0 : p.prof_cap) : nullptr;
@@ -436,15 +452,16 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             if (att) // K/V rows of this split -> L2 while the QKV phase runs
                 for (int j = k0 * 8 + tid; j < k1 * 8 && j < apos * 8; j += SK_THREADS) { // 8 lines of 128 B per key (K row + V row)
                     const float *row = ((j & 4) ? vc : kc) + (size_t)(j >> 3) * kvd + hkv * 128 + (j & 3) * 32;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row) : "memory");
+                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(row) : "memory");
                 }
             // small per-layer parameters: issue the loads now, use them after the exchange waits
-            warm_gamma(p.in_norm[l]);
-            warm_gamma(p.post_norm[l]);
+            float2 g_in[2], g_post[2];
+            load_gamma(p.in_norm[l], g_in);
+            load_gamma(p.post_norm[l], g_post);
             const float4 qn4 = __ldg(reinterpret_cast<const float4 *>(p.qn[l]) + lane), kn4 = __ldg(reinterpret_cast<const float4 *>(p.kn[l]) + lane);
             mark();
             // ---------------- QKV
-            stage_norm(l > 0 ? p.ll_xdn : nullptr, tag - 1, p.in_norm[l]);
+            stage_norm(l > 0 ? p.ll_xdn : nullptr, tag - 1, g_in);
             mark();
             run_phase(4096, H, [&](int s, int row, int r, auto &&rowsum) { ll_store(p.ll_qkv + s * 4096 + row, rowsum(r) * norm_scale(s), tag); });
             mark();
@@ -588,60 +605,73 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             mark();
             // ---------------- WO: input = attention output merged over the S key splits
             {
-                auto merge_splits = [&](auto ns_c) { // NS = compile-time bound on S (1 for contexts of <= 32 keys)
-                    constexpr int NS = decltype(ns_c)::value;
+                auto merge_splits = [&](auto ns_c, auto pg_c) { // NS = compile-time bound on S; PG = pairs per thread whose loads fly together
+                    constexpr int NS = decltype(ns_c)::value, PG = decltype(pg_c)::value;
 #pragma unroll 1
-                    for (int i = 0; i < 2 * NSEQ; i++) {
-                        const int q = tid + i * SK_THREADS;   // pair q = s * 1024 + pr: elements 2pr, 2pr+1 of sequence s' head-major vector
-                        const int s = q >> 10, pr = q & 1023;
-                        const int hh = pr >> 6, dd = (pr & 63) * 2;
-                        const u64 *pb = p.ll_att + s * att_words + (size_t)(hh * SK_ATT_MAXS) * SK_ATT_STRIDE;
-                        u64 w[NS][4];
+                    for (int i0 = 0; i0 < 2 * NSEQ; i0 += PG) {
+                        u64 w[PG][NS][4];
+                        const u64 *pb[PG];
+                        int dd[PG];
 #pragma unroll
-                        for (int t = 0; t < NS; t++) {
-                            if (t < S) {
-                                ll_load2(pb + t * SK_ATT_STRIDE + dd, w[t][0], w[t][1]);
-                                ll_load2(pb + t * SK_ATT_STRIDE + 128, w[t][2], w[t][3]);
-                            } else w[t][0] = w[t][1] = w[t][2] = w[t][3] = (u64)tag << 32;
+                        for (int g = 0; g < PG; g++) {
+                            const int q = tid + (i0 + g) * SK_THREADS;   // pair q = s * 1024 + pr: elements 2pr, 2pr+1 of sequence s' head-major vector
+                            const int s = q >> 10, pr = q & 1023;
+                            dd[g] = (pr & 63) * 2;
+                            pb[g] = p.ll_att + s * att_words + (size_t)((pr >> 6) * SK_ATT_MAXS) * SK_ATT_STRIDE;
+#pragma unroll
+                            for (int t = 0; t < NS; t++) {
+                                if (t < S) {
+                                    ll_load2(pb[g] + t * SK_ATT_STRIDE + dd[g], w[g][t][0], w[g][t][1]);
+                                    ll_load2(pb[g] + t * SK_ATT_STRIDE + 128, w[g][t][2], w[g][t][3]);
+                                } else w[g][t][0] = w[g][t][1] = w[g][t][2] = w[g][t][3] = (u64)tag << 32;
+                            }
                         }
                         for (;;) {
                             bool ok = true;
 #pragma unroll
-                            for (int t = 0; t < NS; t++)
-                                ok = ok && (unsigned)(w[t][0] >> 32) == tag && (unsigned)(w[t][1] >> 32) == tag && (unsigned)(w[t][2] >> 32) == tag && (unsigned)(w[t][3] >> 32) == tag;
+                            for (int g = 0; g < PG; g++)
+#pragma unroll
+                                for (int t = 0; t < NS; t++)
+                                    ok = ok && (unsigned)(w[g][t][0] >> 32) == tag && (unsigned)(w[g][t][1] >> 32) == tag && (unsigned)(w[g][t][2] >> 32) == tag && (unsigned)(w[g][t][3] >> 32) == tag;
                             if (__all_sync(QASR_FULL, ok)) break;
                             top_up();
 #pragma unroll
-                            for (int t = 0; t < NS; t++) {
-                                if ((unsigned)(w[t][0] >> 32) != tag || (unsigned)(w[t][1] >> 32) != tag) ll_load2(pb + t * SK_ATT_STRIDE + dd, w[t][0], w[t][1]);
-                                if ((unsigned)(w[t][2] >> 32) != tag || (unsigned)(w[t][3] >> 32) != tag) ll_load2(pb + t * SK_ATT_STRIDE + 128, w[t][2], w[t][3]);
-                            }
+                            for (int g = 0; g < PG; g++)
+#pragma unroll
+                                for (int t = 0; t < NS; t++) {
+                                    if ((unsigned)(w[g][t][0] >> 32) != tag || (unsigned)(w[g][t][1] >> 32) != tag) ll_load2(pb[g] + t * SK_ATT_STRIDE + dd[g], w[g][t][0], w[g][t][1]);
+                                    if ((unsigned)(w[g][t][2] >> 32) != tag || (unsigned)(w[g][t][3] >> 32) != tag) ll_load2(pb[g] + t * SK_ATT_STRIDE + 128, w[g][t][2], w[g][t][3]);
+                                }
                         }
-                        float M = -1e30f, Ls = 0.f, o0 = 0.f, o1 = 0.f;
 #pragma unroll
-                        for (int t = 0; t < NS; t++)
-                            if (t < S) M = fmaxf(M, __uint_as_float((unsigned)w[t][2]));
+                        for (int g = 0; g < PG; g++) {
+                            const int q = tid + (i0 + g) * SK_THREADS;
+                            float M = -1e30f, Ls = 0.f, o0 = 0.f, o1 = 0.f;
 #pragma unroll
-                        for (int t = 0; t < NS; t++)
-                            if (t < S) {
-                                const float e = expf(__uint_as_float((unsigned)w[t][2]) - M);
-                                Ls += __uint_as_float((unsigned)w[t][3]) * e;
-                                o0 += __uint_as_float((unsigned)w[t][0]) * e;
-                                o1 += __uint_as_float((unsigned)w[t][1]) * e;
-                            }
-                        const float invL = Ls > 0.0f ? 1.0f / Ls : 0.0f;
-                        sk_put_pair<NSEQ>(sm_xf, s, pr, o0 * invL, o1 * invL);
+                            for (int t = 0; t < NS; t++)
+                                if (t < S) M = fmaxf(M, __uint_as_float((unsigned)w[g][t][2]));
+#pragma unroll
+                            for (int t = 0; t < NS; t++)
+                                if (t < S) {
+                                    const float e = expf(__uint_as_float((unsigned)w[g][t][2]) - M);
+                                    Ls += __uint_as_float((unsigned)w[g][t][3]) * e;
+                                    o0 += __uint_as_float((unsigned)w[g][t][0]) * e;
+                                    o1 += __uint_as_float((unsigned)w[g][t][1]) * e;
+                                }
+                            const float invL = Ls > 0.0f ? 1.0f / Ls : 0.0f;
+                            sk_put_pair<NSEQ>(sm_xf, q >> 10, q & 1023, o0 * invL, o1 * invL);
+                        }
                     }
                 };
-                if (S == 1) merge_splits(std::integral_constant<int, 1>{});
-                else merge_splits(std::integral_constant<int, SK_ATT_MAXS>{});
+                if (S == 1) merge_splits(std::integral_constant<int, 1>{}, std::integral_constant<int, 2 * NSEQ>{});
+                else merge_splits(std::integral_constant<int, SK_ATT_MAXS>{}, std::integral_constant<int, 2>{});
                 sk_csync();
                 mark();
                 run_phase(H, 2048, [&](int s, int row, int r, auto &&rowsum) { ll_store(p.ll_xwo + s * H + row, sm_x[s * H + row] + rowsum(r), tag); });
             }
             mark();
             // ---------------- GU + SwiGLU: rows (2j, 2j+1) = (gate_j, up_j) are neighbours in a chunk
-            stage_norm(p.ll_xwo, tag, p.post_norm[l]);
+            stage_norm(p.ll_xwo, tag, g_post);
             mark();
             run_phase(2 * I, H, [&](int s, int row, int r, auto &&rowsum) {
                 if (!(row & 1)) {
@@ -652,15 +682,18 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             mark();
             // ---------------- DOWN
             {
-                const int ip = I >> 1;
+                const int ip = I >> 1, total = NSEQ * ip; // the NSEQ activation vectors as one long vector, 6 pairs per thread per pass
 #pragma unroll 1
-                for (int s = 0; s < NSEQ; s++) { // one sequence per pass (6 pairs per thread in flight)
+                for (int base = 0; base < total; base += 6 * SK_THREADS) {
                     float v[6][2];
-                    ll_gather_pairs<6>(p.ll_act + (size_t)s * I, ip, tag, tid, v, top_up);
+                    ll_gather_pairs<6>(p.ll_act + 2 * (size_t)base, min(total - base, 6 * SK_THREADS), tag, tid, v, top_up);
 #pragma unroll
                     for (int i = 0; i < 6; i++) {
-                        const int pr = tid + i * SK_THREADS;
-                        if (pr < ip) sk_put_pair<NSEQ>(sm_xf, s, pr, v[i][0], v[i][1]);
+                        const int q = base + tid + i * SK_THREADS;
+                        if (q < total) {
+                            const int s = NSEQ == 1 ? 0 : q / ip;
+                            sk_put_pair<NSEQ>(sm_xf, s, q - s * ip, v[i][0], v[i][1]);
+                        }
                     }
                 }
                 sk_csync();
@@ -671,8 +704,9 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
         }
         // ---------------- HEAD: greedy argmax over this CTA's vocab rows of the tied embedding, per sequence
         const unsigned htag = p.tag_base + (unsigned)(step * (L + 1) + L + 1);
-        warm_gamma(p.final_norm);
-        stage_norm(p.ll_xdn, htag - 1, p.final_norm); // argmax is invariant under the positive RMSNorm scale: not applied
+        float2 g_fin[2];
+        load_gamma(p.final_norm, g_fin);
+        stage_norm(p.ll_xdn, htag - 1, g_fin); // argmax is invariant under the positive RMSNorm scale: not applied
         float bv = -1e30f;
         int bi = 0x7fffffff;
         run_phase(p.V, H, [&](int s, int row, int r, auto &&rowsum) { const float y = rowsum(r); if (sk_better(y, row, bv, bi)) { bv = y; bi = row; } });

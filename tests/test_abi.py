@@ -51,6 +51,28 @@ def test_sass_is_blackwell_native(pkg):
     assert "HGMMA" not in r.stdout
 
 
+def test_decode_stream_sass_has_no_undefined_descriptor(pkg):
+    """Canary for a ptxas 12.9 mis-assembly seen while building qasr_stream.cu: cache-hinted LDGSTS (cp.async) whose
+    shared address was split into [R+UR0] got descriptor registers UR0/UR1 that no instruction ever writes
+    (CUDA_EXCEPTION_4 on the first copy).  Every uniform register an LDGSTS reads must be written somewhere."""
+    r = subprocess.run(["cuobjdump", "-sass", pkg.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    funcs = re.split(r"\n\s*Function : ", r.stdout)
+    checked = 0
+    for f in funcs:
+        if not f.startswith("_Z20decode_stream_kernel"):
+            continue
+        checked += 1
+        used = set(re.findall(r"LDGSTS[^;]*?(UR\d+)", f)) | set(re.findall(r"LDGSTS[^;]*desc\[(UR\d+)\]", f))
+        for ur in used:
+            n = int(ur[2:])
+            writers = [rf"\b{ur}\s*,", rf"\bUR{n - 1}\s*," if n % 2 else r"$^"]  # written directly, or as the high half of a 64-bit pair
+            assert any(re.search(rf"^\s*/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?(?!LDGSTS)[A-Z0-9_.]+\s+{w}", f, re.M) for w in writers), \
+                f"{ur} is read by an LDGSTS but never written in {f[:60]}"
+    assert checked >= 3
+
+
 def test_no_cpu_fallback_without_gpu(pkg):
     lib = pkg.load_library()
     if lib.qasr_cuda_device_count() > 0:
