@@ -175,7 +175,7 @@ def main_multi(args, rank, local_rank, world):
         dt = time.perf_counter() - t0
         eng.close()
         value = audio_s / dt
-        print(json.dumps({"impl": "reference", "metric": "realtime_factor", "value": value, "unit": "x realtime (audio s / wall s)", "n_gpus": 0,
+        print(json.dumps({"impl": "reference", "metric": "realtime_factor", "value": value, "unit": "x realtime (audio s / wall s)", "n_gpus": args.gpus,
                           "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                           "dtype": "f32 activations x bf16 weights (CPU)", "data": "synthetic", "config": {"workload": desc},
                           "cpu_baseline": {"value": value, "unit": "x realtime", "cores": cores, "kind": kind, "sample": sample},
@@ -345,7 +345,7 @@ def main():
         value = audio_s / r["sec_per_step"]
         sample = f"{steps} timed + {warm} warm-up full utterance passes (mel+encoder+prefill+{max_new} greedy tokens) of the same workload"
         out = {"impl": "reference", "metric": "realtime_factor", "value": value, "unit": "x realtime (audio s / wall s)",
-               "n_gpus": 0, "steps": steps, "warmup": warm, "ms_per_step": 1000.0 * r["sec_per_step"], "higher_is_better": True,
+               "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1000.0 * r["sec_per_step"], "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32 activations x bf16 weights (CPU)", "data": "synthetic",
                "config": config,
                "cpu_baseline": {"value": value, "unit": "x realtime", "cores": r["cores"], "kind": r["kind"], "sample": sample,

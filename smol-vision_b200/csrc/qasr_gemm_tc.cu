@@ -112,7 +112,7 @@ struct TcParams {
     GemmEpilogue epi;
 };
 
-template <int BN>
+template <int BN, int STAGES = (BN > 128 ? 3 : TC_STAGES)>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
@@ -122,9 +122,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     constexpr uint32_t B_BYTES = BN * TC_BK * 2;
     constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + B_BYTES;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + TC_STAGES * STAGE_BYTES);
-    uint64_t *empty_bar = full_bar + TC_STAGES;
-    uint64_t *tmem_full_bar = empty_bar + TC_STAGES;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *tmem_full_bar = empty_bar + STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -135,7 +135,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         if (p.nsplit == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -154,8 +154,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (lane == 0) {
             const uint32_t tx = (p.nsplit == 2 ? 2 * A_BYTES : A_BYTES) + B_BYTES;
             for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % TC_STAGES;
-                const uint32_t ph = (kb / TC_STAGES) & 1;
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t *st = smem + s * STAGE_BYTES;
                 mbar_expect_tx(&full_bar[s], tx);
@@ -172,8 +172,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(TC_BM >> 4) << 24);
             for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % TC_STAGES;
-                const uint32_t ph = (kb / TC_STAGES) & 1;
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
@@ -481,7 +481,7 @@ static PFN_encodeTiled g_encode = nullptr;
 
 template <int BN>
 static constexpr size_t tc_smem_bytes() {
-    return (size_t)TC_STAGES * (2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 256 + 1024;
+    return (size_t)(BN > 128 ? 3 : TC_STAGES) * (2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 256 + 1024;
 }
 
 template <int MP, int STAGES>
@@ -503,6 +503,7 @@ int gemm_tc_init(void) {
     }
     g_encode = (PFN_encodeTiled)fn;
     e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64>());
     if (e == cudaSuccess)
@@ -632,6 +633,11 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
     // Narrow tiles when the 128-wide grid would leave most of the 148 SMs idle.
     const int tiles128 = ((M + TC_BM - 1) / TC_BM) * ((N + 127) / 128);
     const bool bn64 = tiles128 < 120;
+    // 128 x 256 tiles (43 -> 65 MACs per byte of L2 -> shared traffic: the 128 x 128 kernel is L2-feed bound with hi/lo
+    // operands) once there are enough tiles to fill the SMs for several waves
+    static int bn256_min_tiles = -1;
+    if (bn256_min_tiles < 0) { const char *ev = getenv("QASR_GEMM_BN256_MIN_TILES"); bn256_min_tiles = ev ? atoi(ev) : 400; }
+    const bool bn256 = !bn64 && ((M + TC_BM - 1) / TC_BM) * ((N + 255) / 256) >= bn256_min_tiles;
     TcParams p;
     p.M = M; p.N = N; p.K = K;
     p.nsplit = A_lo ? 2 : 1;
@@ -639,8 +645,11 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
     CUtensorMap ma, ml, mb;
     if (make_map(&ma, A_hi, M, K, TC_BM) != 0) return -1;
     if (make_map(&ml, A_lo ? A_lo : A_hi, M, K, TC_BM) != 0) return -1;
-    if (make_map(&mb, W, N, K, bn64 ? 64 : 128) != 0) return -1;
-    if (bn64) {
+    if (make_map(&mb, W, N, K, bn64 ? 64 : (bn256 ? 256 : 128)) != 0) return -1;
+    if (bn256) {
+        dim3 grid((N + 255) / 256, (M + TC_BM - 1) / TC_BM);
+        gemm_tc_kernel<256><<<grid, TC_THREADS, tc_smem_bytes<256>(), s>>>(ma, ml, mb, p);
+    } else if (bn64) {
         dim3 grid((N + 63) / 64, (M + TC_BM - 1) / TC_BM);
         gemm_tc_kernel<64><<<grid, TC_THREADS, tc_smem_bytes<64>(), s>>>(ma, ml, mb, p);
     } else {

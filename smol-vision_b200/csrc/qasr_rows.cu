@@ -161,129 +161,179 @@ __device__ __forceinline__ void soft_update(float sc, float &m, float &l, float 
     }
 }
 
-// ------------------------------------------------------------------ causal GQA attention (prefill)
-// reference qwen_asr_kernels.c:1101-1148.  head_dim = 128.  CTA = (kv head, 16 query positions), 8 warps;
-// a warp owns 2 consecutive positions x the 2 query heads of the kv head => 4 queries share every K/V
-// row; lane owns dims 4l..4l+3.  K/V rows are staged through shared memory in 32-key tiles (coalesced
-// loads, then ~30-cycle LDS instead of an L2 round trip per key).  Query i attends keys [0, q_offset+i].
+// ------------------------------------------------------------------ tiled attention core (prefill + encoder)
+// Lane-per-key scheme: for a tile of 32 keys every lane owns ONE key and computes its full head_dim dot product
+// against 4 queries of the warp (K tile transposed in shared memory so the lane's float4 reads are conflict free,
+// q rows read as broadcasts) - no per-key warp reduction.  The softmax of the tile needs two warp reductions per
+// query per 32 keys (max, sum); the probabilities go through a per-warp scratch so that in the P.V pass every lane
+// owns HD/32 output dims.  Online softmax across tiles with the reference's initial max of -1e30
+// (qwen_asr_kernels.c:1054-1148); same arithmetic as the per-key recurrence, different rounding order.
 #define ATT_KT 32
+template <int HD>
+struct AttSmem {
+    float4 kt[HD / 4][ATT_KT + 1];   // K tile transposed: [dim/4][key] (+1 float4 of padding: conflict-free stores)
+    float vs[ATT_KT][HD];            // V tile
+    float qs[32][HD];                // 32 queries of the CTA
+    float4 ps[8][ATT_KT];            // per-warp probabilities [key][4 queries]
+};
+
+// one 32-key tile for the 4 queries of a warp.  hi[j]: query j may attend absolute keys < hi[j] (and >= t0 - always true here)
+template <int HD>
+__device__ __forceinline__ void att_tile(AttSmem<HD> &sm, int warp, int lane, int t0, int nk, const int (&hi)[4], float scale,
+                                         float (&m)[4], float (&l)[4], float (&acc)[4][HD / 32]) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int d4 = 0; d4 < HD / 4; d4++) {
+        const float4 k4 = sm.kt[d4][lane];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float4 q4 = reinterpret_cast<const float4 *>(sm.qs[warp * 4 + j])[d4];
+            s[j] = fmaf(q4.x, k4.x, fmaf(q4.y, k4.y, fmaf(q4.z, k4.z, fmaf(q4.w, k4.w, s[j]))));
+        }
+    }
+    float pj[4];
+    int kmax = 0; // keys of this tile any of the 4 queries attends (warp-uniform)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const bool valid = lane < nk && t0 + lane < hi[j];
+        const float sj = valid ? s[j] * scale : -INFINITY;
+        const float mnew = fmaxf(m[j], warp_max(sj));
+        const float pv = valid ? expf(sj - mnew) : 0.0f;
+        const float c = expf(m[j] - mnew);
+        l[j] = l[j] * c + warp_sum(pv);
+#pragma unroll
+        for (int i = 0; i < HD / 32; i++) acc[j][i] *= c;
+        m[j] = mnew;
+        pj[j] = pv;
+        kmax = max(kmax, min(nk, hi[j] - t0));
+    }
+    sm.ps[warp][lane] = make_float4(pj[0], pj[1], pj[2], pj[3]);
+    __syncwarp();
+    for (int kk = 0; kk < kmax; kk++) {
+        const float4 p4 = sm.ps[warp][kk];
+        const float pq[4] = {p4.x, p4.y, p4.z, p4.w};
+        float vv[HD / 32];
+        if (HD == 128) {
+            const float4 v4 = reinterpret_cast<const float4 *>(sm.vs[kk])[lane];
+            vv[0] = v4.x; vv[1] = v4.y; vv[HD / 32 - 2] = v4.z; vv[HD / 32 - 1] = v4.w;
+        } else {
+            const float2 v2 = reinterpret_cast<const float2 *>(sm.vs[kk])[lane];
+            vv[0] = v2.x; vv[1] = v2.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int i = 0; i < HD / 32; i++) acc[j][i] = fmaf(pq[j], vv[i], acc[j][i]);
+    }
+    __syncwarp();
+}
+
+// cooperative load of a K/V tile: rows [t0, t0+nk) of k / v (row stride ld, head column offset col0), K transposed
+template <int HD>
+__device__ __forceinline__ void att_load_tile(AttSmem<HD> &sm, const float *k, const float *v, size_t ld, int col0, int t0, int nk) {
+    constexpr int C4 = HD / 4;
+    for (int e = threadIdx.x; e < nk * C4; e += blockDim.x) {
+        const int kk = e / C4, c4 = e - kk * C4;
+        sm.kt[c4][kk] = *reinterpret_cast<const float4 *>(k + (size_t)(t0 + kk) * ld + col0 + c4 * 4);
+        reinterpret_cast<float4 *>(sm.vs[kk])[c4] = *reinterpret_cast<const float4 *>(v + (size_t)(t0 + kk) * ld + col0 + c4 * 4);
+    }
+}
+
+// ------------------------------------------------------------------ causal GQA attention (prefill)
+// reference qwen_asr_kernels.c:1101-1148.  head_dim = 128.  CTA = (kv head, 16 query positions) = 32 queries (both
+// query heads of the kv head share every K/V tile); warp w owns queries 4w..4w+3 = positions p0+2w, p0+2w+1 x 2 heads.
+// Query position i attends keys [0, q_offset + i].
 __global__ void __launch_bounds__(256)
 attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, const float *__restrict__ vc,
                     int q_offset, int P, int seq_k, int n_heads, int n_kv_heads, float scale, float *of, bf16_t *ohi,
                     bf16_t *olo) {
-    __shared__ __align__(16) float ks[ATT_KT][128], vs[ATT_KT][128];
+    extern __shared__ __align__(16) uint8_t att_raw[];
+    AttSmem<128> &sm = *reinterpret_cast<AttSmem<128> *>(att_raw);
     const int kvh = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ib = blockIdx.y * 16, i0 = ib + warp * 2;
+    const int ib = blockIdx.y * 16;
     const int per = n_heads / n_kv_heads; // 2
-    const int qld = n_heads * 128, kld = n_kv_heads * 128;
-    const bool act0 = i0 < P, act1 = i0 + 1 < P;
-    float qv[4][4], acc[4][4], m[4], l[4];
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-        const int qi = i0 + (a >> 1), hh = kvh * per + (a & 1);
-        const float4 t4 = ((a < 2) ? act0 : act1) ? *reinterpret_cast<const float4 *>(q + (size_t)qi * qld + hh * 128 + lane * 4)
-                                                 : make_float4(0, 0, 0, 0);
-        qv[a][0] = t4.x; qv[a][1] = t4.y; qv[a][2] = t4.z; qv[a][3] = t4.w;
-        acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.0f;
-        m[a] = -1e30f; l[a] = 0.0f;
+    const size_t qld = (size_t)n_heads * 128, kld = (size_t)n_kv_heads * 128;
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) { // 32 queries x 32 float4
+        const int qi = e >> 5, c4 = e & 31, pos = ib + (qi >> 1), hh = kvh * per + (qi & 1);
+        reinterpret_cast<float4 *>(sm.qs[qi])[c4] = pos < P ? *reinterpret_cast<const float4 *>(q + (size_t)pos * qld + hh * 128 + c4 * 4)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    int kend0 = min(q_offset + i0 + 1, seq_k), kend1 = min(q_offset + i0 + 2, seq_k);
-    if (!act0) kend0 = 0;
-    if (!act1) kend1 = 0;
+    int hi[4];
+    float m[4], l[4], acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int pos = ib + ((warp * 4 + j) >> 1);
+        hi[j] = pos < P ? min(q_offset + pos + 1, seq_k) : 0;
+        m[j] = -1e30f; l[j] = 0.0f;
+        acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+    }
     const int kmax_cta = min(q_offset + min(ib + 16, P), seq_k); // keys needed by the last position of the CTA
     for (int t0 = 0; t0 < kmax_cta; t0 += ATT_KT) {
         const int nk = min(ATT_KT, kmax_cta - t0);
         __syncthreads();
-        for (int e = threadIdx.x; e < nk * 32; e += 256) { // 32 float4 per key row
-            const int kk = e >> 5, c4 = e & 31;
-            reinterpret_cast<float4 *>(ks[kk])[c4] = *reinterpret_cast<const float4 *>(kc + (size_t)(t0 + kk) * kld + kvh * 128 + c4 * 4);
-            reinterpret_cast<float4 *>(vs[kk])[c4] = *reinterpret_cast<const float4 *>(vc + (size_t)(t0 + kk) * kld + kvh * 128 + c4 * 4);
-        }
+        att_load_tile<128>(sm, kc, vc, kld, kvh * 128, t0, nk);
         __syncthreads();
-        const int jend = min(nk, max(kend0, kend1) - t0);
-        for (int jj = 0; jj < jend; jj++) {
-            const int j = t0 + jj;
-            const float4 k4 = reinterpret_cast<const float4 *>(ks[jj])[lane];
-            const float4 v4 = reinterpret_cast<const float4 *>(vs[jj])[lane];
-            const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-            float sc[4];
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-                sc[a] = warp_sum(qv[a][0] * k4.x + qv[a][1] * k4.y + qv[a][2] * k4.z + qv[a][3] * k4.w) * scale;
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-                if (j < ((a < 2) ? kend0 : kend1)) soft_update<4>(sc[a], m[a], l[a], acc[a], vv);
-        }
+        if (t0 < max(max(hi[0], hi[1]), max(hi[2], hi[3]))) att_tile<128>(sm, warp, lane, t0, nk, hi, scale, m, l, acc);
     }
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
-        if (!((a < 2) ? act0 : act1)) continue;
-        const int qi = i0 + (a >> 1), hh = kvh * per + (a & 1);
-        const float inv = l[a] > 0.0f ? 1.0f / l[a] : 0.0f;
-        const size_t base = (size_t)qi * qld + hh * 128 + lane * 4;
+    for (int j = 0; j < 4; j++) {
+        const int qi = warp * 4 + j, pos = ib + (qi >> 1), hh = kvh * per + (qi & 1);
+        if (pos >= P) continue;
+        const float inv = l[j] > 0.0f ? 1.0f / l[j] : 0.0f;
+        const size_t base = (size_t)pos * qld + hh * 128 + lane * 4;
 #pragma unroll
-        for (int c = 0; c < 4; c++) store_out(acc[a][c] * inv, base + c, of, ohi, olo);
+        for (int c = 0; c < 4; c++) store_out(acc[j][c] * inv, base + c, of, ohi, olo);
     }
 }
 void launch_attn_prefill(cudaStream_t s, const float *q, const float *kc, const float *vc, int q_offset, int P, int seq_k,
                          int n_heads, int n_kv_heads, float scale, float *out_f32, bf16_t *out_hi, bf16_t *out_lo) {
     if (P <= 0) return;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttSmem<128>)); attr_set = true; }
     dim3 grid(n_kv_heads, (P + 15) / 16);
-    attn_prefill_kernel<<<grid, 256, 0, s>>>(q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, out_f32, out_hi, out_lo);
+    attn_prefill_kernel<<<grid, 256, sizeof(AttSmem<128>), s>>>(q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, out_f32, out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------ windowed bidirectional attention (encoder)
-// reference qwen_asr_kernels.c:1054-1099.  head_dim = 64: lane owns dims 2l,2l+1; CTA = (head, window,
-// 32 queries), 8 warps x 4 consecutive queries; the window's K/V rows of the head are staged through
-// shared memory in 32-key tiles.  q/k/v may be column slices of one [T, ld] buffer (fused QKV output).
+// reference qwen_asr_kernels.c:1054-1099.  head_dim = 64; CTA = (head, window, 32 queries), warp w owns queries
+// 4w..4w+3; every key of the window is attended.  q/k/v may be column slices of one [T, ld] buffer (fused QKV output).
 __global__ void __launch_bounds__(256)
 attn_windowed_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v, int ld,
                      const int *__restrict__ window_starts, float scale, int out_ld, float *of, bf16_t *ohi,
                      bf16_t *olo) {
-    __shared__ __align__(16) float ks[ATT_KT][64], vs[ATT_KT][64];
+    __shared__ AttSmem<64> sm;
     const int h = blockIdx.x, w = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ws = window_starts[w], we = window_starts[w + 1];
     const int ib = ws + blockIdx.z * 32;
     if (ib >= we) return; // whole CTA
-    const int i0 = ib + warp * 4;
-    float qv[4][2], acc[4][2], m[4], l[4];
+    for (int e = threadIdx.x; e < 32 * 16; e += 256) { // 32 queries x 16 float4
+        const int qi = e >> 4, c4 = e & 15;
+        reinterpret_cast<float4 *>(sm.qs[qi])[c4] = ib + qi < we ? *reinterpret_cast<const float4 *>(q + (size_t)(ib + qi) * ld + h * 64 + c4 * 4)
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    int hi[4];
+    float m[4], l[4], acc[4][2];
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
-        const int qi = i0 + a;
-        const float2 t2 = qi < we ? *reinterpret_cast<const float2 *>(q + (size_t)qi * ld + h * 64 + lane * 2) : make_float2(0, 0);
-        qv[a][0] = t2.x; qv[a][1] = t2.y;
-        acc[a][0] = acc[a][1] = 0.0f;
-        m[a] = -1e30f; l[a] = 0.0f;
+    for (int j = 0; j < 4; j++) {
+        hi[j] = ib + warp * 4 + j < we ? we : 0;
+        m[j] = -1e30f; l[j] = 0.0f;
+        acc[j][0] = acc[j][1] = 0.0f;
     }
     for (int t0 = ws; t0 < we; t0 += ATT_KT) {
         const int nk = min(ATT_KT, we - t0);
         __syncthreads();
-        for (int e = threadIdx.x; e < nk * 16; e += 256) { // 16 float4 per key row
-            const int kk = e >> 4, c4 = e & 15;
-            reinterpret_cast<float4 *>(ks[kk])[c4] = *reinterpret_cast<const float4 *>(k + (size_t)(t0 + kk) * ld + h * 64 + c4 * 4);
-            reinterpret_cast<float4 *>(vs[kk])[c4] = *reinterpret_cast<const float4 *>(v + (size_t)(t0 + kk) * ld + h * 64 + c4 * 4);
-        }
+        att_load_tile<64>(sm, k, v, (size_t)ld, h * 64, t0, nk);
         __syncthreads();
-        if (i0 < we)
-            for (int jj = 0; jj < nk; jj++) {
-                const float2 k2 = reinterpret_cast<const float2 *>(ks[jj])[lane];
-                const float2 v2 = reinterpret_cast<const float2 *>(vs[jj])[lane];
-                const float vv[2] = {v2.x, v2.y};
-                float sc[4];
-#pragma unroll
-                for (int a = 0; a < 4; a++) sc[a] = warp_sum(qv[a][0] * k2.x + qv[a][1] * k2.y) * scale;
-#pragma unroll
-                for (int a = 0; a < 4; a++) soft_update<2>(sc[a], m[a], l[a], acc[a], vv);
-            }
+        if (hi[0] > 0) att_tile<64>(sm, warp, lane, t0, nk, hi, scale, m, l, acc);
     }
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
-        const int qi = i0 + a;
+    for (int j = 0; j < 4; j++) {
+        const int qi = ib + warp * 4 + j;
         if (qi >= we) break;
-        const float inv = l[a] > 0.0f ? 1.0f / l[a] : 0.0f;
+        const float inv = l[j] > 0.0f ? 1.0f / l[j] : 0.0f;
         const size_t base = (size_t)qi * out_ld + h * 64 + lane * 2;
-        store_out(acc[a][0] * inv, base, of, ohi, olo);
-        store_out(acc[a][1] * inv, base + 1, of, ohi, olo);
+        store_out(acc[j][0] * inv, base, of, ohi, olo);
+        store_out(acc[j][1] * inv, base + 1, of, ohi, olo);
     }
 }
 void launch_attn_windowed(cudaStream_t s, const float *q, const float *k, const float *v, int ld, int n_heads,

@@ -10,7 +10,8 @@ f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER
 shapes = [("pre.qkv", 61, 2048, 4096), ("pre.wo", 61, 2048, 2048), ("pre.gu", 61, 2048, 12288), ("pre.down", 61, 6144, 2048),
           ("enc.qkv", 47, 1024, 3072), ("enc.wo", 47, 1024, 1024), ("enc.fc1", 47, 1024, 4096), ("enc.fc2", 47, 4096, 1024),
           ("conv2", 1456, 4320, 480), ("conv3", 384, 4320, 480), ("convout", 47, 7680, 1024),
-          ("jfk.qkv", 157, 1024, 4096), ("30s.gu", 404, 2048, 12288)]
+          ("jfk.qkv", 157, 1024, 4096), ("30s.gu", 404, 2048, 12288), ("30s.down", 404, 6144, 2048),
+          ("b4.enc.fc1", 1560, 1024, 4096), ("b4.pre.gu", 1616, 2048, 12288), ("b16.enc.fc1", 6240, 1024, 4096), ("big", 8192, 4096, 8192)]
 for name, M, K, N in shapes:
     us = C.c_double(0)
     rc = f(eng.ctx, M, K, N, 64, 0, C.byref(us))
