@@ -402,7 +402,8 @@ static void select_seq(qasr_ctx_t *c, int q) { c->seq = q; c->kv_k = c->kv_ks[q]
 static int ensure_kv(qasr_ctx_t *c, int need_pos, int keep) {
     const size_t kvd = (size_t)c->kv_heads * c->hd;
     if (need_pos <= c->kv_max && c->kv_ks[c->seq]) return 0;
-    int cap = c->kv_max ? c->kv_max : 2048;
+    int cap = c->kv_max;
+    if (!cap) { const char *e = getenv("QASR_KV_INIT_ROWS"); cap = e && atoi(e) > 0 ? atoi(e) : 2048; } // reference: seq + 1024 (qwen_asr_decoder.c:168-177)
     while (cap < need_pos) cap *= 2;
     const size_t bytes = (size_t)c->dec_layers * cap * kvd * 4;
     CK(cudaStreamSynchronize(c->stream));
@@ -1268,7 +1269,8 @@ int qasr_cuda_transcribe_batch(qasr_ctx_t *c, const float *const *samples, const
     int i = 0;
     while (i < count) {
         int B = count - i >= 4 && maxb >= 4 ? 4 : (count - i >= 2 && maxb >= 2 ? 2 : 1);
-        CKR(transcribe_group(c, samples + i, n_samples + i, B, max_new + i, ids_stride, out_ids + (size_t)i * ids_stride, out_n + i, timings_ms));
+        const int rc = transcribe_group(c, samples + i, n_samples + i, B, max_new + i, ids_stride, out_ids + (size_t)i * ids_stride, out_n + i, timings_ms);
+        if (rc != 0) { select_seq(c, 0); return rc; }
         i += B;
     }
     select_seq(c, 0);

@@ -244,3 +244,20 @@ def test_batched_decode_1p7b_pairs(pkg, model17):
         assert [b.tolist() for b in batched] == single
     finally:
         eng.close()
+
+
+def test_kv_cache_growth_preserves_every_sequence(pkg, model06, monkeypatch):
+    """KV caches start tiny (QASR_KV_INIT_ROWS=32) so prefill, single-sequence decode and the batched decode all
+    cross several capacity doublings (reference kv_cache_grow, qwen_asr_decoder.c:179-206); ids must not change."""
+    units = [pkg.synth_audio(s, seed=70 + i) for i, s in enumerate([2.4, 1.1, 3.0, 1.6])]
+    ref = pkg.QasrCuda(0).load(model06)
+    want = [ref.transcribe_ids(u, 14)[0].tolist() for u in units]
+    ref.close()
+    monkeypatch.setenv("QASR_KV_INIT_ROWS", "32")
+    eng = pkg.QasrCuda(0).load(model06)
+    try:
+        assert [eng.transcribe_ids(u, 14)[0].tolist() for u in units] == want
+        got, _ = eng.transcribe_batch(units, 14)
+        assert [g.tolist() for g in got] == want
+    finally:
+        eng.close()
