@@ -964,6 +964,7 @@ static int enqueue_steps(qasr_ctx_t *c, int n, int nseq = 1) {
         { const char *dbg = getenv("QASR_MEGA_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
         { const char *tc = getenv("QASR_MEGA_TRACE_CTA"); p.trace_cta = tc ? atoi(tc) : 0; }
         { const char *e = getenv("QASR_SK_L2AHEAD"); p.l2_ahead_units = e ? atoi(e) : 8; }
+        { const char *e = getenv("QASR_SK_L2ISSUE"); p.l2_issue = e ? atoi(e) : 2; }
         if (launch_decode_stream(c->stream, p) != 0) return set_err(QASR_ERR_CUDA, "%s", stream_error());
         c->launches += 1;
         return 0;

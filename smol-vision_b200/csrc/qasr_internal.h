@@ -91,6 +91,7 @@ struct StreamParams {
     int prof_cap;
     int debug;
     int trace_cta;                         // CTA whose warp 0 writes the per-unit trace (debug bit 6)
+    int l2_issue;                          // units prefetched per poll iteration
     int l2_ahead_units;                    // second-level prefetch distance into L2, in 2 KB units per warp (0 = off)
 };
 int stream_init(void);

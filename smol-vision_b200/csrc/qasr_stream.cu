@@ -283,6 +283,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
 #pragma unroll
     for (int i = 0; i < SLOTS; i++) fetch_into(i);
     auto top_up = [&]() { // service hook of every poll loop (runs converged: the loops are warp-uniform)
+#pragma unroll 1
+        for (int rep = 0; rep < p.l2_issue; rep++) // units per poll iteration
         if (lpos - fpos < l2_window) {
             if (lane < 16) {
                 if (p.debug & 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + loff + lane * 128) : "memory");
