@@ -201,7 +201,7 @@ struct SkLayout {
     static __host__ __device__ size_t xf_bytes(int kmax) { return (size_t)kmax * 4 * NSEQ; }            // [kb][8*NSEQ lanes][2] u32
     static __host__ __device__ size_t x_bytes(int H) { return (size_t)NSEQ * H * 4; }
     static constexpr size_t partial_bytes = (size_t)2 * 128 * SK_PSTRIDE * 4;
-    static constexpr size_t small_bytes = (64 + NSEQ * SK_WARPS + SK_WARPS) * 4;
+    static constexpr size_t small_bytes = (64 + NSEQ * SK_WARPS + SK_WARPS + NSEQ * 16 * SK_ATT_MAXS) * 4;
     static __host__ __device__ size_t total(int kmax, int H) { return ring_bytes + xf_bytes(kmax) + x_bytes(H) + partial_bytes + small_bytes + 1024; }
 };
 
@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
     float *sm_red = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(sm_partial) + LY::partial_bytes); // [64]
     float *sm_ssq = sm_red + 64;                                                                            // [NSEQ][16]
     int *sm_redi = reinterpret_cast<int *>(sm_ssq + NSEQ * SK_WARPS);                                       // [16]
+    float *sm_fac = reinterpret_cast<float *>(sm_redi + SK_WARPS);                                         // [NSEQ][16 heads][SK_ATT_MAXS] split weights
 
     for (int e = tid; e < NSEQ * H; e += SK_THREADS) sm_x[e] = p.x_io[e];
     __syncthreads();
@@ -607,6 +608,94 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             mark();
             // ---------------- WO: input = attention output merged over the S key splits
             {
+                if constexpr (NSEQ == 4) { // two-phase merge: fewer words per thread, one extra bar.sync (pays off only with 4 sequences)
+                // (1) softmax weights of the key splits, once per (sequence, head): thread t < 16 NSEQ polls the S (m, l) pairs
+                {
+                    const bool act_a = tid < NSEQ * 16;
+                    const u64 *pm = p.ll_att + (tid >> 4) * att_words + (size_t)((tid & 15) * SK_ATT_MAXS) * SK_ATT_STRIDE + 128;
+                    u64 wm[SK_ATT_MAXS][2];
+#pragma unroll
+                    for (int t = 0; t < SK_ATT_MAXS; t++) {
+                        if (act_a && t < S) ll_load2(pm + t * SK_ATT_STRIDE, wm[t][0], wm[t][1]);
+                        else wm[t][0] = wm[t][1] = (u64)tag << 32;
+                    }
+                    for (;;) {
+                        bool ok = true;
+#pragma unroll
+                        for (int t = 0; t < SK_ATT_MAXS; t++) ok = ok && (unsigned)(wm[t][0] >> 32) == tag && (unsigned)(wm[t][1] >> 32) == tag;
+                        if (__all_sync(QASR_FULL, ok)) break;
+                        top_up();
+#pragma unroll
+                        for (int t = 0; t < SK_ATT_MAXS; t++)
+                            if ((unsigned)(wm[t][0] >> 32) != tag || (unsigned)(wm[t][1] >> 32) != tag) ll_load2(pm + t * SK_ATT_STRIDE, wm[t][0], wm[t][1]);
+                    }
+                    if (act_a) {
+                        float M = -1e30f, Ls = 0.f, e[SK_ATT_MAXS];
+#pragma unroll
+                        for (int t = 0; t < SK_ATT_MAXS; t++)
+                            if (t < S) M = fmaxf(M, __uint_as_float((unsigned)wm[t][0]));
+#pragma unroll
+                        for (int t = 0; t < SK_ATT_MAXS; t++) {
+                            e[t] = t < S ? expf(__uint_as_float((unsigned)wm[t][0]) - M) : 0.0f;
+                            Ls += t < S ? __uint_as_float((unsigned)wm[t][1]) * e[t] : 0.0f;
+                        }
+                        const float invL = Ls > 0.0f ? 1.0f / Ls : 0.0f;
+#pragma unroll
+                        for (int t = 0; t < SK_ATT_MAXS; t++) sm_fac[tid * SK_ATT_MAXS + t] = e[t] * invL;
+                    }
+                    sk_csync();
+                }
+                // (2) weighted sum of the split accumulators: PG pairs per thread in flight together
+                auto merge_splits = [&](auto ns_c, auto pg_c) { // NS = compile-time bound on S
+                    constexpr int NS = decltype(ns_c)::value, PG = decltype(pg_c)::value;
+#pragma unroll 1
+                    for (int i0 = 0; i0 < 2 * NSEQ; i0 += PG) {
+                        u64 w[PG][NS][2];
+                        const u64 *pb[PG];
+#pragma unroll
+                        for (int g = 0; g < PG; g++) {
+                            const int q = tid + (i0 + g) * SK_THREADS;   // pair q = s * 1024 + pr: elements 2pr, 2pr+1 of sequence s' head-major vector
+                            const int pr = q & 1023;
+                            pb[g] = p.ll_att + (q >> 10) * att_words + (size_t)((pr >> 6) * SK_ATT_MAXS) * SK_ATT_STRIDE + (pr & 63) * 2;
+#pragma unroll
+                            for (int t = 0; t < NS; t++) {
+                                if (t < S) ll_load2(pb[g] + t * SK_ATT_STRIDE, w[g][t][0], w[g][t][1]);
+                                else w[g][t][0] = w[g][t][1] = (u64)tag << 32;
+                            }
+                        }
+                        for (;;) {
+                            bool ok = true;
+#pragma unroll
+                            for (int g = 0; g < PG; g++)
+#pragma unroll
+                                for (int t = 0; t < NS; t++) ok = ok && (unsigned)(w[g][t][0] >> 32) == tag && (unsigned)(w[g][t][1] >> 32) == tag;
+                            if (__all_sync(QASR_FULL, ok)) break;
+                            top_up();
+#pragma unroll
+                            for (int g = 0; g < PG; g++)
+#pragma unroll
+                                for (int t = 0; t < NS; t++)
+                                    if ((unsigned)(w[g][t][0] >> 32) != tag || (unsigned)(w[g][t][1] >> 32) != tag) ll_load2(pb[g] + t * SK_ATT_STRIDE, w[g][t][0], w[g][t][1]);
+                        }
+#pragma unroll
+                        for (int g = 0; g < PG; g++) {
+                            const int q = tid + (i0 + g) * SK_THREADS, pr = q & 1023;
+                            const float *f = sm_fac + ((q >> 10) * 16 + (pr >> 6)) * SK_ATT_MAXS;
+                            float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+                            for (int t = 0; t < NS; t++)
+                                if (t < S) {
+                                    o0 = fmaf(__uint_as_float((unsigned)w[g][t][0]), f[t], o0);
+                                    o1 = fmaf(__uint_as_float((unsigned)w[g][t][1]), f[t], o1);
+                                }
+                            sk_put_pair<NSEQ>(sm_xf, q >> 10, pr, o0, o1);
+                        }
+                    }
+                };
+                if (S == 1) merge_splits(std::integral_constant<int, 1>{}, std::integral_constant<int, 2 * NSEQ>{});
+                else if (S == 2) merge_splits(std::integral_constant<int, 2>{}, std::integral_constant<int, (NSEQ > 2 ? 4 : 2 * NSEQ)>{});
+                else merge_splits(std::integral_constant<int, SK_ATT_MAXS>{}, std::integral_constant<int, 2>{});
+                } else {
                 auto merge_splits = [&](auto ns_c, auto pg_c) { // NS = compile-time bound on S; PG = pairs per thread whose loads fly together
                     constexpr int NS = decltype(ns_c)::value, PG = decltype(pg_c)::value;
 #pragma unroll 1
@@ -667,6 +756,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
                 };
                 if (S == 1) merge_splits(std::integral_constant<int, 1>{}, std::integral_constant<int, 2 * NSEQ>{});
                 else merge_splits(std::integral_constant<int, SK_ATT_MAXS>{}, std::integral_constant<int, 2>{});
+                }
                 sk_csync();
                 mark();
                 run_phase(H, 2048, [&](int s, int row, int r, auto &&rowsum) { ll_store(p.ll_xwo + s * H + row, sm_x[s * H + row] + rowsum(r), tag); });
@@ -684,13 +774,14 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             mark();
             // ---------------- DOWN
             {
-                const int ip = I >> 1, total = NSEQ * ip; // the NSEQ activation vectors as one long vector, 6 pairs per thread per pass
+                const int ip = I >> 1, total = NSEQ * ip; // the NSEQ activation vectors as one long vector
+                constexpr int NPD = NSEQ == 4 ? 12 : 6;   // pairs per thread in flight per pass
 #pragma unroll 1
-                for (int base = 0; base < total; base += 6 * SK_THREADS) {
-                    float v[6][2];
-                    ll_gather_pairs<6>(p.ll_act + 2 * (size_t)base, min(total - base, 6 * SK_THREADS), tag, tid, v, top_up);
+                for (int base = 0; base < total; base += NPD * SK_THREADS) {
+                    float v[NPD][2];
+                    ll_gather_pairs<NPD>(p.ll_act + 2 * (size_t)base, min(total - base, NPD * SK_THREADS), tag, tid, v, top_up);
 #pragma unroll
-                    for (int i = 0; i < 6; i++) {
+                    for (int i = 0; i < NPD; i++) {
                         const int q = base + tid + i * SK_THREADS;
                         if (q < total) {
                             const int s = NSEQ == 1 ? 0 : q / ip;
