@@ -38,6 +38,7 @@
 #include "qasr_internal.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <type_traits>
 
 #define SK_WARPS 16
@@ -916,6 +917,7 @@ int stream_init(void) {
         return -1;
     }
     g_sk_grid = sms;
+    { const char *e = getenv("QASR_SK_GRID"); if (e && atoi(e) >= 16 && atoi(e) <= sms) g_sk_grid = atoi(e); } // fewer CTAs = cheaper exchanges, less streaming headroom
     return 0;
 }
 int stream_grid(void) { return stream_init() == 0 ? g_sk_grid : 0; }

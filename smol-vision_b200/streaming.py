@@ -36,8 +36,9 @@ def common_prefix_rows(a, b):
 
 
 class StreamSession:
-    def __init__(self, engine, window_sec=8.0, max_windows=4, max_new=32, pre_ids=PROMPT_PRE, suf_ids=PROMPT_SUF):
+    def __init__(self, engine, window_sec=8.0, max_windows=4, max_new=32, pre_ids=PROMPT_PRE, suf_ids=PROMPT_SUF, enc_cache=True):
         self.eng = engine
+        self.enc_cache = enc_cache    # False = re-encode every window on every chunk (reference QWEN_STREAM_NO_ENC_CACHE=1, qwen_asr.c:1352)
         self.window = int(round(window_sec * SAMPLE_RATE))
         self.max_windows = max_windows
         self.max_new = max_new
@@ -60,7 +61,7 @@ class StreamSession:
         n_full = len(samples) // self.window
         new_windows = 0
         for w in range(max(0, n_full - self.max_windows), n_full):
-            if w not in self.win_rows:
+            if w not in self.win_rows or not self.enc_cache:
                 self.win_rows[w] = self._encode_span(samples[w * self.window:(w + 1) * self.window])
                 new_windows += 1
         for w in [k for k in self.win_rows if k < n_full - self.max_windows]:

@@ -261,3 +261,15 @@ def test_kv_cache_growth_preserves_every_sequence(pkg, model06, monkeypatch):
         assert [g.tolist() for g in got] == want
     finally:
         eng.close()
+
+
+def test_stream_encoder_cache_equivalence(gpu06, pkg):
+    """The reference's only exact-equality test (asr_regression.py:388-513, `make test-stream-cache`): streaming with the
+    encoder-window cache must give byte-identical output to re-encoding every window on every chunk
+    (QWEN_STREAM_NO_ENC_CACHE=1).  Here: identical ids AND identical prefix reuse, chunk by chunk."""
+    audio = pkg.synth_audio(7.0, seed=33)
+    kw = dict(window_sec=2.0, max_windows=2, max_new=5)
+    a = pkg.streaming.run_stream(gpu06, audio, 1.0, enc_cache=True, **kw)
+    b = pkg.streaming.run_stream(gpu06, audio, 1.0, enc_cache=False, **kw)
+    assert [(r["ids"], r["reused"], r["rows"]) for r in a] == [(r["ids"], r["reused"], r["rows"]) for r in b]
+    assert sum(r["new_windows"] for r in a) == 3 and sum(r["new_windows"] for r in b) > 3

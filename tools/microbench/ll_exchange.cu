@@ -81,19 +81,22 @@ __global__ void __launch_bounds__(512, 1) k(u64 *ll_base, float *plain, unsigned
     if (tid == 0) out[b] = t1 - t0;
     if (acc == 1234.5f) out[200] = 1;
 }
+static int g_grid = 148;
 template <int NP> void run(int N, int mode, const char *name) {
     u64 *ll; float *plain; unsigned *gbar; long long *out;
     CK(cudaMalloc(&ll, 2 * 8192 * 8)); CK(cudaMemset(ll, 0, 2 * 8192 * 8));
     CK(cudaMalloc(&plain, 8192 * 4)); CK(cudaMalloc(&gbar, 4)); CK(cudaMemset(gbar, 0, 4)); CK(cudaMalloc(&out, 256 * 8));
     int iters = 2000;
     void *args[] = {&ll, &plain, &gbar, &out, &N, &iters, &mode};
-    CK(cudaLaunchCooperativeKernel((const void *)k<NP>, dim3(148), dim3(512), args, 0, 0));
+    CK(cudaLaunchCooperativeKernel((const void *)k<NP>, dim3(g_grid), dim3(512), args, 0, 0));
     CK(cudaDeviceSynchronize());
     long long h[148]; CK(cudaMemcpy(h, out, sizeof h, cudaMemcpyDeviceToHost));
-    printf("%-52s N=%4d: %.3f us per exchange\n", name, N, (double)h[0] / iters / 1965.0);
+    printf("grid %3d  %-44s N=%4d: %.3f us per exchange\n", g_grid, name, N, (double)h[0] / iters / 1965.0);
     cudaFree(ll); cudaFree(plain); cudaFree(gbar); cudaFree(out);
 }
-int main() {
+int main(int argc, char **argv) {
+    for (int gi = 1; gi < argc; gi++) { g_grid = atoi(argv[gi]); run<2>(1024, 0, "A. LL all-gather"); run<2>(2048, 0, "A. LL all-gather"); run<6>(6144, 0, "A. LL all-gather"); }
+    if (argc > 1) return 0;
     run<2>(2048, 0, "A. LL all-gather");
     run<6>(6144, 0, "A. LL all-gather");
     run<2>(2048, 1, "B. grid barrier + plain L2 read");
