@@ -67,6 +67,32 @@ def ncu_traffic_per_step(variant):
     return float(json.load(open(p))["dram_bytes_per_step"])
 
 
+def gemm_rooflines(eng):
+    """Secondary rooflines of the tcgen05 GEMM path (north_star items 2-3), device-timed by the library's own hook
+    (CUDA-graph replay of 64 launches): the prefill GEMM of this workload against the HBM roofline (a weight stream at
+    M = 61) and a batched-encoder / large shape against the measured bf16 tensor peak (hi+lo operand planes: two MMAs
+    per k-block are issued and counted)."""
+    import ctypes as C
+    f = eng.lib.qasr_debug_gemm_bench
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peaks_d = json.load(open(p)) if os.path.exists(p) else {}
+    hbm, tf = float(peaks_d.get("hbm_gbs", 6650.0)), float(peaks_d.get("bf16_tflops_sustained", peaks_d.get("bf16_tflops", 2250.0)))
+    out = []
+    for name, M, K, N, bound in (("prefill gate/up, M=61", 61, 2048, 12288, "hbm"), ("encoder fc1, 16 x 30 s batched, M=6240", 6240, 1024, 4096, "tensor"),
+                                 ("8192 x 8192 x 4096", 8192, 4096, 8192, "tensor")):
+        us = C.c_double(0)
+        if f(eng.ctx, M, K, N, 64, 0, C.byref(us)) != 0 or us.value <= 0:
+            continue
+        if bound == "hbm":
+            ach = 2.0 * N * K / us.value / 1e3
+            out.append({"shape": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "us": us.value})
+        else:
+            ach = 2.0 * 2.0 * M * N * K / us.value / 1e6
+            out.append({"shape": name, "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s (hi+lo MMAs)", "frac": ach / tf, "us": us.value})
+    return out
+
+
 def decode_bytes_per_step(cfg, kv_positions):
     """Algorithmic bytes of one decode step: bf16 decoder-layer weights + tied lm_head
     + f32 KV rows read (229 376 B per cached position)."""
@@ -448,6 +474,10 @@ def main():
                             "kernel": "one greedy step of decode_stream_kernel (persistent cooperative kernel, qasr_stream.cu; a launch runs up to 16 steps)",
                             "bytes_per_launch": step_bytes, "ms_per_launch": dec_ms_per_step,
                             "frac_of_8000_nominal": achieved / 8000.0}}
+        try:
+            out["gemm_rooflines"] = gemm_rooflines(eng)
+        except Exception as ex:  # debug hook missing: the headline does not depend on it
+            out["gemm_rooflines"] = str(ex)[:120]
         if not args.no_cpu_baseline:
             try:
                 r = cpu_reference_run(variant, audio, max_new, 0, 2)
