@@ -273,3 +273,17 @@ def test_stream_encoder_cache_equivalence(gpu06, pkg):
     b = pkg.streaming.run_stream(gpu06, audio, 1.0, enc_cache=False, **kw)
     assert [(r["ids"], r["reused"], r["rows"]) for r in a] == [(r["ids"], r["reused"], r["rows"]) for r in b]
     assert sum(r["new_windows"] for r in a) == 3 and sum(r["new_windows"] for r in b) > 3
+
+
+@pytest.mark.parametrize("mode", ["graph", "mega2"])
+def test_comparison_decode_paths_give_identical_ids(pkg, model06, gpu06, monkeypatch, mode):
+    """QASR_DECODE=graph (per-phase kernels in a CUDA graph) and =mega2 (grid-barrier megakernel) are kept as the
+    comparison paths of profiles/README.md; they must produce the ids of the default streaming kernel."""
+    audio = pkg.synth_audio(2.3, seed=17)
+    want = gpu06.transcribe_ids(audio, 12)[0].tolist()
+    monkeypatch.setenv("QASR_DECODE", mode)
+    eng = pkg.QasrCuda(0).load(model06)
+    try:
+        assert eng.transcribe_ids(audio, 12)[0].tolist() == want
+    finally:
+        eng.close()
