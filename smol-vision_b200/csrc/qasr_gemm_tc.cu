@@ -194,58 +194,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         }
     } else {
         // ===== epilogue warps 2..5 =====
+        // tcgen05.ld hands thread i the 32 columns of ROW i; storing from that layout makes every store instruction touch
+        // 32 different rows (32 memory transactions for 128 bytes, and 2-byte scattered stores for the bf16 planes), which
+        // bounded the medium-M GEMMs.  Each 32 x 32 block is transposed through shared memory (the operand ring is free:
+        // the accumulator barrier fires only after every MMA has read it) so that a warp stores 32 consecutive columns of
+        // one row per instruction.
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int q = warp & 3; // TMEM lane quarter this warp may access
-        const int row = m0 + q * 32 + lane;
+        float *stage = reinterpret_cast<float *>(smem) + q * (32 * 33);
         const GemmEpilogue &e = p.epi;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
             tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            if (row < p.M) {
-                const int nb = n0 + c0;
-                if (e.mode == QASR_GEMM_F32 || e.mode == QASR_GEMM_RESIDUAL) {
-                    float *orow = e.out_f32 + (size_t)row * e.ldo;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int n = nb + j;
-                        if (n < p.N) {
-                            float v = __uint_as_float(r[j]);
-                            if (e.bias) v += e.bias[n];
-                            if (e.mode == QASR_GEMM_RESIDUAL) v += orow[n];
-                            orow[n] = v;
-                        }
+            for (int j = 0; j < 32; j++) stage[lane * 33 + j] = __uint_as_float(r[j]);
+            __syncwarp();
+            const int n = n0 + c0 + lane;
+            const float bias = (e.bias && n < p.N) ? e.bias[n] : 0.0f;
+            const int rows = min(32, p.M - (m0 + q * 32));
+            for (int rr = 0; rr < rows; rr++) {
+                const int row = m0 + q * 32 + rr;
+                float v = stage[rr * 33 + lane];
+                if (e.mode == QASR_GEMM_F32 || e.mode == QASR_GEMM_RESIDUAL) {
+                    if (n < p.N) {
+                        float *o = e.out_f32 + (size_t)row * e.ldo + n;
+                        v += bias;
+                        if (e.mode == QASR_GEMM_RESIDUAL) v += *o;
+                        *o = v;
                     }
                 } else if (e.mode == QASR_GEMM_GELU_SPLIT) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int n = nb + j;
-                        if (n < p.N) {
-                            float v = __uint_as_float(r[j]);
-                            if (e.bias) v += e.bias[n];
-                            v = gelu_tanh(v);
-                            __nv_bfloat16 hi, lo;
-                            split_bf16(v, hi, lo);
-                            e.out_hi[(size_t)row * e.ldo + n] = __bfloat16_as_ushort(hi);
-                            if (e.out_lo) e.out_lo[(size_t)row * e.ldo + n] = __bfloat16_as_ushort(lo);
-                        }
+                    if (n < p.N) {
+                        v = gelu_tanh(v + bias);
+                        __nv_bfloat16 hi, lo;
+                        split_bf16(v, hi, lo);
+                        e.out_hi[(size_t)row * e.ldo + n] = __bfloat16_as_ushort(hi);
+                        if (e.out_lo) e.out_lo[(size_t)row * e.ldo + n] = __bfloat16_as_ushort(lo);
                     }
-                } else { // SWIGLU: columns (2j, 2j+1) = (gate_j, up_j), reference qwen_asr_decoder.c:140-152
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const int n = nb + j;
-                        if (n + 1 < p.N) {
-                            const float g = __uint_as_float(r[j]), u = __uint_as_float(r[j + 1]);
-                            const float v = silu(g) * u;
-                            __nv_bfloat16 hi, lo;
-                            split_bf16(v, hi, lo);
-                            e.out_hi[(size_t)row * e.ldo + (n >> 1)] = __bfloat16_as_ushort(hi);
-                            if (e.out_lo) e.out_lo[(size_t)row * e.ldo + (n >> 1)] = __bfloat16_as_ushort(lo);
-                        }
+                } else { // SWIGLU: columns (2j, 2j+1) = (gate_j, up_j) sit in neighbouring lanes, reference qwen_asr_decoder.c:140-152
+                    const float u = __shfl_down_sync(0xffffffffu, v, 1);
+                    if (!(lane & 1) && n + 1 < p.N) {
+                        const float w = silu(v) * u;
+                        __nv_bfloat16 hi, lo;
+                        split_bf16(w, hi, lo);
+                        e.out_hi[(size_t)row * e.ldo + (n >> 1)] = __bfloat16_as_ushort(hi);
+                        if (e.out_lo) e.out_lo[(size_t)row * e.ldo + (n >> 1)] = __bfloat16_as_ushort(lo);
                     }
                 }
             }
+            __syncwarp();
         }
         tc_fence_before();
     }

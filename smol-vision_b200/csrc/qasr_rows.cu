@@ -288,8 +288,13 @@ attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, c
 void launch_attn_prefill(cudaStream_t s, const float *q, const float *kc, const float *vc, int q_offset, int P, int seq_k,
                          int n_heads, int n_kv_heads, float scale, float *out_f32, bf16_t *out_hi, bf16_t *out_lo) {
     if (P <= 0) return;
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttSmem<128>)); attr_set = true; }
+    static unsigned attr_set = 0; // per-device bit: the attribute belongs to the (function, device) pair
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_set >> (dev & 31) & 1u)) {
+        cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttSmem<128>));
+        attr_set |= 1u << (dev & 31);
+    }
     dim3 grid(n_kv_heads, (P + 15) / 16);
     attn_prefill_kernel<<<grid, 256, sizeof(AttSmem<128>), s>>>(q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, out_f32, out_hi, out_lo);
 }
