@@ -70,14 +70,14 @@ def ncu_traffic_per_step(variant):
 def gemm_rooflines(eng):
     """Secondary rooflines of the tcgen05 GEMM path (north_star items 2-3), device-timed by the library's own hook
     (CUDA-graph replay of 64 launches): the prefill GEMM of this workload against the HBM roofline (a weight stream at
-    M = 61) and a batched-encoder / large shape against the measured bf16 tensor peak (hi+lo operand planes: two MMAs
-    per k-block are issued and counted)."""
+    M = 61) and a batched-encoder / large shape against the measured (burst) bf16 tensor peak (hi+lo operand planes: two
+    MMAs per k-block are issued and counted)."""
     import ctypes as C
     f = eng.lib.qasr_debug_gemm_bench
     f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peaks_d = json.load(open(p)) if os.path.exists(p) else {}
-    hbm, tf = float(peaks_d.get("hbm_gbs", 6650.0)), float(peaks_d.get("bf16_tflops_sustained", peaks_d.get("bf16_tflops", 2250.0)))
+    hbm, tf = float(peaks_d.get("hbm_gbs", 6650.0)), float(peaks_d.get("bf16_tflops", 2250.0))  # burst figure: these kernels are timed alone
     out = []
     for name, M, K, N, bound in (("prefill gate/up, M=61", 61, 2048, 12288, "hbm"), ("encoder fc1, 16 x 30 s batched, M=6240", 6240, 1024, 4096, "tensor"),
                                  ("8192 x 8192 x 4096", 8192, 4096, 8192, "tensor")):

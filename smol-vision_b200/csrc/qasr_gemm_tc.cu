@@ -630,12 +630,14 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
     }
     // Narrow tiles when the 128-wide grid would leave most of the 148 SMs idle.
     const int tiles128 = ((M + TC_BM - 1) / TC_BM) * ((N + 127) / 128);
-    const bool bn64 = tiles128 < 120;
+    static int force_bn = -1;
+    if (force_bn < 0) { const char *ev = getenv("QASR_GEMM_FORCE_BN"); force_bn = ev ? atoi(ev) : 0; }
+    const bool bn64 = force_bn ? force_bn == 64 : tiles128 < 80; // measured crossover (tools/gemm_bench.py medium): 84-96 tiles are faster at 128 wide
     // 128 x 256 tiles (43 -> 65 MACs per byte of L2 -> shared traffic: the 128 x 128 kernel is L2-feed bound with hi/lo
     // operands) once there are enough tiles to fill the SMs for several waves
     static int bn256_min_tiles = -1;
     if (bn256_min_tiles < 0) { const char *ev = getenv("QASR_GEMM_BN256_MIN_TILES"); bn256_min_tiles = ev ? atoi(ev) : 400; }
-    const bool bn256 = !bn64 && ((M + TC_BM - 1) / TC_BM) * ((N + 255) / 256) >= bn256_min_tiles;
+    const bool bn256 = force_bn ? force_bn == 256 : (!bn64 && ((M + TC_BM - 1) / TC_BM) * ((N + 255) / 256) >= bn256_min_tiles);
     TcParams p;
     p.M = M; p.N = N; p.K = K;
     p.nsplit = A_lo ? 2 : 1;

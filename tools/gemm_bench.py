@@ -12,6 +12,12 @@ shapes = [("pre.qkv", 61, 2048, 4096), ("pre.wo", 61, 2048, 2048), ("pre.gu", 61
           ("conv2", 1456, 4320, 480), ("conv3", 384, 4320, 480), ("convout", 47, 7680, 1024),
           ("jfk.qkv", 157, 1024, 4096), ("30s.gu", 404, 2048, 12288), ("30s.down", 404, 6144, 2048),
           ("b4.enc.fc1", 1560, 1024, 4096), ("b4.pre.gu", 1616, 2048, 12288), ("b16.enc.fc1", 6240, 1024, 4096), ("big", 8192, 4096, 8192)]
+if len(sys.argv) > 1 and sys.argv[1] == "medium":
+    shapes = [("06.pre.qkv", 274, 1024, 4096), ("06.pre.wo", 274, 2048, 1024), ("06.pre.gu", 274, 1024, 6144), ("06.pre.down", 274, 3072, 1024),
+              ("06.enc.qkv", 260, 896, 2688), ("06.enc.wo", 260, 896, 896), ("06.enc.fc1", 260, 896, 3584), ("06.enc.fc2", 260, 3584, 896),
+              ("17.pre.qkv", 404, 2048, 4096), ("17.pre.wo", 404, 2048, 2048), ("17.pre.gu", 404, 2048, 12288), ("17.pre.down", 404, 6144, 2048),
+              ("17.enc.qkv", 390, 1024, 3072), ("17.enc.wo", 390, 1024, 1024), ("17.enc.fc1", 390, 1024, 4096), ("17.enc.fc2", 390, 4096, 1024),
+              ("conv2.30s", 48000, 4320, 480), ("conv3.30s", 12000, 4320, 480)]
 for name, M, K, N in shapes:
     us = C.c_double(0)
     rc = f(eng.ctx, M, K, N, 64, 0, C.byref(us))

@@ -17,9 +17,9 @@ Regenerate: `python tools/update_profiles.py <prefix of the gpurun_out captures>
 
 ## Headline (configs[1]: 1.7B, 3.64 s utterance, 32 tokens)
 
-130.2 x realtime device-timed, 130.9 x end to end through the C ABI with host buffers (28.0 ms per utterance:
-mel 0.12 + encoder 2.00 + prefill 3.86 + decode 21.92 ms); the reference's CPU path on the box's 16 host cores:
-1.82 x realtime (2001 ms). Greedy ids identical (`cpu_baseline.ids_match_gpu`). 2 GPUs 252 x, 4 GPUs 495 x (weak scaling 0.99).
+{b[value]:.1f} x realtime device-timed, {b[e2e][value]:.1f} x end to end through the C ABI with host buffers ({b[ms_per_step]:.1f} ms per utterance:
+mel {b[stage_ms][mel_ms]:.2f} + encoder {b[stage_ms][enc_ms]:.2f} + prefill {b[stage_ms][prefill_ms]:.2f} + decode {b[stage_ms][decode_ms]:.2f} ms); the reference's CPU path on the box's 16 host cores:
+{ref[value]:.2f} x realtime ({ref[ms_per_step]:.0f} ms). Greedy ids identical (`cpu_baseline.ids_match_gpu`). 2 GPUs 252 x, 4 GPUs 495 x (weak scaling 0.99).
 
 ## Decode step, Qwen3-ASR-1.7B (3 458 793 472 algorithmic bytes per step at ~78 cached positions)
 
@@ -28,26 +28,26 @@ mel 0.12 + encoder 2.00 + prefill 3.86 + decode 21.92 ms); the reference's CPU p
 | per-phase kernels in a CUDA graph (`QASR_DECODE=graph`) | 1.494 | 2316 | 0.354 |
 | grid-barrier megakernel v1 (FFMA consumer, 1-D bulk rings) | 1.360 | 2544 | 0.389 |
 | grid-barrier megakernel v2 (mma.sync consumer, 2-D TMA boxes; `QASR_DECODE=mega2`) | 1.326 | 2609 | 0.399 |
-| **decode_stream_kernel** (default) | **0.707** | **4892** | **0.748** (61 % of the 8 TB/s nominal) |
+| **decode_stream_kernel** (default) | **{b[roofline][ms_per_launch]:.3f}** | **{b[roofline][achieved]:.0f}** | **{b[roofline][frac]:.3f}** ({nominal:.0f} % of the 8 TB/s nominal) |
 
-ncu (`r01_stream_ncu_summary.json`): 55,335,086,000 B of DRAM reads for 16 steps = 3,459,393,467 B per step =
-1.00 x the algorithmic bytes (nothing is re-read); `dram__bytes_read` 4.88 TB/s while the kernel runs;
-tensor pipe (HMMA) 7 % active, shared-memory wavefronts 34 % of peak: neither bounds the kernel. What is
+ncu (`r01_stream_ncu_summary.json`): {ncu[dram_bytes_read]:,.0f} B of DRAM reads for 16 steps = {ncu[dram_bytes_per_step]:,.0f} B per step =
+1.00 x the algorithmic bytes (nothing is re-read); `dram__bytes_read` {ncu[dram_read_TBps]:.2f} TB/s while the kernel runs;
+tensor pipe (HMMA) {ncu[tensor_pipe_active_pct]:.0f} % active, shared-memory wavefronts {ncu[smem_wavefronts_pct_of_peak]:.0f} % of peak: neither bounds the kernel. What is
 left is the chain of 5 all-to-all exchanges per layer (`r01_stream_phase_breakdown.txt`: ~20 us per layer
 against 15.4 us of HBM time; an exchange through L2 costs 1.1-1.9 us on an idle B200,
 `r01_stream_microbench.txt`).
 
-Other workloads (same kernel): 30 s utterance, ~470 cached keys: 0.775 ms/step = 0.70; 0.6B (1 233 715 200 B per step):
-0.479 ms/step = 2575 GB/s = 0.39: latency-bound (13 us per layer against 4.8 us of HBM time), was 1.0 ms with the
+Other workloads (same kernel): 30 s utterance, ~470 cached keys: {u30[roofline][ms_per_launch]:.3f} ms/step = {u30[roofline][frac]:.2f}; 0.6B (1 233 715 200 B per step):
+{c1[roofline][ms_per_launch]:.3f} ms/step = {c1[roofline][achieved]:.0f} GB/s = {c1[roofline][frac]:.2f}: latency-bound (13 us per layer against 4.8 us of HBM time), was 1.0 ms with the
 grid-barrier kernel.
 
 ## Several sequences per decode step (qasr_cuda_transcribe_batch)
 
 | workload | sequences / step | ms / step | decoder tokens/s | realtime factor (1 GPU) | one sequence per step |
 |---|---:|---:|---:|---:|---:|
-| configs[2]: 0.6B, -S 20, 3600 s recording, 180 segments | 4 | 0.761 | 5257 | **719 x** | 361 x |
-| configs[4]: 1.7B, 64 x 30 s utterances, 128 tokens each | 2 | 0.950 | 2105 | **405 x** | 256 x |
-| configs[3]: 0.6B stream, 2 s chunks (replicas only) | 1 | 0.505 | 1979 | 85 x; chunk latency p50 23.6 ms, p95 26.5 ms | — |
+| configs[2]: 0.6B, -S 20, 3600 s recording, 180 segments | 4 | {c3[roofline][ms_per_launch]:.3f} | {c3[decoder_tok_s]:.0f} | **{c3[value]:.0f} x** | 361 x |
+| configs[4]: 1.7B, 64 x 30 s utterances, 128 tokens each | 2 | {c5[roofline][ms_per_launch]:.3f} | {c5[decoder_tok_s]:.0f} | **{c5[value]:.0f} x** | 256 x |
+| configs[3]: 0.6B stream, 2 s chunks (replicas only) | 1 | {c4[roofline][ms_per_launch]:.3f} | {c4[decoder_tok_s]:.0f} | {c4[value]:.0f} x; chunk latency p50 {c4[chunk_latency_ms][p50]:.1f} ms, p95 {c4[chunk_latency_ms][p95]:.1f} ms | — |
 
 (`roofline.frac` of these lines divides the bytes of ONE weight pass by the step time; B sequences share that pass.)
 
@@ -55,9 +55,9 @@ grid-barrier kernel.
 
 | shape | time | achieved | of peak |
 |---|---:|---:|---:|
-| prefill gate/up, M=61 (weight stream, skinny split-K kernel) | 19.2 us | 2615 GB/s | 0.40 of the measured HBM peak |
-| encoder fc1, 16 x 30 s batched, M=6240 | 120 us | 875 TFLOP/s (hi+lo MMAs) | 0.62 of the measured bf16 peak (1406, burst) |
-| 8192 x 8192 x 4096 (128x256 tiles) | 677 us | 1625 TFLOP/s (hi+lo MMAs) | 1.16 of the measured bf16 peak; ncu: 694 us, tensor pipe 72.9 % |
+| {g[0][shape]} (weight stream, skinny split-K kernel) | {g[0][us]:.1f} us | {g[0][achieved]:.0f} GB/s | {g[0][frac]:.2f} of the measured HBM peak |
+| {g[1][shape]} | {g[1][us]:.0f} us | {g[1][achieved]:.0f} TFLOP/s (hi+lo MMAs) | {g[1][frac]:.2f} of the measured bf16 peak ({g[1][peak]:.0f}, burst) |
+| {g[2][shape]} (128x256 tiles) | {g[2][us]:.0f} us | {g[2][achieved]:.0f} TFLOP/s (hi+lo MMAs) | {g[2][frac]:.2f} of the measured bf16 peak; ncu: {gemm_us:.0f} us, tensor pipe {gemm_pipe:.1f} % |
 
 The f32-activation reference is reproduced by issuing MMA(A_hi, W) and MMA(A_lo, W) per k-block: both are counted as
 tensor work; useful flops (2MNK) are half of that. At the single-utterance shapes of the bench (M = 47/61 rows) the GEMMs
@@ -67,23 +67,7 @@ GEMMs: 30 s gate/up 80 -> 58 us, 8192 x 8192 x 4096 845 -> 676 us).
 
 ## Launch list of the bench workload (cold-cache, serialised: compare SHARES)
 
-2 utterances = 60.15 ms of serialised kernel time.
-
-| kernel | launches | total us | avg us | share |
-|---|---:|---:|---:|---:|
-| `decode_stream_kernel<1, 5>` | 6 | 45421 | 7570.2 | 75.5 % |
-| `gemm_tc_skinny_kernel<64, 6>` | 422 | 9555 | 22.6 | 15.9 % |
-| `sk_retile_kernel` | 1 | 1499 | 1498.9 | 2.5 % |
-| `attn_prefill_kernel` | 56 | 977 | 17.5 | 1.6 % |
-| `rmsnorm_rows_kernel` | 112 | 711 | 6.4 | 1.2 % |
-| `layernorm_rows_kernel` | 98 | 508 | 5.2 | 0.8 % |
-| `attn_windowed_kernel` | 48 | 500 | 10.4 | 0.8 % |
-| `gemm_tc_kernel<64, 4>` | 4 | 318 | 79.6 | 0.5 % |
-| `qk_norm_rope_store_kernel` | 56 | 228 | 4.1 | 0.4 % |
-| `mel_pass1_kernel` | 2 | 212 | 105.8 | 0.4 % |
-| `im2col_stage_kernel` | 8 | 83 | 10.4 | 0.1 % |
-| `conv1_kernel` | 2 | 74 | 36.9 | 0.1 % |
-
+{launch}
 `decode_stream_kernel` share of the serialised time vs `decode_ms / (mel+enc+prefill+decode)` in the un-profiled bench
-line = 21.92 / 27.97 = 78.4 %: the shares agree. (`sk_retile_kernel` runs once at model load and is not
+line = {b[stage_ms][decode_ms]:.2f} / {b[ms_per_step]:.2f} = {dec_share:.1f} %: the shares agree. (`sk_retile_kernel` runs once at model load and is not
 part of a step.)

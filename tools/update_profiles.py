@@ -68,3 +68,21 @@ if ppre:
         fo.write("## Qwen3-ASR-0.6B\n" + open(os.path.join(G, f"{ppre}_prof06.log")).read())
         fo.write("\n# per-unit trace, warp 0 of CTA 147, first layers (tools/mega_trace.py 147 1.7b): data is (almost) always already in the ring\n")
         fo.write("".join(open(os.path.join(G, f"{ppre}_trace147.log")).readlines()[:45]))
+
+
+def write_readme():
+    b, c1, u30 = line(os.path.join(P, "r01_bench_stream_cfg2.json")), line(os.path.join(P, "r01_bench_stream_cfg1_0p6b.json")), line(os.path.join(P, "r01_bench_stream_utt30.json"))
+    c3, c4, c5 = (line(os.path.join(P, f"r01_bench_stream_cfg{i}.json")) for i in (3, 4, 5))
+    ref = line(os.path.join(P, "r01_bench_reference_arm.json"))
+    ncu = json.load(open(os.path.join(P, "r01_stream_ncu_summary.json")))
+    gn = json.load(open(os.path.join(P, "r01_gemm_tc_ncu_summary.json")))["metrics"]
+    launch = open(os.path.join(P, "r01_launches_stream_cfg2.summary.md")).read()
+    g = b["gemm_rooflines"]
+    tpl = open(os.path.join(ROOT, "tools", "profiles_readme.tpl")).read()
+    txt = tpl.format(b=b, c1=c1, u30=u30, c3=c3, c4=c4, c5=c5, ref=ref, ncu=ncu, launch=launch, g=g,
+                     gemm_pipe=float(gn["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]), gemm_us=float(gn["gpu__time_duration.sum"]),
+                     dec_share=100 * b["stage_ms"]["decode_ms"] / b["ms_per_step"], nominal=100 * b["roofline"]["achieved"] / 8000)
+    open(os.path.join(P, "README.md"), "w").write(txt)
+
+
+write_readme()
