@@ -120,6 +120,13 @@ int qasr_cuda_generate(qasr_ctx_t *ctx, int first_token, int kv_len, int max_new
 int qasr_cuda_transcribe_ids(qasr_ctx_t *ctx, const float *samples, int n_samples, int max_new,
                              int *out_ids, int *out_n, double *timings_ms, int *out_enc_tokens);
 
+/* Prompt used by qasr_cuda_transcribe_ids / _staged / _batch around the audio rows (default: no system text, no forced
+ * language).  Replaces what qwen_set_prompt / qwen_set_force_language / past-text conditioning add to the token
+ * sequence (reference qwen_asr.c:388-399,685-759): pre = [151644, 8948, 198] + system-prompt tokens +
+ * [151645, 198, 151644, 872, 198, 151669]; suf = [151670, 151645, 198, 151644, 77091, 198] (+ "language X" tokens +
+ * 151704) (+ past-text tokens + 151704).  n_suf >= 1. */
+int qasr_cuda_set_prompt(qasr_ctx_t *ctx, const int *pre_ids, int n_pre, const int *suf_ids, int n_suf);
+
 /* Independent units (the segments of -S mode, reference qwen_asr.c:941-1103, or separate utterances) decoded
  * together: up to qasr_cuda_max_batch() sequences share every decode step (one pass over the weights serves all
  * of them); front end, encoder and prefill run per unit.  samples[i] / n_samples[i] / max_new[i] describe unit i;

@@ -46,6 +46,7 @@ SIGNATURES = {
     "qasr_cuda_step_logits": (ci, [vp, f32p, ci, f32p]),
     "qasr_cuda_generate": (ci, [vp, ci, ci, ci, i32p, ip, ip]),
     "qasr_cuda_transcribe_ids": (ci, [vp, f32p, ci, ci, i32p, ip, vp, ip]),
+    "qasr_cuda_set_prompt": (ci, [vp, i32p, ci, i32p, ci]),
     "qasr_cuda_max_batch": (ci, [vp]),
     "qasr_cuda_transcribe_batch": (ci, [vp, vp, i32p, ci, i32p, ci, i32p, i32p, vp]),
     "qasr_cuda_stage_audio": (ci, [vp, f32p, ci]),
@@ -248,6 +249,12 @@ class QasrCuda:
                                                    tm.ctypes.data_as(vp), C.byref(T)))
         return ids[:n.value].copy(), dict(mel_ms=tm[0], enc_ms=tm[1], prefill_ms=tm[2], decode_ms=tm[3],
                                           enc_tokens=T.value)
+
+    def set_prompt(self, pre_ids, suf_ids):
+        """Prompt tokens around the audio rows for transcribe_ids / transcribe_batch (system text, forced language)."""
+        pre = np.ascontiguousarray(pre_ids, np.int32)
+        suf = np.ascontiguousarray(suf_ids, np.int32)
+        self._ck(self.lib.qasr_cuda_set_prompt(self.ctx, pre, len(pre), suf, len(suf)))
 
     @property
     def max_batch(self):

@@ -120,6 +120,9 @@ struct qasr_ctx {
     unsigned long long *sk_cta_off = nullptr;
     unsigned long long *ll_qkv = nullptr, *ll_att = nullptr, *ll_xwo = nullptr, *ll_act = nullptr, *ll_xdn = nullptr, *ll_head = nullptr;
     unsigned sk_tag = 1;                   // next free exchange tag
+    // prompt around the audio rows used by the whole-segment entry points (reference qwen_asr.c:388-399,685-759): default = no system text, no forced language
+    std::vector<int> pre_ids = {151644, 8948, 198, 151645, 198, 151644, 872, 198, 151669};
+    std::vector<int> suf_ids = {151670, 151645, 198, 151644, 77091, 198};
     float *head_val = nullptr;
     int *head_idx = nullptr;
     unsigned *grid_bar = nullptr;
@@ -1134,8 +1137,8 @@ int qasr_cuda_generate(qasr_ctx_t *c, int first_token, int kv_len, int max_new, 
 // Whole offline segment. reference transcribe_segment, qwen_asr.c:649-842
 static int transcribe_impl(qasr_ctx_t *c, const float *samples, int n_samples, int max_new, int *out_ids, int *out_n,
                            double *timings_ms, int *out_enc_tokens) {
-    static const int PRE[] = {151644, 8948, 198, 151645, 198, 151644, 872, 198, 151669}; // qwen_asr.c:388-393
-    static const int SUF[] = {151670, 151645, 198, 151644, 77091, 198};                  // qwen_asr.c:394-396
+    const int *PRE = c ? c->pre_ids.data() : nullptr, *SUF = c ? c->suf_ids.data() : nullptr; // qwen_asr.c:388-396 (+ prompt / language tokens)
+    const int n_pre = c ? (int)c->pre_ids.size() : 0, n_suf = c ? (int)c->suf_ids.size() : 0;
     if (!c || !out_ids || !out_n) return set_err(QASR_ERR_ARG, "null argument");
     if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
     CK(cudaSetDevice(c->device));
@@ -1145,10 +1148,10 @@ static int transcribe_impl(qasr_ctx_t *c, const float *samples, int n_samples, i
     CK(cudaEventRecord(c->ev[2], c->stream));
     CKR(encode_device(c, c->ws_mel.as<float>(), frames, &T));
     CK(cudaEventRecord(c->ev[3], c->stream));
-    CKR(prefill_prompt_device(c, PRE, 9, T, SUF, 6, 0));
+    CKR(prefill_prompt_device(c, PRE, n_pre, T, SUF, n_suf, 0));
     CK(cudaMemcpyAsync(c->x, c->pending, (size_t)c->H * 4, cudaMemcpyDeviceToDevice, c->stream));
     c->has_pending = false;
-    const int kv0 = 9 + T + 6 - 1;
+    const int kv0 = n_pre + T + n_suf - 1;
     CKR(ensure_kv(c, kv0 + max_new + 2, kv0));
     CKR(ensure_rope(c, kv0 + max_new + 2));
     launch_set_state(c->stream, c->d_pos, kv0, c->d_done, 0, c->d_step, 0);
@@ -1187,8 +1190,8 @@ int qasr_cuda_max_batch(const qasr_ctx_t *c) {
 
 static int transcribe_group(qasr_ctx_t *c, const float *const *samples, const int *n_samples, int B, const int *max_new, int ids_stride,
                             int *out_ids, int *out_n, double *tm) {
-    static const int PRE[] = {151644, 8948, 198, 151645, 198, 151644, 872, 198, 151669}; // qwen_asr.c:388-393
-    static const int SUF[] = {151670, 151645, 198, 151644, 77091, 198};                  // qwen_asr.c:394-396
+    const int *PRE = c ? c->pre_ids.data() : nullptr, *SUF = c ? c->suf_ids.data() : nullptr; // qwen_asr.c:388-396 (+ prompt / language tokens)
+    const int n_pre = c ? (int)c->pre_ids.size() : 0, n_suf = c ? (int)c->suf_ids.size() : 0;
     int kv0[QASR_STREAM_MAX_SEQS] = {}, n[QASR_STREAM_MAX_SEQS] = {};
     bool done[QASR_STREAM_MAX_SEQS] = {};
     int cap_new = 0;
@@ -1201,7 +1204,7 @@ static int transcribe_group(qasr_ctx_t *c, const float *const *samples, const in
         CK(cudaEventRecord(c->ev[2], c->stream));
         CKR(encode_device(c, c->ws_mel.as<float>(), frames, &T));
         CK(cudaEventRecord(c->ev[3], c->stream));
-        CKR(prefill_prompt_device(c, PRE, 9, T, SUF, 6, 0));
+        CKR(prefill_prompt_device(c, PRE, n_pre, T, SUF, n_suf, 0));
         CK(cudaMemcpyAsync(c->x + (size_t)q * c->H, c->pending, (size_t)c->H * 4, cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaEventRecord(c->ev[4], c->stream));
         CK(cudaEventSynchronize(c->ev[4]));
@@ -1211,7 +1214,7 @@ static int transcribe_group(qasr_ctx_t *c, const float *const *samples, const in
             cudaEventElapsedTime(&a, c->ev[0], c->ev[2]); cudaEventElapsedTime(&b, c->ev[2], c->ev[3]); cudaEventElapsedTime(&d, c->ev[3], c->ev[4]);
             tm[0] += a; tm[1] += b; tm[2] += d;
         }
-        kv0[q] = 9 + T + 6 - 1;
+        kv0[q] = n_pre + T + n_suf - 1;
         if (max_new[q] > cap_new) cap_new = max_new[q];
     }
     int cap = 0;
@@ -1275,6 +1278,20 @@ int qasr_cuda_transcribe_batch(qasr_ctx_t *c, const float *const *samples, const
         i += B;
     }
     select_seq(c, 0);
+    return 0;
+}
+
+// Prompt of the whole-segment entry points: pre = tokens before the audio rows, suf = tokens after them.  The reference
+// builds them in qwen_set_prompt / qwen_set_force_language / transcribe_segment (qwen_asr.c:388-399,685-759):
+// pre = [151644, 8948, 198] + system-prompt tokens + [151645, 198, 151644, 872, 198, 151669],
+// suf = [151670, 151645, 198, 151644, 77091, 198] (+ "language X" tokens + 151704) (+ past-text tokens + 151704).
+int qasr_cuda_set_prompt(qasr_ctx_t *c, const int *pre_ids, int n_pre, const int *suf_ids, int n_suf) {
+    if (!c || n_pre < 0 || n_suf < 1 || (n_pre > 0 && !pre_ids) || !suf_ids) return set_err(QASR_ERR_ARG, "bad prompt (the suffix needs at least one token)");
+    if (n_pre > 4096 || n_suf > 4096) return set_err(QASR_ERR_ARG, "prompt too long");
+    for (int i = 0; i < n_pre; i++) if (pre_ids[i] < 0 || pre_ids[i] >= c->V) return set_err(QASR_ERR_ARG, "token id out of range");
+    for (int i = 0; i < n_suf; i++) if (suf_ids[i] < 0 || suf_ids[i] >= c->V) return set_err(QASR_ERR_ARG, "token id out of range");
+    c->pre_ids.assign(pre_ids, pre_ids + n_pre);
+    c->suf_ids.assign(suf_ids, suf_ids + n_suf);
     return 0;
 }
 

@@ -287,3 +287,25 @@ def test_comparison_decode_paths_give_identical_ids(pkg, model06, gpu06, monkeyp
         assert eng.transcribe_ids(audio, 12)[0].tolist() == want
     finally:
         eng.close()
+
+
+def test_custom_prompt_matches_entry_point_composition(gpu06, oracle06, pkg):
+    """qasr_cuda_set_prompt (system text + forced language, reference qwen_asr.c:388-399,685-759): the whole-segment
+    entry points, single and batched, must give the ids of the oracle driven with the same token sequence."""
+    pre = [151644, 8948, 198, 2610, 525, 264, 1273, 13, 151645, 198, 151644, 872, 198, 151669]     # with system-prompt tokens
+    suf = [151670, 151645, 198, 151644, 77091, 198, 11528, 6364, 151704]                          # "language English" + <asr_text>
+    audio = pkg.synth_audio(1.7, seed=52)
+    enc = oracle06.encode(oracle06.mel(audio))
+    rows = np.stack([oracle06.embed(t) for t in pre] + list(enc) + [oracle06.embed(t) for t in suf]).astype(np.float32)
+    oracle06.kv_len = 0
+    oracle06.prefill(rows[:-1])
+    want = [oracle06.step(rows[-1])]
+    for _ in range(6):
+        want.append(oracle06.step(oracle06.embed(want[-1])))
+    gpu06.set_prompt(pre, suf)
+    try:
+        assert gpu06.transcribe_ids(audio, 7)[0].tolist() == want
+        got, _ = gpu06.transcribe_batch([audio, pkg.synth_audio(1.2, seed=53)], 7)
+        assert got[0].tolist() == want
+    finally:
+        gpu06.set_prompt(PRE, SUF)
