@@ -1,39 +1,42 @@
-// qasr_stream.cu - the decode kernel (v3): whole greedy loop for a chunk of tokens in ONE cooperative
-// launch, weights streamed from a pre-tiled HBM image, phases chained by flag-in-data exchanges
-// instead of grid barriers.  Reference hot loop: qwen_asr.c:788-818 -> qwen_decoder_forward,
-// qwen_asr_decoder.c:592-685; kernels qwen_asr_kernels.c:336-373,486-543,801-924,946-1010,
-// 1101-1148,1233-1298.
+// qasr_stream.cu - the decode kernel: whole greedy loop for a chunk of tokens (and up to 4 independent sequences)
+// in ONE cooperative launch, weights streamed from a pre-tiled HBM image, phases chained by flag-in-data
+// exchanges instead of grid barriers.  Reference hot loop: qwen_asr.c:788-818 -> qwen_decoder_forward,
+// qwen_asr_decoder.c:592-685; kernels qwen_asr_kernels.c:336-373,486-543,801-924,946-1010,1101-1148,1233-1298.
 //
-// What bounds a decode step: 3.44 GB (1.7B) / 1.19 GB (0.6B) of bf16 weights read exactly once ->
-// HBM.  What actually limited rounds 1-2 (profiles/r01_*, r02_mega2_*): 142 dependent phases per
-// token, each paying a grid barrier (~2.6 us with skew), a re-staging of the input vector from L2
-// and, for attention, serial HBM-latency loads: 40 us per layer against 15.4 us of HBM time; and
-// 2-D TMA boxes with 128-byte rows fetch at only 3.6 TB/s (tools/microbench/cluster16.cu).
+// What bounds a decode step: 3.44 GB (1.7B) / 1.19 GB (0.6B) of bf16 weights read exactly once -> HBM.
+// What actually limited the earlier kernels of this round (profiles/r01_megakernel_*, r01_mega2_*): 142 dependent
+// phases per token, each paying a grid barrier (~2.6 us with skew), a re-staging of the input vector from L2 and,
+// for attention, serial HBM-latency loads: 40 us per layer against 15.4 us of HBM time; 2-D TMA boxes with
+// 128-byte rows fetch at only 3.6 TB/s (tools/microbench/cluster16.cu); and every bulk copy costs ~0.1 us of
+// issue time on the issuing warp.
 //
 // Design
-//  * Weight image.  At load time every decoder matrix (and the tied lm_head) is re-tiled on the
-//    device into "units" of 16 rows x 64 columns (2 KB) stored in mma.m16n8k16 A-fragment order, and
-//    the units are laid out in HBM in exactly the order each (CTA, warp) consumes them.  A warp's
-//    whole per-token weight stream is ONE contiguous byte range that it walks cyclically with 2 KB
-//    1-D bulk copies (cp.async.bulk + mbarrier complete_tx) into a private 5-slot shared-memory
-//    ring: no tensor maps, no address arithmetic, fully sequential DRAM pages, and the ring keeps
-//    filling across phase (and token) boundaries because weight addresses never depend on data.
-//  * Dot products on tensor cores: A = weight unit (one conflict-free LDS.128 per lane per 16x16
-//    tile), B = the phase input as two columns x_hi = RN(x), x_lo = RN(x - x_hi) held in shared
-//    memory in B-fragment order, so D[:,0] + D[:,1] = W.x to ~2^-17 relative (weights are exact bf16).
-//    Warp w owns column slices {w, w+16, ...} of every 16-row group of its CTA; the 16 per-warp partial
-//    sums of a row are added in fixed order => bitwise reproducible.
-//  * Exchanges.  Every phase output is written to global memory as 8-byte {f32 value, u32 tag}
-//    words (one atomic 64-bit store; tag = launch base + step*(L+1) + layer + 1) and every consumer
-//    polls the words it needs until the tag matches: one L2 round trip after the data lands, no
-//    separate barrier, no fence, no re-read.  The residual stream x lives in every CTA's shared
-//    memory (replicated, updated identically), so nothing but the exchange buffers is shared.
-//  * Attention: 16 q heads x S key splits (S = ceil(keys/128) <= 4) CTAs; K/V rows of the f32 cache
-//    are prefetched to L2 at the top of the layer and then loaded 8 rows at a time per warp.
+//  * Weight image.  At load time every decoder matrix (and the tied lm_head) is re-tiled on the device into
+//    "units" of 16 rows x 64 columns (2 KB) stored in mma.m16n8k16 A-fragment order, and the units are laid out in
+//    HBM in exactly the order each (CTA, warp) consumes them.  A warp's whole per-token weight stream is ONE
+//    contiguous byte range that it walks cyclically: every lane copies its own 4 x 16 B of each unit with cp.async
+//    (LDGSTS, 128-bit, L1 bypass) into its private bytes of the warp's ring (5 slots, 4 in the batched variants;
+//    160 / 128 KB per SM) and later reads back exactly those bytes as its A fragments - a per-lane FIFO tracked by
+//    the cp.async group counter alone: no mbarrier, no tensor map, no address arithmetic, sequential DRAM pages.
+//    The ring keeps filling across phase (and token) boundaries because weight addresses never depend on data;
+//    while a warp polls an exchange it also pulls the next units beyond its ring into L2.
+//  * Dot products on tensor cores: A = weight unit (one conflict-free LDS.128 per lane per 16x16 tile), B = the
+//    phase input as two columns x_hi = RN(x), x_lo = RN(x - x_hi) held in shared memory in B-fragment order, so
+//    D[:,0] + D[:,1] = W.x to ~2^-17 relative (weights are exact bf16).  Sequence s of a batched launch uses
+//    columns 2s, 2s+1.  Warp w owns column slices {w, w+16, ...} of every 16-row group of its CTA; the 16 per-warp
+//    partial sums of a row are added in fixed order => bitwise reproducible.
+//  * Exchanges.  Every phase output is written to global memory as 8-byte {f32 value, u32 tag} words (one atomic
+//    64-bit store; tag = launch base + step*(L+1) + layer + 1) and every consumer polls the words it needs until the
+//    tag matches: data and flag travel together, no separate barrier, no fence, no re-read.  The residual stream x
+//    lives in every CTA's shared memory (replicated, updated identically), so nothing but the exchange buffers is
+//    shared.  A writer can never lap a reader: every buffer is rewritten only after a later all-to-all exchange.
+//  * Attention: (sequence, q head, key split) CTAs with S = ceil(keys/32) <= 4 splits; everything up to the final
+//    merge is warp-local; K/V rows of the f32 cache are prefetched to L2 at the top of the layer and loaded into
+//    registers before the q words are polled.
 //
-// Phases per layer:  QKV | ATTN | WO(+residual) | GU(+SwiGLU) | DOWN(+residual); then HEAD (per-CTA
-// argmax, exchange of the 148 winners, lowest index wins ties, reference qwen_asr_kernels.c:536-541)
-// and the embedding gather of the next input row by every CTA.
+// Phases per layer:  QKV | ATTN | WO(+residual) | GU(+SwiGLU) | DOWN(+residual); then HEAD (per-CTA argmax,
+// exchange of the 148 winners, lowest index wins ties, reference qwen_asr_kernels.c:536-541) and the embedding
+// gather of the next input row by every CTA.
 #include "qasr_common.cuh"
 #include "qasr_internal.h"
 
