@@ -136,6 +136,16 @@ int qasr_cuda_max_batch(const qasr_ctx_t *ctx);
 int qasr_cuda_transcribe_batch(qasr_ctx_t *ctx, const float *const *samples, const int *n_samples, int count,
                                const int *max_new, int ids_stride, int *out_ids, int *out_n, double *timings_ms);
 
+/* Streaming session with every buffer in HBM: the device-visible part of the reference's stream_impl
+ * (qwen_asr.c:1273-1900).  stream_begin resets the session (window_sec = 8, max_windows = 4 in the reference).
+ * stream_feed takes ALL audio received so far: windows completed since the last call are encoded once and cached on the
+ * device, the partial tail is re-encoded, the prompt (qasr_cuda_set_prompt) is assembled on the device, the rows shared
+ * with the previous chunk are reused from the KV cache (*out_reused), the rest is prefilled and up to max_new greedy ids
+ * are produced.  The token bookkeeping that follows in the reference (:1906-2146) stays on the host. */
+int qasr_cuda_stream_begin(qasr_ctx_t *ctx, float window_sec, int max_windows);
+int qasr_cuda_stream_feed(qasr_ctx_t *ctx, const float *samples, int n_samples, int max_new, int *out_ids, int *out_n,
+                          int *out_reused, int *out_rows);
+
 /* Benchmark plumbing: keep a segment's samples resident in HBM and transcribe from there (no
  * per-call host->device copy), a CUDA-event stopwatch on the library's own stream (the stream
  * every kernel here is launched on), and the accumulated device time / step count of the greedy

@@ -49,6 +49,8 @@ SIGNATURES = {
     "qasr_cuda_set_prompt": (ci, [vp, i32p, ci, i32p, ci]),
     "qasr_cuda_max_batch": (ci, [vp]),
     "qasr_cuda_transcribe_batch": (ci, [vp, vp, i32p, ci, i32p, ci, i32p, i32p, vp]),
+    "qasr_cuda_stream_begin": (ci, [vp, cf, ci]),
+    "qasr_cuda_stream_feed": (ci, [vp, f32p, ci, ci, i32p, ip, ip, ip]),
     "qasr_cuda_stage_audio": (ci, [vp, f32p, ci]),
     "qasr_cuda_transcribe_staged": (ci, [vp, ci, i32p, ip, vp, ip]),
     "qasr_cuda_timer_start": (ci, [vp]),
@@ -274,6 +276,17 @@ class QasrCuda:
         tm = np.zeros(4, np.float64)
         self._ck(self.lib.qasr_cuda_transcribe_batch(self.ctx, C.cast(ptrs, vp), lens, n, caps, stride, ids, cnt, tm.ctypes.data_as(vp)))
         return [ids[i, :cnt[i]].copy() for i in range(n)], dict(mel_ms=tm[0], enc_ms=tm[1], prefill_ms=tm[2], decode_ms=tm[3])
+
+    def stream_begin(self, window_sec=8.0, max_windows=4):
+        self._ck(self.lib.qasr_cuda_stream_begin(self.ctx, float(window_sec), int(max_windows)))
+
+    def stream_feed(self, samples, max_new=32):
+        """Device-resident streaming chunk: `samples` = all audio so far.  Returns dict(ids, reused, rows)."""
+        samples = _f32(samples)
+        ids = np.zeros(max(max_new, 1), np.int32)
+        n, reused, rows = ci(0), ci(0), ci(0)
+        self._ck(self.lib.qasr_cuda_stream_feed(self.ctx, samples, len(samples), max_new, ids, C.byref(n), C.byref(reused), C.byref(rows)))
+        return dict(ids=[int(t) for t in ids[:n.value]], reused=reused.value, rows=rows.value)
 
     # ---- benchmark plumbing
     def stage_audio(self, samples):

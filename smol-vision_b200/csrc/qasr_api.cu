@@ -115,7 +115,7 @@ struct qasr_ctx {
     int graph_nodes = 0;
     bool use_graph = true;
     bool use_mega = true; // persistent cooperative decode kernel (QASR_DECODE=graph selects per-phase kernels)
-    bool use_stream = true; // qasr_stream.cu (default); QASR_DECODE=mega2 selects the round-2 TMA-box kernel
+    bool use_stream = true; // qasr_stream.cu (default); QASR_DECODE=mega2 selects the earlier grid-barrier TMA-box kernel
     uint8_t *sk_image = nullptr;           // decode weight image (pre-tiled, per-warp streams)
     unsigned long long *sk_cta_off = nullptr;
     unsigned long long *ll_qkv = nullptr, *ll_att = nullptr, *ll_xwo = nullptr, *ll_act = nullptr, *ll_xdn = nullptr, *ll_head = nullptr;
@@ -123,6 +123,12 @@ struct qasr_ctx {
     // prompt around the audio rows used by the whole-segment entry points (reference qwen_asr.c:388-399,685-759): default = no system text, no forced language
     std::vector<int> pre_ids = {151644, 8948, 198, 151645, 198, 151644, 872, 198, 151669};
     std::vector<int> suf_ids = {151670, 151645, 198, 151644, 77091, 198};
+    // streaming session (qasr_cuda_stream_*): encoder rows of the completed windows stay in HBM
+    struct StreamWin { long long index = -1; int T = 0; DevBuf rows; };
+    StreamWin st_win[8];
+    int st_window = 0, st_max_windows = 0;      // samples per window, windows kept
+    std::vector<long long> st_prev;             // window indices of the previous chunk's prompt, in order
+    bool st_active = false, st_fed = false;     // session open / at least one chunk fed (the KV cache holds its prompt)
     float *head_val = nullptr;
     int *head_idx = nullptr;
     unsigned *grid_bar = nullptr;
@@ -205,6 +211,7 @@ void qasr_cuda_free(qasr_ctx_t *c) {
     if (c->h_tokens) cudaFreeHost(c->h_tokens);
     c->ws_samples.release(); c->ws_meltmp.release(); c->ws_mel.release(); c->ws_enc.release();
     c->ws_encout.release(); c->ws_pre.release(); c->ws_ids.release(); c->ws_geom.release();
+    for (auto &w : c->st_win) w.rows.release();
     for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; i++) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
     cudaStreamDestroy(c->stream);
@@ -972,7 +979,7 @@ static int enqueue_steps(qasr_ctx_t *c, int n, int nseq = 1) {
         c->launches += 1;
         return 0;
     }
-    if (c->use_mega) { // round-2 kernel (QASR_DECODE=mega2): 2-D TMA boxes + grid barriers
+    if (c->use_mega) { // earlier kernel of this round (QASR_DECODE=mega2): 2-D TMA boxes + grid barriers
         if (c->dec_layers > 28) return set_err(QASR_ERR_ARG, "decode megakernel supports up to 28 decoder layers");
         MegaParams p;
         p.maps = (const CUtensorMap_st *)c->mega_maps;
@@ -1292,6 +1299,111 @@ int qasr_cuda_set_prompt(qasr_ctx_t *c, const int *pre_ids, int n_pre, const int
     for (int i = 0; i < n_suf; i++) if (suf_ids[i] < 0 || suf_ids[i] >= c->V) return set_err(QASR_ERR_ARG, "token id out of range");
     c->pre_ids.assign(pre_ids, pre_ids + n_pre);
     c->suf_ids.assign(suf_ids, suf_ids + n_suf);
+    return 0;
+}
+
+// ------------------------------------------------------------------ streaming session (device-resident)
+// The device-visible part of the reference's stream_impl (qwen_asr.c:1273-1900) with every buffer in
+// HBM: encoder rows of completed windows are computed once and cached on the device (:1601-1641), the partial tail is
+// re-encoded (:1643-1659), at most `max_windows` windows are kept (:1670-1683), the prompt rows are assembled on the
+// device, the reusable prefix is found from the window identities instead of a memcmp of float rows (:1811-1823: rows
+// are equal exactly when they come from the same cached window at the same position), the delta is prefilled
+// (:1825-1829) and up to max_new greedy tokens are decoded (:1880-1888).  Only samples go in and ids come out.
+int qasr_cuda_stream_begin(qasr_ctx_t *c, float window_sec, int max_windows) {
+    if (!c) return set_err(QASR_ERR_ARG, "null context");
+    if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
+    if (!(window_sec > 0.05f) || max_windows < 1 || max_windows > 8) return set_err(QASR_ERR_ARG, "window_sec > 0.05 and 1 <= max_windows <= 8");
+    c->st_window = (int)lroundf(window_sec * 16000.0f);
+    c->st_max_windows = max_windows;
+    for (auto &w : c->st_win) { w.index = -1; w.T = 0; }
+    c->st_prev.clear();
+    c->st_active = true;
+    c->st_fed = false;
+    return 0;
+}
+
+int qasr_cuda_stream_feed(qasr_ctx_t *c, const float *samples, int n_samples, int max_new, int *out_ids, int *out_n,
+                          int *out_reused, int *out_rows) {
+    if (!c || !samples || !out_ids || !out_n || n_samples <= 0 || max_new < 1) return set_err(QASR_ERR_ARG, "bad argument");
+    if (!c->loaded || !c->st_active) return set_err(QASR_ERR_STATE, "call qasr_cuda_stream_begin first");
+    CK(cudaSetDevice(c->device));
+    select_seq(c, 0);
+    const int H = c->H, W = c->st_window, MW = c->st_max_windows;
+    const long long n_full = n_samples / W, first = n_full > MW ? n_full - MW : 0;
+    // (1) newly completed windows: mel over the window's own span, encoder, rows into the cache slot of that window
+    for (long long w = first; w < n_full; w++) {
+        qasr_ctx::StreamWin &slot = c->st_win[w % MW];
+        if (slot.index == w) continue;
+        int frames = 0, T = 0;
+        CKR(mel_device(c, samples + (size_t)w * W, W, &frames));
+        CKR(encode_device(c, c->ws_mel.as<float>(), frames, &T));
+        if (slot.rows.reserve((size_t)T * H * 4)) return set_err(QASR_ERR_NOMEM, "window cache");
+        CK(cudaMemcpyAsync(slot.rows.p, c->ws_encout.p, (size_t)T * H * 4, cudaMemcpyDeviceToDevice, c->stream));
+        slot.index = w; slot.T = T;
+    }
+    // (2) partial tail (re-encoded on every chunk); stays in ws_encout
+    int T_tail = 0;
+    const int tail_n = n_samples - (int)(n_full * W);
+    if (tail_n >= 400) {
+        int frames = 0;
+        CKR(mel_device(c, samples + (size_t)n_full * W, tail_n, &frames));
+        CKR(encode_device(c, c->ws_mel.as<float>(), frames, &T_tail));
+    }
+    // (3) prompt layout and reusable prefix
+    const int n_pre = (int)c->pre_ids.size(), n_suf = (int)c->suf_ids.size();
+    std::vector<long long> cur;
+    int total = n_pre + T_tail + n_suf, reused = n_pre;
+    for (long long w = first; w < n_full; w++) { cur.push_back(w); total += c->st_win[w % MW].T; }
+    if (!c->st_fed) reused = 0; // first chunk of the session: the KV cache holds nothing of this prompt yet
+    else
+        for (size_t i = 0; i < cur.size() && i < c->st_prev.size() && cur[i] == c->st_prev[i]; i++) reused += c->st_win[cur[i] % MW].T;
+    if (reused > total - 1) reused = total - 1;
+    // (4) rows [reused, total) assembled in the prefill workspace (the reused prefix is already in the KV cache)
+    const int P = total - reused; // includes the last row, which goes through the single-token step
+    CKR(reserve_prefill(c, P));
+    if (c->ws_ids.reserve((size_t)(n_pre + n_suf + 1) * 4)) return set_err(QASR_ERR_NOMEM, "ids alloc");
+    int *d_ids = c->ws_ids.as<int>();
+    float *x = c->ws_pre.as<float>();
+    CK(cudaMemcpyAsync(d_ids, c->pre_ids.data(), (size_t)n_pre * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_ids + n_pre, c->suf_ids.data(), (size_t)n_suf * 4, cudaMemcpyHostToDevice, c->stream));
+    int row = 0; // absolute row of the next segment
+    auto place = [&](int seg_rows, auto &&emit) { // emit(dst_row_in_x, first_row_of_segment, count)
+        const int lo = reused > row ? reused - row : 0;
+        if (lo < seg_rows) emit(row + lo - reused, lo, seg_rows - lo);
+        row += seg_rows;
+    };
+    int rc = 0;
+    place(n_pre, [&](int dst, int off, int cnt) { launch_embed_gather(c->stream, c->emb, d_ids + off, cnt, H, x + (size_t)dst * H); c->launches += 1; });
+    for (long long w : cur) {
+        qasr_ctx::StreamWin &slot = c->st_win[w % MW];
+        place(slot.T, [&](int dst, int off, int cnt) {
+            if (cudaMemcpyAsync(x + (size_t)dst * H, slot.rows.as<float>() + (size_t)off * H, (size_t)cnt * H * 4, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) rc = -1;
+        });
+    }
+    place(T_tail, [&](int dst, int off, int cnt) {
+        if (cudaMemcpyAsync(x + (size_t)dst * H, c->ws_encout.as<float>() + (size_t)off * H, (size_t)cnt * H * 4, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) rc = -1;
+    });
+    place(n_suf, [&](int dst, int off, int cnt) { launch_embed_gather(c->stream, c->emb, d_ids + n_pre + off, cnt, H, x + (size_t)dst * H); c->launches += 1; });
+    if (rc != 0) return set_err(QASR_ERR_CUDA, "assembling the prompt rows failed");
+    CK(cudaMemcpyAsync(c->x, x + (size_t)(P - 1) * H, (size_t)H * 4, cudaMemcpyDeviceToDevice, c->stream));
+    // (5) delta prefill at kv_len = reused (rollback moves no data, qwen_asr.c:1823), first step, greedy loop
+    if (P > 1) CKR(prefill_device(c, P - 1, reused));
+    const int kv0 = total - 1;
+    CKR(ensure_kv(c, kv0 + max_new + 2, kv0));
+    CKR(ensure_rope(c, kv0 + max_new + 2));
+    launch_set_state(c->stream, c->d_pos, kv0, c->d_done, 0, c->d_step, 0);
+    c->launches += 1;
+    CKR(enqueue_steps(c, 1));
+    CK(cudaStreamSynchronize(c->stream));
+    const int first_tok = c->h_tokens[0];
+    c->x_token = first_tok;
+    c->has_pending = false;
+    int kv_out = 0;
+    CKR(generate_device(c, first_tok, kv0 + 1, max_new, out_ids, out_n, &kv_out));
+    c->st_prev = cur;
+    c->st_fed = true;
+    if (out_reused) *out_reused = reused;
+    if (out_rows) *out_rows = total;
     return 0;
 }
 

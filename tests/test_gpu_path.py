@@ -309,3 +309,19 @@ def test_custom_prompt_matches_entry_point_composition(gpu06, oracle06, pkg):
         assert got[0].tolist() == want
     finally:
         gpu06.set_prompt(PRE, SUF)
+
+
+@pytest.mark.parametrize("seconds,window,maxw", [(3.0, 2.0, 2), (7.0, 2.0, 2), (5.5, 1.5, 3)])
+def test_device_stream_session_equals_host_session(gpu06, pkg, seconds, window, maxw):
+    """qasr_cuda_stream_begin / _feed (window cache, prompt assembly and prefix reuse all in HBM) must give,
+    chunk by chunk, the ids / reused prefix / prompt length of the host-driven session (streaming.py), which itself is
+    checked against the CPU oracle; includes window completion, cached-window reuse and eviction."""
+    audio = pkg.synth_audio(seconds, seed=81)
+    host = pkg.streaming.run_stream(gpu06, audio, 1.0, window_sec=window, max_windows=maxw, max_new=5)
+    gpu06.stream_begin(window, maxw)
+    dev = [gpu06.stream_feed(audio[:min(end, len(audio))], 5) for end in range(16000, len(audio) + 16000, 16000)]
+    assert len(dev) == len(host)
+    for d, h in zip(dev, host):
+        assert (d["ids"], d["reused"], d["rows"]) == (h["ids"], h["reused"], h["rows"])
+    gpu06.stream_begin(window, maxw)     # a second session on the same context starts from an empty cache
+    assert gpu06.stream_feed(audio[:16000], 5)["reused"] == 0
