@@ -151,6 +151,12 @@ int qasr_cuda_stream_feed(qasr_ctx_t *ctx, const float *samples, int n_samples, 
  * every kernel here is launched on), and the accumulated device time / step count of the greedy
  * decode-step launches since the last reset (for the decode roofline). */
 int qasr_cuda_stage_audio(qasr_ctx_t *ctx, const float *samples, int n_samples);
+/* Interleaved 16-bit PCM (the payload of a WAV "data" chunk) at any sample rate -> f32 mono 16 kHz on the device: channel
+ * average, 1/32768 scaling and the reference's windowed-sinc resampler (qwen_parse_wav_buffer, qwen_asr_audio.c:81-164;
+ * the RIFF chunk walk :40-79 stays host code).  The result is staged for qasr_cuda_transcribe_staged; `out` (nullable,
+ * out_cap samples) receives a host copy.  *out_n = floor(n_frames * 16000 / sample_rate). */
+int qasr_cuda_decode_pcm16(qasr_ctx_t *ctx, const int16_t *pcm, int n_frames, int channels, int sample_rate, float *out,
+                           int out_cap, int *out_n);
 int qasr_cuda_transcribe_staged(qasr_ctx_t *ctx, int max_new, int *out_ids, int *out_n, double *timings_ms,
                                 int *out_enc_tokens);
 int qasr_cuda_timer_start(qasr_ctx_t *ctx);

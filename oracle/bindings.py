@@ -95,6 +95,14 @@ class RefLib:
         self.lib.ref_free_buf(ptr)
         return out
 
+    def parse_wav(self, data):
+        """WAV bytes -> f32 mono 16 kHz through the reference's qwen_parse_wav_buffer (None if unsupported)."""
+        self.lib.ref_parse_wav.restype = C.POINTER(C.c_float)
+        self.lib.ref_parse_wav.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
+        n = C.c_int(0)
+        p = self.lib.ref_parse_wav(bytes(data), len(data), C.byref(n))
+        return self._take(p, n.value) if p else None
+
     def mel(self, samples):
         samples = np.ascontiguousarray(samples, np.float32)
         fr = C.c_int(0)
@@ -211,6 +219,14 @@ class OracleLib:
         out = np.ctypeslib.as_array(ptr, shape=(n,)).copy()
         self.lib.qo_free_buf(ptr)
         return out
+
+    def parse_wav(self, data):
+        """WAV bytes -> f32 mono 16 kHz (restatement of qwen_parse_wav_buffer; None if unsupported)."""
+        self.lib.qo_parse_wav_buffer.restype = C.POINTER(C.c_float)
+        self.lib.qo_parse_wav_buffer.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int)]
+        n = C.c_int(0)
+        p = self.lib.qo_parse_wav_buffer(bytes(data), len(data), C.byref(n))
+        return self._take(p, n.value) if p else None
 
     def mel(self, samples):
         samples = np.ascontiguousarray(samples, np.float32)

@@ -729,3 +729,79 @@ int qo_transcribe_ids(qo_model_t *m, const float *samples, int n_samples, int ma
     if (out_T) *out_T = T;
     return n;
 }
+
+
+/* ---------------------------------------------------------------- WAV bytes -> f32 mono 16 kHz
+ * Restates qwen_parse_wav_buffer (reference qwen_asr_audio.c:40-168): RIFF chunk walk (:52-69), 16-bit PCM only
+ * (:71-75), channels averaged and scaled by 1/32768 (:81-94), then - if the file is not at 16 kHz - a windowed-sinc
+ * resampler (:96-164): 32 taps around floor(i / ratio), sinc cut at min(ratio, 1), Kaiser window beta = 6 with I0 as a
+ * 20-term power series, every output divided by the sum of the coefficients used.  All of it in double, like the
+ * reference. */
+static double qo_bessel_i0(double x) { /* :109-116 */
+    double sum = 1.0, term = 1.0, xx = x * x;
+    for (int k = 1; k <= 20; k++) {
+        term *= xx / (4.0 * (double)k * (double)k);
+        sum += term;
+    }
+    return sum;
+}
+
+float *qo_resample_to_16k(const float *in, int n, int rate, int *out_n) {
+    const double pi = 3.14159265358979323846;
+    int new_n = (int)((long long)n * 16000 / rate); /* :99 */
+    float *out = (float *)malloc((size_t)(new_n > 0 ? new_n : 1) * sizeof(float));
+    double ratio = 16000.0 / (double)rate, cutoff = ratio < 1.0 ? ratio : 1.0, inv_i0 = 1.0 / qo_bessel_i0(6.0);
+    for (int i = 0; i < new_n; i++) {
+        double pos = (double)i / ratio, acc = 0.0, wsum = 0.0;
+        int c = (int)pos;
+        for (int j = c - 15; j <= c + 16; j++) { /* SINC_HALF = 16: j in [c-16+1, c+16], :126-127 */
+            double d = (double)j - pos, x = d * cutoff;
+            double sv = fabs(x) < 1e-9 ? 1.0 : sin(pi * x) / (pi * x);
+            double np_ = d / 16.0;
+            double w = (np_ <= -1.0 || np_ >= 1.0) ? 0.0 : qo_bessel_i0(6.0 * sqrt(1.0 - np_ * np_)) * inv_i0;
+            double coeff = sv * w * cutoff;
+            if (j >= 0 && j < n) acc += (double)in[j] * coeff;
+            wsum += coeff;
+        }
+        out[i] = wsum > 1e-9 ? (float)(acc / wsum) : 0.0f;
+    }
+    *out_n = new_n;
+    return out;
+}
+
+static unsigned qo_rd16(const uint8_t *p) { return (unsigned)p[0] | ((unsigned)p[1] << 8); }
+static unsigned qo_rd32(const uint8_t *p) { return (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24); }
+
+float *qo_parse_wav_buffer(const uint8_t *data, size_t size, int *out_n) {
+    if (size < 44 || memcmp(data, "RIFF", 4) || memcmp(data + 8, "WAVE", 4)) return NULL;
+    int fmt = 0, ch = 0, rate = 0, bits = 0, pcm_bytes = 0;
+    const uint8_t *pcm = NULL, *p = data + 12, *end = data + size;
+    while (p + 8 <= end) {
+        unsigned len = qo_rd32(p + 4);
+        if (p + 8 + len > end) break;
+        if (!memcmp(p, "fmt ", 4) && len >= 16) { fmt = qo_rd16(p + 8); ch = qo_rd16(p + 10); rate = (int)qo_rd32(p + 12); bits = qo_rd16(p + 22); }
+        else if (!memcmp(p, "data", 4)) { pcm = p + 8; pcm_bytes = (int)len; }
+        p += 8 + len + (len & 1);
+    }
+    if (fmt != 1 || bits != 16 || !pcm || ch < 1) return NULL;
+    int n = pcm_bytes / (ch * 2);
+    float *mono = (float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(float));
+    for (int i = 0; i < n; i++) {
+        if (ch == 1) {
+            int16_t v; memcpy(&v, pcm + (size_t)i * 2, 2);
+            mono[i] = v / 32768.0f;
+        } else { /* float sum of the channels, then / channels / 32768, :86-92 */
+            float sum = 0;
+            for (int c = 0; c < ch; c++) { int16_t v; memcpy(&v, pcm + ((size_t)i * ch + c) * 2, 2); sum += v; }
+            mono[i] = (sum / ch) / 32768.0f;
+        }
+    }
+    if (rate != 16000) {
+        int nn = 0;
+        float *r = qo_resample_to_16k(mono, n, rate, &nn);
+        free(mono);
+        mono = r; n = nn;
+    }
+    *out_n = n;
+    return mono;
+}

@@ -69,6 +69,7 @@ float *ref_encode(void *c, const float *mel, int frames, int *T) {
     return qwen_encoder_forward((qwen_ctx_t *)c, mel, frames, T);
 }
 void ref_free_buf(void *p) { free(p); }
+float *ref_parse_wav(const unsigned char *data, size_t size, int *n) { return qwen_parse_wav_buffer(data, size, n); }
 
 void ref_set_kv_len(void *c, int n) { ((qwen_ctx_t *)c)->kv_cache_len = n; }
 int ref_get_kv_len(void *c) { return ((qwen_ctx_t *)c)->kv_cache_len; }

@@ -52,6 +52,7 @@ SIGNATURES = {
     "qasr_cuda_stream_begin": (ci, [vp, cf, ci]),
     "qasr_cuda_stream_feed": (ci, [vp, f32p, ci, ci, i32p, ip, ip, ip]),
     "qasr_cuda_stage_audio": (ci, [vp, f32p, ci]),
+    "qasr_cuda_decode_pcm16": (ci, [vp, vp, ci, ci, ci, vp, ci, ip]),
     "qasr_cuda_transcribe_staged": (ci, [vp, ci, i32p, ip, vp, ip]),
     "qasr_cuda_timer_start": (ci, [vp]),
     "qasr_cuda_timer_stop": (ci, [vp, C.POINTER(C.c_double)]),
@@ -292,6 +293,17 @@ class QasrCuda:
     def stage_audio(self, samples):
         samples = _f32(samples)
         self._ck(self.lib.qasr_cuda_stage_audio(self.ctx, samples, len(samples)))
+
+    def decode_pcm16(self, pcm, channels, sample_rate, want_host=True):
+        """Interleaved int16 PCM -> f32 mono 16 kHz (device resampler); the result is also left staged."""
+        pcm = np.ascontiguousarray(pcm, np.int16).reshape(-1)
+        n_frames = len(pcm) // channels
+        cap = n_frames if sample_rate == 16000 else int(n_frames * 16000 // sample_rate)
+        out = np.empty(max(cap, 1), np.float32) if want_host else None
+        n = ci(0)
+        self._ck(self.lib.qasr_cuda_decode_pcm16(self.ctx, pcm.ctypes.data_as(vp), n_frames, channels, sample_rate,
+                                                 out.ctypes.data_as(vp) if want_host else None, cap, C.byref(n)))
+        return out[:n.value] if want_host else n.value
 
     def transcribe_staged(self, max_new, ids_buf=None):
         ids = ids_buf if ids_buf is not None else np.zeros(max(max_new, 1), np.int32)

@@ -138,7 +138,7 @@ struct qasr_ctx {
     long long ws_gen = 0;                // bumped whenever a workspace the graphs point into is reallocated
     void *mega_maps = nullptr; // device array of CUtensorMap (128 B each): decoder matrices in phase order + embedding
     // scratch
-    DevBuf ws_samples, ws_meltmp, ws_mel, ws_enc, ws_encout, ws_pre, ws_ids, ws_geom;
+    DevBuf ws_samples, ws_meltmp, ws_mel, ws_enc, ws_encout, ws_pre, ws_ids, ws_geom, ws_pcm, ws_mono;
     int *d_gmax = nullptr;
     int mel_frames = 0, enc_T = 0;
     cudaEvent_t ev[5] = {};
@@ -212,6 +212,7 @@ void qasr_cuda_free(qasr_ctx_t *c) {
     c->ws_samples.release(); c->ws_meltmp.release(); c->ws_mel.release(); c->ws_enc.release();
     c->ws_encout.release(); c->ws_pre.release(); c->ws_ids.release(); c->ws_geom.release();
     for (auto &w : c->st_win) w.rows.release();
+    c->ws_pcm.release(); c->ws_mono.release();
     for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; i++) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
     cudaStreamDestroy(c->stream);
@@ -1465,6 +1466,30 @@ int qasr_cuda_stream_feed(qasr_ctx_t *c, const float *samples, int n_samples, in
     c->st_fed = true;
     if (out_reused) *out_reused = reused;
     if (out_rows) *out_rows = total;
+    return 0;
+}
+
+// Interleaved 16-bit PCM at any sample rate -> f32 mono 16 kHz on the device (reference qwen_parse_wav_buffer,
+// qwen_asr_audio.c:81-164).  The result is left staged like qasr_cuda_stage_audio (so qasr_cuda_transcribe_staged can
+// consume it without another copy) and optionally copied to the host.
+int qasr_cuda_decode_pcm16(qasr_ctx_t *c, const int16_t *pcm, int n_frames, int channels, int sample_rate, float *out, int out_cap, int *out_n) {
+    if (!c || !pcm || !out_n || n_frames <= 0 || channels < 1 || sample_rate < 1000) return set_err(QASR_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(c->device));
+    const int new_n = sample_rate == 16000 ? n_frames : (int)((long long)n_frames * 16000 / sample_rate);
+    if (new_n <= 0) return set_err(QASR_ERR_ARG, "audio too short");
+    if (out && out_cap < new_n) return set_err(QASR_ERR_ARG, "output buffer holds %d samples, %d needed", out_cap, new_n);
+    if (c->ws_pcm.reserve((size_t)n_frames * channels * 2) || c->ws_mono.reserve((size_t)n_frames * 4) || c->ws_samples.reserve((size_t)new_n * 4))
+        return set_err(QASR_ERR_NOMEM, "audio buffers");
+    CK(cudaMemcpyAsync(c->ws_pcm.p, pcm, (size_t)n_frames * channels * 2, cudaMemcpyHostToDevice, c->stream));
+    float *mono = sample_rate == 16000 ? c->ws_samples.as<float>() : c->ws_mono.as<float>();
+    launch_pcm16_to_mono(c->stream, c->ws_pcm.as<int16_t>(), n_frames, channels, mono);
+    if (sample_rate != 16000) launch_resample_sinc(c->stream, mono, n_frames, sample_rate, c->ws_samples.as<float>(), new_n);
+    c->launches += sample_rate != 16000 ? 2 : 1;
+    CK(cudaGetLastError());
+    if (out) CK(cudaMemcpyAsync(out, c->ws_samples.p, (size_t)new_n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->staged_samples = new_n;
+    *out_n = new_n;
     return 0;
 }
 

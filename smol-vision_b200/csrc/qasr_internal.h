@@ -147,6 +147,9 @@ void launch_im2col_stage(cudaStream_t s, const bf16_t *src, bf16_t *dst, const C
 void launch_mel(cudaStream_t s, const float *samples, int n, int frames, const float *d_cos, const float *d_sin,
                 const float *d_win, const float *d_fb, float *mel_tmp, int *d_gmax, float *mel_out);
 
+void launch_pcm16_to_mono(cudaStream_t s, const int16_t *pcm, int n, int channels, float *out);
+void launch_resample_sinc(cudaStream_t s, const float *in, int n, int rate, float *out, int new_n);
+
 // ---- tcgen05 GEMM (qasr_gemm_tc.cu)
 // C[M,N] = A[M,K] * W[N,K]^T with A given as bf16 hi (+ optional lo) planes, W bf16, f32 accumulate in TMEM.
 int gemm_tc_init(void); // resolves cuTensorMapEncodeTiled, sets smem attributes; 0 on success

@@ -110,3 +110,53 @@ void launch_mel(cudaStream_t s, const float *samples, int n, int frames, const f
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
     mel_pass2_kernel<<<blocks, 256, 0, s>>>(mel_tmp, d_gmax, frames, mel_out);
 }
+
+
+// ------------------------------------------------------------------ PCM16 -> f32 mono 16 kHz
+// reference qwen_parse_wav_buffer, qwen_asr_audio.c:81-164: channels averaged in f32 and scaled by 1/32768, then - for
+// files that are not at 16 kHz - a 32-tap windowed-sinc resampler evaluated in double (sinc cut at min(ratio, 1), Kaiser
+// window beta = 6 with I0 as a 20-term power series, output divided by the sum of the coefficients).  One thread per sample.
+__global__ void pcm16_to_mono_kernel(const int16_t *__restrict__ pcm, int n, int channels, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (channels == 1) { out[i] = (float)pcm[i] / 32768.0f; return; }
+    float sum = 0.0f;
+    for (int c = 0; c < channels; c++) sum += (float)pcm[(size_t)i * channels + c];
+    out[i] = (sum / (float)channels) / 32768.0f;
+}
+__device__ __forceinline__ double bessel_i0_series(double x) {
+    double sum = 1.0, term = 1.0;
+    const double xx = x * x;
+#pragma unroll 1
+    for (int k = 1; k <= 20; k++) {
+        term *= xx / (4.0 * (double)k * (double)k);
+        sum += term;
+    }
+    return sum;
+}
+__global__ void resample_sinc_kernel(const float *__restrict__ in, int n, int rate, float *__restrict__ out, int new_n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= new_n) return;
+    const double pi = 3.14159265358979323846;
+    const double ratio = 16000.0 / (double)rate, cutoff = ratio < 1.0 ? ratio : 1.0, inv_i0 = 1.0 / bessel_i0_series(6.0);
+    const double pos = (double)i / ratio;
+    const int c = (int)pos;
+    double acc = 0.0, wsum = 0.0;
+#pragma unroll 1
+    for (int j = c - 15; j <= c + 16; j++) {
+        const double d = (double)j - pos, x = d * cutoff;
+        const double sv = fabs(x) < 1e-9 ? 1.0 : sin(pi * x) / (pi * x);
+        const double np_ = d / 16.0;
+        const double w = (np_ <= -1.0 || np_ >= 1.0) ? 0.0 : bessel_i0_series(6.0 * sqrt(1.0 - np_ * np_)) * inv_i0;
+        const double coeff = sv * w * cutoff;
+        if (j >= 0 && j < n) acc += (double)in[j] * coeff;
+        wsum += coeff;
+    }
+    out[i] = wsum > 1e-9 ? (float)(acc / wsum) : 0.0f;
+}
+void launch_pcm16_to_mono(cudaStream_t s, const int16_t *pcm, int n, int channels, float *out) {
+    if (n > 0) pcm16_to_mono_kernel<<<(n + 255) / 256, 256, 0, s>>>(pcm, n, channels, out);
+}
+void launch_resample_sinc(cudaStream_t s, const float *in, int n, int rate, float *out, int new_n) {
+    if (new_n > 0) resample_sinc_kernel<<<(new_n + 127) / 128, 128, 0, s>>>(in, n, rate, out, new_n);
+}

@@ -325,3 +325,21 @@ def test_device_stream_session_equals_host_session(gpu06, pkg, seconds, window, 
         assert (d["ids"], d["reused"], d["rows"]) == (h["ids"], h["reused"], h["rows"])
     gpu06.stream_begin(window, maxw)     # a second session on the same context starts from an empty cache
     assert gpu06.stream_feed(audio[:16000], 5)["reused"] == 0
+
+
+@pytest.mark.parametrize("channels,rate,n", [(1, 16000, 20000), (2, 44100, 50000), (1, 8000, 12000), (2, 48000, 30001), (1, 22050, 33333)])
+def test_device_pcm_decode_and_resample_vs_oracle(gpu06, oracle_lib, channels, rate, n):
+    """qasr_cuda_decode_pcm16 (channel average, 1/32768, the reference's windowed-sinc resampler in double on the device,
+    SURVEY 8f-4) against the CPU restatement of qwen_parse_wav_buffer, which is pinned to the compiled reference."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from make_golden import wav_bytes
+    rng = np.random.default_rng(channels * 1000 + rate)
+    pcm = (rng.standard_normal((n, channels)) * 6000).astype(np.int16)
+    want = oracle_lib().parse_wav(wav_bytes(pcm, channels, rate))
+    got = gpu06.decode_pcm16(pcm, channels, rate)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 2e-7          # double sin/sqrt on the device vs libm: at most an f32 ulp
+    ids_a = gpu06.transcribe_staged(5)[0].tolist()   # the resampled audio is left staged in HBM
+    ids_b = gpu06.transcribe_ids(got, 5)[0].tolist()
+    assert ids_a == ids_b

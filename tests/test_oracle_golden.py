@@ -141,3 +141,20 @@ def test_segment_against_reference_golden(oracle06, golden_seg, pkg):
     ids, info = oracle06.transcribe_ids(audio, len(g["ids"]))
     assert info["enc_tokens"] == g["enc"].shape[0]
     assert ids.tolist() == g["ids"].tolist()
+
+
+def test_wav_parse_and_resample_against_reference_golden(oracle_lib):
+    """qo_parse_wav_buffer (restatement of qwen_parse_wav_buffer, reference qwen_asr_audio.c:40-168: RIFF walk, stereo
+    average, 1/32768, windowed-sinc resampler in double) against outputs of the compiled reference (tests/golden/wav.npz,
+    tools/make_golden.py --wav-only)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from make_golden import wav_bytes
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wav.npz"))
+    o = oracle_lib()
+    for i in range(int(g["count"])):
+        ch, rate, n = (int(v) for v in g[f"meta{i}"])
+        out = o.parse_wav(wav_bytes(g[f"pcm{i}"].reshape(n, ch), ch, rate))
+        assert out.shape == g[f"out{i}"].shape == ((n,) if rate == 16000 else (n * 16000 // rate,))
+        assert np.abs(out - g[f"out{i}"]).max() <= 1e-7
+    assert o.parse_wav(b"RIFFxxxxWAVEjunk" + b"\0" * 40) is None       # no fmt / data chunk: rejected like the reference

@@ -49,3 +49,19 @@ def test_kv_rollback_and_delta_prefill(ref06, oracle06, pkg):
         outs.append((t_full, t_delta, eng.kv_len))
     assert outs[0] == outs[1]
     assert outs[0][0] == outs[0][1]
+
+
+def test_wav_parse_and_resample_live(ref_lib, oracle_lib):
+    """Live: restated qwen_parse_wav_buffer vs the compiled reference on random PCM at several rates / channel counts."""
+    if ref_lib is None:
+        pytest.skip("oracle/_ref not available")
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from make_golden import wav_bytes
+    r, o = ref_lib(), oracle_lib()
+    rng = np.random.default_rng(9)
+    for ch, rate, n in [(1, 16000, 4000), (2, 44100, 9000), (1, 8000, 3000), (3, 32000, 5000), (1, 11025, 2500)]:
+        pcm = (rng.standard_normal((n, ch)) * 7000).astype(np.int16)
+        w = wav_bytes(pcm, ch, rate)
+        a, b = o.parse_wav(w), r.parse_wav(w)
+        assert a.shape == b.shape and np.abs(a - b).max() <= 1e-7

@@ -163,10 +163,39 @@ def ops_golden(ref):
     print("ops:", sorted(g))
 
 
+def wav_bytes(pcm, channels, rate):
+    """Minimal RIFF/WAVE file around interleaved int16 PCM."""
+    import struct
+    data = np.ascontiguousarray(pcm, np.int16).tobytes()
+    return (b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 1, channels, rate, rate * channels * 2, channels * 2, 16)
+            + b"data" + struct.pack("<I", len(data)) + data)
+
+
+def wav_golden(ref):
+    """qwen_parse_wav_buffer (reference qwen_asr_audio.c:40-168) on small synthetic WAV files: mono/stereo, 16 kHz
+    pass-through, down- and up-sampling."""
+    g = {}
+    rng = np.random.default_rng(2024)
+    for i, (ch, rate, n) in enumerate([(1, 16000, 1500), (2, 44100, 3000), (1, 8000, 1200), (2, 48000, 2400), (1, 22050, 2345)]):
+        t = np.arange(n) / rate
+        base = 0.3 * np.sin(2 * np.pi * 440.0 * t) + 0.1 * np.sin(2 * np.pi * 3100.0 * t)
+        pcm = np.stack([base * (1.0 - 0.2 * c) for c in range(ch)], axis=1) + 0.02 * rng.standard_normal((n, ch))
+        pcm = np.clip(np.round(pcm * 32768.0), -32768, 32767).astype(np.int16)
+        g[f"pcm{i}"], g[f"meta{i}"] = pcm.reshape(-1), np.array([ch, rate, n], np.int32)
+        g[f"out{i}"] = ref.parse_wav(wav_bytes(pcm, ch, rate))
+    g["count"] = np.array(5, np.int32)
+    np.savez_compressed(os.path.join(OUT, "wav.npz"), **g)
+    print("wav:", [len(g[f"out{i}"]) for i in range(5)])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = RefLib()
+    if "--wav-only" in sys.argv:
+        wav_golden(ref)
+        return
     ops_golden(ref)
+    wav_golden(ref)
     ref.load(pkg.ensure_model_dir("0.6b"))
     segment_golden(ref, "0p6b", seconds=2.5, seed=7, n_ids=16, n_logit_steps=3)
     ref.close()
