@@ -46,22 +46,19 @@
 
 #define SK_WARPS 16
 #define SK_THREADS (SK_WARPS * 32)
-#ifndef SK_SLOTS
-#define SK_SLOTS 5
-#endif
 #define SK_UNIT 2048          /* 16 rows x 64 cols bf16, A-fragment order: [kb 0..3][lane][a0..a3] */
 #define SK_CHUNK_GROUPS 8     /* 16-row groups reduced together (128 rows) */
 #define SK_PSTRIDE 17
 #define SK_MAX_K 6144
 #define SK_MAX_H 2048
 #ifndef SK_ATT_MAXS
-#define SK_ATT_MAXS 4
+#define SK_ATT_MAXS 4         /* key splits per (sequence, head); measured: 4 > 8 (the merge at the WO stage grows with it) */
 #endif
 #ifndef SK_ATT_BATCH
-#define SK_ATT_BATCH 2
+#define SK_ATT_BATCH 2        /* cached keys per warp whose K/V rows are loaded ahead of the q words; a split holds 32 keys per batch */
 #endif
-//      SK_ATT_BATCH:      /* cached keys per warp whose K/V rows are loaded ahead of the q words */
 #define SK_ATT_STRIDE 130     /* 128 acc + m + l */
+// p.debug bits: 4 = stall-driven L2 prefetch without the evict_last hint, 64 = per-unit trace of warp 0 of CTA p.trace_cta
 
 typedef unsigned long long u64;
 
