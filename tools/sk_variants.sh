@@ -8,5 +8,4 @@ run "batch4 maxs4 l2w16" 16
 build "-DSK_ATT_BATCH=2"; run "batch2 maxs4 l2w8"
 build "-DSK_ATT_BATCH=2 -DSK_ATT_MAXS=8"; run "batch2 maxs8 l2w8"
 build "-DSK_ATT_BATCH=1 -DSK_ATT_MAXS=8"; run "batch1 maxs8 l2w8"
-build "-DSK_SLOTS=4"; run "slots4 l2w8"
 build "";
