@@ -141,6 +141,7 @@ struct qasr_ctx {
     DevBuf ws_samples, ws_meltmp, ws_mel, ws_enc, ws_encout, ws_pre, ws_ids, ws_geom, ws_pcm, ws_mono;
     int *d_gmax = nullptr;
     int mel_frames = 0, enc_T = 0;
+    int geom_frames = 0; // frame count whose chunk / window tables sit in ws_geom
     cudaEvent_t ev[5] = {};
     cudaEvent_t tev[2] = {};
     double last_decode_ms = 0.0;
@@ -778,9 +779,13 @@ static int encode_device(qasr_ctx_t *c, const float *d_mel, int frames, int *T_o
     }
     if (c->ws_geom.reserve((geom.size() + aux.size()) * 4)) return set_err(QASR_ERR_NOMEM, "geom alloc");
     int *dg = c->ws_geom.as<int>();
-    CK(cudaMemcpyAsync(dg, geom.data(), geom.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(dg + geom.size(), aux.data(), aux.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaStreamSynchronize(c->stream)); // host vectors go out of scope below
+    if (c->geom_frames != frames || c->ws_geom.grew) { // the tables depend on `frames` only: same length, nothing to upload and no host sync
+        c->geom_frames = 0;
+        CK(cudaMemcpyAsync(dg, geom.data(), geom.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(dg + geom.size(), aux.data(), aux.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream)); // host vectors go out of scope below
+        c->geom_frames = frames;
+    }
     ConvGeom g;
     g.n_chunks = nc; g.d_w0 = dg; g.d_mel0 = dg + nc; g.d_off1 = dg + 2 * nc; g.d_off2 = g.d_off1 + nc + 1; g.d_off3 = g.d_off2 + nc + 1;
     g.total1 = tot1; g.total2 = tot2; g.total3 = tot3;

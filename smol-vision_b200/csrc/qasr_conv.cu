@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256)
 conv1_kernel(const float *__restrict__ mel, int frames, const float *__restrict__ w /*[480][9]*/,
              const float *__restrict__ b, const int *__restrict__ w0s, const int *__restrict__ mel0s,
              const int *__restrict__ off1, bf16_t *__restrict__ ohi, bf16_t *__restrict__ olo) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float in_s[3][130]; // [kj][ih+1], zero padded
     __shared__ float w_s[480 * 9];
     __shared__ float b_s[480];
@@ -55,7 +57,7 @@ void launch_conv1(cudaStream_t s, const float *mel, int frames, const float *w, 
                   bf16_t *out_hi, bf16_t *out_lo) {
     if (g.n_chunks <= 0) return;
     dim3 grid(g.n_chunks, 50);
-    conv1_kernel<<<grid, 256, 0, s>>>(mel, frames, w, b, g.d_w0, g.d_mel0, g.d_off1, out_hi, out_lo);
+    launch_pdl(conv1_kernel, grid, 256, 0, s, mel, frames, w, b, g.d_w0, g.d_mel0, g.d_off1, out_hi, out_lo);
 }
 
 // Patch gather for stage 2 (64 x w1 -> 32 x w2) or 3 (32 x w2 -> 16 x w3).
@@ -65,6 +67,8 @@ __global__ void __launch_bounds__(256)
 im2col_stage_kernel(const bf16_t *__restrict__ src, bf16_t *__restrict__ dst, const int *__restrict__ w0s,
                     const int *__restrict__ off_in, const int *__restrict__ off_out, int n_chunks, int stage,
                     int total_out) {
+    pdl_wait();
+    pdl_trigger();
     const int Hin = stage == 2 ? 64 : 32, Hout = Hin / 2;
     const long long n_items = (long long)total_out * 9 * 60;
     for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < n_items;
@@ -96,6 +100,6 @@ void launch_im2col_stage(cudaStream_t s, const bf16_t *src, bf16_t *dst, const C
     if (total_out <= 0) return;
     const long long n_items = (long long)total_out * 540;
     const int blocks = (int)((n_items + 255) / 256 < 148 * 16 ? (n_items + 255) / 256 : 148 * 16);
-    im2col_stage_kernel<<<blocks, 256, 0, s>>>(src, dst, g.d_w0, stage == 2 ? g.d_off1 : g.d_off2,
+    launch_pdl(im2col_stage_kernel, blocks, 256, 0, s, src, dst, g.d_w0, stage == 2 ? g.d_off1 : g.d_off2,
                                               stage == 2 ? g.d_off2 : g.d_off3, g.n_chunks, stage, total_out);
 }

@@ -148,6 +148,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();    // barriers, tensor-map prefetch and the TMEM allocation above overlapped the previous grid
+    pdl_trigger();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -344,6 +346,11 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // The weight producer (warp 0) does not wait for the previous grid: weights are constants, so its first STAGES
+    // tiles stream from HBM while the previous kernel drains.  Every other warp (activation loads, MMAs that consume
+    // them, output stores, split-K scratch) waits, so the grid as a whole still completes after its predecessor.
+    pdl_trigger();
+    if (warp != 0) pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -621,9 +628,9 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
             if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(3d) failed (%d) M=%d K=%d", (int)r, M, K); return -1; }
         }
         dim3 grid(n_tiles, S);
-        if (MP == 64) gemm_tc_skinny_kernel<64, 6><<<grid, SK_THREADS, sk_smem_bytes<64, 6>(), s>>>(mw, ma, sp);
-        else if (MP == 128) gemm_tc_skinny_kernel<128, 4><<<grid, SK_THREADS, sk_smem_bytes<128, 4>(), s>>>(mw, ma, sp);
-        else gemm_tc_skinny_kernel<256, 2><<<grid, SK_THREADS, sk_smem_bytes<256, 2>(), s>>>(mw, ma, sp);
+        if (MP == 64) launch_pdl(gemm_tc_skinny_kernel<64, 6>, grid, SK_THREADS, sk_smem_bytes<64, 6>(), s, mw, ma, sp);
+        else if (MP == 128) launch_pdl(gemm_tc_skinny_kernel<128, 4>, grid, SK_THREADS, sk_smem_bytes<128, 4>(), s, mw, ma, sp);
+        else launch_pdl(gemm_tc_skinny_kernel<256, 2>, grid, SK_THREADS, sk_smem_bytes<256, 2>(), s, mw, ma, sp);
         cudaError_t le = cudaGetLastError();
         if (le != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc skinny launch: %s", cudaGetErrorString(le)); return -1; }
         return 0;
@@ -648,13 +655,13 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
     if (make_map(&mb, W, N, K, bn64 ? 64 : (bn256 ? 256 : 128)) != 0) return -1;
     if (bn256) {
         dim3 grid((N + 255) / 256, (M + TC_BM - 1) / TC_BM);
-        gemm_tc_kernel<256><<<grid, TC_THREADS, tc_smem_bytes<256>(), s>>>(ma, ml, mb, p);
+        launch_pdl(gemm_tc_kernel<256>, grid, TC_THREADS, tc_smem_bytes<256>(), s, ma, ml, mb, p);
     } else if (bn64) {
         dim3 grid((N + 63) / 64, (M + TC_BM - 1) / TC_BM);
-        gemm_tc_kernel<64><<<grid, TC_THREADS, tc_smem_bytes<64>(), s>>>(ma, ml, mb, p);
+        launch_pdl(gemm_tc_kernel<64>, grid, TC_THREADS, tc_smem_bytes<64>(), s, ma, ml, mb, p);
     } else {
         dim3 grid((N + 127) / 128, (M + TC_BM - 1) / TC_BM);
-        gemm_tc_kernel<128><<<grid, TC_THREADS, tc_smem_bytes<128>(), s>>>(ma, ml, mb, p);
+        launch_pdl(gemm_tc_kernel<128>, grid, TC_THREADS, tc_smem_bytes<128>(), s, ma, ml, mb, p);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

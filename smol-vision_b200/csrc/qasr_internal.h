@@ -6,6 +6,34 @@
 
 typedef uint16_t bf16_t; // raw bf16 bits on the host side / in signatures
 
+#ifdef __CUDACC__
+#include <stdlib.h>
+#include <utility>
+// Programmatic dependent launch for the encoder / prefill launch chains (~440 small dependent kernels per utterance):
+// every kernel of a chain starts with pdl_wait() - nothing it reads or writes is touched before the previous grid has
+// completed and flushed - and pdl_trigger(), so the NEXT grid's launch, CTA scheduling and (for the GEMMs) barrier /
+// TMEM set-up overlap this grid instead of following its drain.  Every kernel of a chain must wait, or completion
+// would stop being transitive.  QASR_PDL=0 launches the same kernels with ordinary stream order.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("QASR_PDL"); on = !(e && e[0] == '0'); }
+    return on != 0;
+}
+template <class... KA, class... A>
+inline cudaError_t launch_pdl(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+#endif
+
 enum { QASR_EPI_STORE = 0, QASR_EPI_RESIDUAL = 1, QASR_EPI_SWIGLU = 2 };
 // tensor-core GEMM epilogues
 enum { QASR_GEMM_F32 = 0, QASR_GEMM_RESIDUAL = 1, QASR_GEMM_GELU_SPLIT = 2, QASR_GEMM_SWIGLU_SPLIT = 3 };

@@ -35,6 +35,8 @@ __device__ __forceinline__ float norm_block_sum(float v, float *red) {
 __global__ void __launch_bounds__(NORM_THREADS)
 rmsnorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ gamma, float eps, int H, float *of, bf16_t *ohi,
                     bf16_t *olo) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red[NORM_THREADS / 32];
     const size_t base = (size_t)blockIdx.x * H;
     float v[NORM_MAX_PER];
@@ -54,7 +56,7 @@ rmsnorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ gamma
 }
 void launch_rmsnorm(cudaStream_t s, const float *x, const float *gamma, float eps, int M, int H, float *out_f32,
                     bf16_t *out_hi, bf16_t *out_lo) {
-    if (M > 0) rmsnorm_rows_kernel<<<M, NORM_THREADS, 0, s>>>(x, gamma, eps, H, out_f32, out_hi, out_lo);
+    if (M > 0) launch_pdl(rmsnorm_rows_kernel, M, NORM_THREADS, 0, s, x, gamma, eps, H, out_f32, out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------ LayerNorm (rows)
@@ -62,6 +64,8 @@ void launch_rmsnorm(cudaStream_t s, const float *x, const float *gamma, float ep
 __global__ void __launch_bounds__(NORM_THREADS)
 layernorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b, float eps, int H,
                       float *of, bf16_t *ohi, bf16_t *olo) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float red[NORM_THREADS / 32];
     const size_t base = (size_t)blockIdx.x * H;
     float v[NORM_MAX_PER];
@@ -89,7 +93,7 @@ layernorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ w, 
 }
 void launch_layernorm(cudaStream_t s, const float *x, const float *w, const float *b, float eps, int M, int H,
                       float *out_f32, bf16_t *out_hi, bf16_t *out_lo) {
-    if (M > 0) layernorm_rows_kernel<<<M, NORM_THREADS, 0, s>>>(x, w, b, eps, H, out_f32, out_hi, out_lo);
+    if (M > 0) launch_pdl(layernorm_rows_kernel, M, NORM_THREADS, 0, s, x, w, b, eps, H, out_f32, out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------ per-head RMSNorm (in place)
@@ -117,6 +121,8 @@ __global__ void __launch_bounds__(128)
 qk_norm_rope_store_kernel(const float *__restrict__ qkv, const float *__restrict__ qn, const float *__restrict__ kn,
                           const float *__restrict__ rope_cos, const float *__restrict__ rope_sin, int start_pos,
                           float eps, float *__restrict__ q_out, float *__restrict__ kc, float *__restrict__ vc) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ float tmp[128];
     __shared__ float red[4];
     const int p = blockIdx.x, slot = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -141,7 +147,7 @@ qk_norm_rope_store_kernel(const float *__restrict__ qkv, const float *__restrict
 }
 void launch_qk_norm_rope_store(cudaStream_t s, const float *qkv, const float *qn, const float *kn, const float *rope_cos,
                                const float *rope_sin, int start_pos, int P, float eps, float *q_out, float *kc, float *vc) {
-    if (P > 0) qk_norm_rope_store_kernel<<<dim3(P, 32), 128, 0, s>>>(qkv, qn, kn, rope_cos, rope_sin, start_pos, eps, q_out, kc, vc);
+    if (P > 0) launch_pdl(qk_norm_rope_store_kernel, dim3(P, 32), 128, 0, s, qkv, qn, kn, rope_cos, rope_sin, start_pos, eps, q_out, kc, vc);
 }
 
 // ------------------------------------------------------------------ online-softmax helpers
@@ -247,6 +253,8 @@ __global__ void __launch_bounds__(256)
 attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, const float *__restrict__ vc,
                     int q_offset, int P, int seq_k, int n_heads, int n_kv_heads, float scale, float *of, bf16_t *ohi,
                     bf16_t *olo) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ __align__(16) uint8_t att_raw[];
     AttSmem<128> &sm = *reinterpret_cast<AttSmem<128> *>(att_raw);
     const int kvh = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -296,7 +304,7 @@ void launch_attn_prefill(cudaStream_t s, const float *q, const float *kc, const 
         attr_set |= 1u << (dev & 31);
     }
     dim3 grid(n_kv_heads, (P + 15) / 16);
-    attn_prefill_kernel<<<grid, 256, sizeof(AttSmem<128>), s>>>(q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, out_f32, out_hi, out_lo);
+    launch_pdl(attn_prefill_kernel, grid, 256, sizeof(AttSmem<128>), s, q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, out_f32, out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------ windowed bidirectional attention (encoder)
@@ -306,6 +314,8 @@ __global__ void __launch_bounds__(256)
 attn_windowed_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v, int ld,
                      const int *__restrict__ window_starts, float scale, int out_ld, float *of, bf16_t *ohi,
                      bf16_t *olo) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ AttSmem<64> sm;
     const int h = blockIdx.x, w = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ws = window_starts[w], we = window_starts[w + 1];
@@ -346,7 +356,7 @@ void launch_attn_windowed(cudaStream_t s, const float *q, const float *k, const 
                           float *out_f32, bf16_t *out_hi, bf16_t *out_lo) {
     if (n_windows <= 0) return;
     dim3 grid(n_heads, n_windows, (max_window + 31) / 32);
-    attn_windowed_kernel<<<grid, 256, 0, s>>>(q, k, v, ld, d_window_starts, scale, out_ld, out_f32, out_hi, out_lo);
+    launch_pdl(attn_windowed_kernel, grid, 256, 0, s, q, k, v, ld, d_window_starts, scale, out_ld, out_f32, out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------ small element-wise kernels
@@ -362,12 +372,14 @@ void launch_split_f32(cudaStream_t s, const float *x, size_t n, bf16_t *hi, bf16
 
 // x[m, :] += table[row_idx[m], :]   (per-chunk sinusoidal PE, reference qwen_asr_encoder.c:280-284)
 __global__ void add_rows_kernel(float *x, const float *__restrict__ table, const int *__restrict__ row_idx, int d) {
+    pdl_wait();
+    pdl_trigger();
     const int m = blockIdx.x;
     const float *t = table + (size_t)row_idx[m] * d;
     for (int i = threadIdx.x; i < d; i += blockDim.x) x[(size_t)m * d + i] += t[i];
 }
 void launch_add_rows(cudaStream_t s, float *x, const float *table, const int *d_row_idx, int M, int d) {
-    if (M > 0) add_rows_kernel<<<M, 256, 0, s>>>(x, table, d_row_idx, d);
+    if (M > 0) launch_pdl(add_rows_kernel, M, 256, 0, s, x, table, d_row_idx, d);
 }
 
 // op: 0 add (a+=b) 1 mul (a*=b) 2 scale (a*=s) 3 gelu 4 silu
