@@ -263,12 +263,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 // the WEIGHT tile (each weight byte enters shared memory exactly once) and the activations are the
 // N-side operand (MP = M rounded up to 64/128/256 columns of TMEM); split-K spreads one weight
 // matrix over ~148 CTAs.  D[n (TMEM lane), m (column)] = sum_k W[n,k] * A[m,k].
-// Split-K partials go to a workspace; the LAST CTA of a tile (ticket counter) adds the partials in
-// fixed split order and runs the epilogue => deterministic.  Stores are coalesced along n.
+// Split-K: the S CTAs of a tile are launched as one thread-block cluster (1, S, 1).  Each leaves its partial tile in its
+// own shared memory (the drained pipeline stages), the cluster synchronises, and CTA r adds rows [r*M/S, (r+1)*M/S) of
+// all S partials over distributed shared memory in fixed split order and runs the epilogue => deterministic, no
+// global scratch, no atomics, and the reduction itself is spread over the S CTAs.  (QASR_GEMM_SK_CLUSTER=0 keeps the
+// earlier scheme: partials in a global workspace, the last CTA of a tile - ticket counter - reduces them; same sums.)
+// Stores are coalesced along n.
 struct SkParams {
     int M, N, K, nsplit, S, kb_per; // S = split-K factor, kb_per = k-blocks per split
     float *ws;                      // [n_tiles][S][MP][128] f32 partials (S > 1)
     unsigned *tickets;              // [n_tiles], zero between launches
+    int cluster;                    // 1: the S splits of a tile form one thread-block cluster (1, S, 1) and reduce through DSMEM
     GemmEpilogue epi;
 };
 
@@ -298,6 +303,27 @@ __device__ __forceinline__ void sk_epilogue_store(const SkParams &p, int n, int 
         split_bf16(v, hi, lo);
         e.out_hi[(size_t)m * e.ldo + n] = __bfloat16_as_ushort(hi);
         if (e.out_lo) e.out_lo[(size_t)m * e.ldo + n] = __bfloat16_as_ushort(lo);
+    }
+}
+
+// epilogue of 4 consecutive reduced outputs (row m, columns nb..nb+3) of a split-K tile
+template <int MP>
+__device__ __forceinline__ void sk_reduced_store(const SkParams &p, int nb, int m, const float4 v) {
+    if (p.epi.mode == QASR_GEMM_SWIGLU_SPLIT) { // (gate, up) pairs sit inside the float4
+        const GemmEpilogue &e = p.epi;
+        const float r[2] = {silu(v.x) * v.y, silu(v.z) * v.w};
+#pragma unroll
+        for (int j = 0; j < 2; j++)
+            if (nb + 2 * j + 1 < p.N) {
+                __nv_bfloat16 hi, lo;
+                split_bf16(r[j], hi, lo);
+                e.out_hi[(size_t)m * e.ldo + ((nb >> 1) + j)] = __bfloat16_as_ushort(hi);
+                if (e.out_lo) e.out_lo[(size_t)m * e.ldo + ((nb >> 1) + j)] = __bfloat16_as_ushort(lo);
+            }
+    } else {
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) sk_epilogue_store<MP>(p, nb + j, m, vv[j], 0);
     }
 }
 
@@ -400,7 +426,8 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int q = warp & 3, nl = q * 32 + lane, n = n0 + nl;
-        float *wsp = p.ws + ((size_t)(tile * p.S + split) * MP) * 128 + nl;
+        float *wsp = p.cluster ? reinterpret_cast<float *>(smem) + nl // every stage has been consumed: the MMAs that read them are complete
+                               : p.ws + ((size_t)(tile * p.S + split) * MP) * 128 + nl;
 #pragma unroll 1
         for (int c0 = 0; c0 < MP; c0 += 32) {
             if (c0 >= p.M) break; // columns beyond M hold products with zero-filled rows
@@ -423,7 +450,34 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)MP) : "memory");
     }
     if (p.S == 1) return;
-    // ---- split-K: the last CTA to finish this tile reduces the partials in fixed split order
+    if (p.cluster) {
+        // ---- split-K over the cluster: partial tiles sit in the S shared memories; this CTA owns a band of rows
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        const int mper = (p.M + p.S - 1) / p.S, mlo = split * mper, mhi = min(p.M, mlo + mper);
+        uint32_t peer[8];
+#pragma unroll
+        for (int sp = 0; sp < 8; sp++)
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer[sp]) : "r"(smem_u32(smem)), "r"(sp < p.S ? sp : 0));
+        for (int idx = mlo * 32 + threadIdx.x; idx < mhi * 32; idx += SK_THREADS) {
+            const int m = idx >> 5, c4 = idx & 31;
+            const uint32_t off = (uint32_t)(m * 128 + c4 * 4) * 4u;
+            float4 t[8];
+#pragma unroll
+            for (int sp = 0; sp < 8; sp++)
+                if (sp < p.S)
+                    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                 : "=f"(t[sp].x), "=f"(t[sp].y), "=f"(t[sp].z), "=f"(t[sp].w) : "r"(peer[sp] + off) : "memory");
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int sp = 0; sp < 8; sp++)
+                if (sp < p.S) { v.x += t[sp].x; v.y += t[sp].y; v.z += t[sp].z; v.w += t[sp].w; }
+            sk_reduced_store<MP>(p, n0 + c4 * 4, m, v);
+        }
+        // nobody leaves while a peer may still read its shared memory
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        return;
+    }
+    // ---- split-K through global scratch: the last CTA to finish this tile reduces the partials in fixed split order
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -455,25 +509,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         for (int u = 0; u < 4; u++) {
         const int idx = base + u * SK_THREADS + threadIdx.x;
         if (idx >= p.M * 32) continue;
-        const int m = idx >> 5, c4 = idx & 31;
-        const float4 v = acc4[u];
-        const int nb = n0 + c4 * 4;
-        if (p.epi.mode == QASR_GEMM_SWIGLU_SPLIT) { // (gate, up) pairs sit inside the float4
-            const GemmEpilogue &e = p.epi;
-            const float r[2] = {silu(v.x) * v.y, silu(v.z) * v.w};
-#pragma unroll
-            for (int j = 0; j < 2; j++)
-                if (nb + 2 * j + 1 < p.N) {
-                    __nv_bfloat16 hi, lo;
-                    split_bf16(r[j], hi, lo);
-                    e.out_hi[(size_t)m * e.ldo + ((nb >> 1) + j)] = __bfloat16_as_ushort(hi);
-                    if (e.out_lo) e.out_lo[(size_t)m * e.ldo + ((nb >> 1) + j)] = __bfloat16_as_ushort(lo);
-                }
-        } else {
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) sk_epilogue_store<MP>(p, nb + j, m, vv[j], 0);
-        }
+        sk_reduced_store<MP>(p, n0 + (idx & 31) * 4, idx >> 5, acc4[u]);
         }
     }
 }
@@ -600,10 +636,13 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
         int S = (target_ctas + n_tiles - 1) / n_tiles; // split K until ~target_ctas CTAs stream weights
         if (S > total_kb / min_kb) S = total_kb / min_kb;
         if (S < 1) S = 1;
+        static int sk_cluster = -1;
+        if (sk_cluster < 0) { const char *ev = getenv("QASR_GEMM_SK_CLUSTER"); sk_cluster = !(ev && ev[0] == '0'); }
+        if (sk_cluster && S > 8) S = 8; // portable cluster size
         const int kb_per = (total_kb + S - 1) / S;
         S = (total_kb + kb_per - 1) / kb_per;
         const size_t need = (size_t)n_tiles * S * MP * 128 * sizeof(float);
-        if (!sc.tickets || (S > 1 && need > sc.ws_bytes)) {
+        if (!sk_cluster && (!sc.tickets || (S > 1 && need > sc.ws_bytes))) {
             snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: split-K scratch missing or too small (%zu B needed): call gemm_tc_prepare()", need);
             return -1;
         }
@@ -611,6 +650,7 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
         SkParams sp;
         sp.M = M; sp.N = N; sp.K = K; sp.nsplit = A_lo ? 2 : 1; sp.S = S; sp.kb_per = kb_per;
         sp.ws = sc.ws; sp.tickets = sc.tickets; sp.epi = epi;
+        sp.cluster = sk_cluster && S > 1;
         if (A_lo && A_lo != A_hi + (size_t)M * K) {
             snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: lo plane must follow the hi plane (lo = hi + M*K)");
             return -1;
@@ -628,9 +668,9 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
             if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(3d) failed (%d) M=%d K=%d", (int)r, M, K); return -1; }
         }
         dim3 grid(n_tiles, S);
-        if (MP == 64) launch_pdl(gemm_tc_skinny_kernel<64, 6>, grid, SK_THREADS, sk_smem_bytes<64, 6>(), s, mw, ma, sp);
-        else if (MP == 128) launch_pdl(gemm_tc_skinny_kernel<128, 4>, grid, SK_THREADS, sk_smem_bytes<128, 4>(), s, mw, ma, sp);
-        else launch_pdl(gemm_tc_skinny_kernel<256, 2>, grid, SK_THREADS, sk_smem_bytes<256, 2>(), s, mw, ma, sp);
+        if (MP == 64) launch_pdl_cluster(gemm_tc_skinny_kernel<64, 6>, grid, SK_THREADS, sk_smem_bytes<64, 6>(), s, sp.cluster ? S : 1, mw, ma, sp);
+        else if (MP == 128) launch_pdl_cluster(gemm_tc_skinny_kernel<128, 4>, grid, SK_THREADS, sk_smem_bytes<128, 4>(), s, sp.cluster ? S : 1, mw, ma, sp);
+        else launch_pdl_cluster(gemm_tc_skinny_kernel<256, 2>, grid, SK_THREADS, sk_smem_bytes<256, 2>(), s, sp.cluster ? S : 1, mw, ma, sp);
         cudaError_t le = cudaGetLastError();
         if (le != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc skinny launch: %s", cudaGetErrorString(le)); return -1; }
         return 0;

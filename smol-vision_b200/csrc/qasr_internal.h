@@ -21,16 +21,30 @@ inline bool pdl_enabled() {
     if (on < 0) { const char *e = getenv("QASR_PDL"); on = !(e && e[0] == '0'); }
     return on != 0;
 }
+// cluster_y > 1: thread-block clusters of (1, cluster_y, 1) CTAs (gridDim.y must be a multiple)
 template <class... KA, class... A>
-inline cudaError_t launch_pdl(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A &&...args) {
+inline cudaError_t launch_pdl_cluster(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_y, A &&...args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute at[2];
+    unsigned n = 0;
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        n++;
+    }
+    if (cluster_y > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = 1; at[n].val.clusterDim.y = (unsigned)cluster_y; at[n].val.clusterDim.z = 1;
+        n++;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+template <class... KA, class... A>
+inline cudaError_t launch_pdl(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, A &&...args) {
+    return launch_pdl_cluster(kernel, grid, block, smem, s, 1, std::forward<A>(args)...);
 }
 #endif
 

@@ -234,14 +234,38 @@ __device__ __forceinline__ void att_tile(AttSmem<HD> &sm, int warp, int lane, in
     __syncwarp();
 }
 
-// cooperative load of a K/V tile: rows [t0, t0+nk) of k / v (row stride ld, head column offset col0), K transposed
+// K/V tile = rows [t0, t0+nk) of k / v (row stride ld, head column offset col0).  The 256 threads of the CTA fetch it
+// into registers (att_fetch_tile) and store it to shared memory, K transposed (att_store_tile), as two steps, so the
+// global loads of tile t+1 are in flight while tile t is being consumed: one L2 round trip per tile, off the critical path.
 template <int HD>
-__device__ __forceinline__ void att_load_tile(AttSmem<HD> &sm, const float *k, const float *v, size_t ld, int col0, int t0, int nk) {
+struct AttRegs {
+    static constexpr int N = ATT_KT * (HD / 4) / 256; // float4 per thread per matrix
+    float4 k[N], v[N];
+};
+template <int HD>
+__device__ __forceinline__ void att_fetch_tile(AttRegs<HD> &r, const float *k, const float *v, size_t ld, int col0, int t0, int nk) {
     constexpr int C4 = HD / 4;
-    for (int e = threadIdx.x; e < nk * C4; e += blockDim.x) {
-        const int kk = e / C4, c4 = e - kk * C4;
-        sm.kt[c4][kk] = *reinterpret_cast<const float4 *>(k + (size_t)(t0 + kk) * ld + col0 + c4 * 4);
-        reinterpret_cast<float4 *>(sm.vs[kk])[c4] = *reinterpret_cast<const float4 *>(v + (size_t)(t0 + kk) * ld + col0 + c4 * 4);
+#pragma unroll
+    for (int i = 0; i < AttRegs<HD>::N; i++) {
+        const int e = threadIdx.x + i * 256;
+        if (e < nk * C4) {
+            const int kk = e / C4, c4 = e - kk * C4;
+            r.k[i] = *reinterpret_cast<const float4 *>(k + (size_t)(t0 + kk) * ld + col0 + c4 * 4);
+            r.v[i] = *reinterpret_cast<const float4 *>(v + (size_t)(t0 + kk) * ld + col0 + c4 * 4);
+        }
+    }
+}
+template <int HD>
+__device__ __forceinline__ void att_store_tile(AttSmem<HD> &sm, const AttRegs<HD> &r, int nk) {
+    constexpr int C4 = HD / 4;
+#pragma unroll
+    for (int i = 0; i < AttRegs<HD>::N; i++) {
+        const int e = threadIdx.x + i * 256;
+        if (e < nk * C4) {
+            const int kk = e / C4, c4 = e - kk * C4;
+            sm.kt[c4][kk] = r.k[i];
+            reinterpret_cast<float4 *>(sm.vs[kk])[c4] = r.v[i];
+        }
     }
 }
 
@@ -261,6 +285,9 @@ attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, c
     const int ib = blockIdx.y * 16;
     const int per = n_heads / n_kv_heads; // 2
     const size_t qld = (size_t)n_heads * 128, kld = (size_t)n_kv_heads * 128;
+    const int kmax_cta = min(q_offset + min(ib + 16, P), seq_k); // keys needed by the last position of the CTA
+    AttRegs<128> regs;
+    att_fetch_tile<128>(regs, kc, vc, kld, kvh * 128, 0, min(ATT_KT, kmax_cta));
     for (int e = threadIdx.x; e < 32 * 32; e += 256) { // 32 queries x 32 float4
         const int qi = e >> 5, c4 = e & 31, pos = ib + (qi >> 1), hh = kvh * per + (qi & 1);
         reinterpret_cast<float4 *>(sm.qs[qi])[c4] = pos < P ? *reinterpret_cast<const float4 *>(q + (size_t)pos * qld + hh * 128 + c4 * 4)
@@ -275,12 +302,12 @@ attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, c
         m[j] = -1e30f; l[j] = 0.0f;
         acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
     }
-    const int kmax_cta = min(q_offset + min(ib + 16, P), seq_k); // keys needed by the last position of the CTA
     for (int t0 = 0; t0 < kmax_cta; t0 += ATT_KT) {
         const int nk = min(ATT_KT, kmax_cta - t0);
+        __syncthreads(); // the previous tile has been consumed
+        att_store_tile<128>(sm, regs, nk);
         __syncthreads();
-        att_load_tile<128>(sm, kc, vc, kld, kvh * 128, t0, nk);
-        __syncthreads();
+        if (t0 + ATT_KT < kmax_cta) att_fetch_tile<128>(regs, kc, vc, kld, kvh * 128, t0 + ATT_KT, min(ATT_KT, kmax_cta - t0 - ATT_KT));
         if (t0 < max(max(hi[0], hi[1]), max(hi[2], hi[3]))) att_tile<128>(sm, warp, lane, t0, nk, hi, scale, m, l, acc);
     }
 #pragma unroll
@@ -321,6 +348,8 @@ attn_windowed_kernel(const float *__restrict__ q, const float *__restrict__ k, c
     const int ws = window_starts[w], we = window_starts[w + 1];
     const int ib = ws + blockIdx.z * 32;
     if (ib >= we) return; // whole CTA
+    AttRegs<64> regs;
+    att_fetch_tile<64>(regs, k, v, (size_t)ld, h * 64, ws, min(ATT_KT, we - ws));
     for (int e = threadIdx.x; e < 32 * 16; e += 256) { // 32 queries x 16 float4
         const int qi = e >> 4, c4 = e & 15;
         reinterpret_cast<float4 *>(sm.qs[qi])[c4] = ib + qi < we ? *reinterpret_cast<const float4 *>(q + (size_t)(ib + qi) * ld + h * 64 + c4 * 4)
@@ -336,9 +365,10 @@ attn_windowed_kernel(const float *__restrict__ q, const float *__restrict__ k, c
     }
     for (int t0 = ws; t0 < we; t0 += ATT_KT) {
         const int nk = min(ATT_KT, we - t0);
+        __syncthreads(); // the previous tile has been consumed
+        att_store_tile<64>(sm, regs, nk);
         __syncthreads();
-        att_load_tile<64>(sm, k, v, (size_t)ld, h * 64, t0, nk);
-        __syncthreads();
+        if (t0 + ATT_KT < we) att_fetch_tile<64>(regs, k, v, (size_t)ld, h * 64, t0 + ATT_KT, min(ATT_KT, we - t0 - ATT_KT));
         if (hi[0] > 0) att_tile<64>(sm, warp, lane, t0, nk, hi, scale, m, l, acc);
     }
 #pragma unroll
