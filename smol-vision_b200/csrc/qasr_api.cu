@@ -845,7 +845,10 @@ static int encode_device(qasr_ctx_t *c, const float *d_mel, int frames, int *T_o
     c->launches += 1;
     return 0;
     };
-    CKR(run_cached_graph(c, 1, frames, c->nsplit, enqueue));
+    {
+        PdlScope pdl(T <= 256);
+        CKR(run_cached_graph(c, 1, frames, c->nsplit, enqueue));
+    }
 #undef HI
 #undef LO
     CK(cudaGetLastError());
@@ -915,7 +918,10 @@ static int prefill_device(qasr_ctx_t *c, int P, int kv_len) {
     }
     return 0;
     };
-    CKR(run_cached_graph(c, 2, P, (long long)kv_len * 8 + c->nsplit + ((long long)c->seq << 48), enqueue));
+    {
+        PdlScope pdl(P <= 256);
+        CKR(run_cached_graph(c, 2, P, (long long)kv_len * 8 + c->nsplit + ((long long)c->seq << 48), enqueue));
+    }
     c->kv_fill[c->seq] = kv_len + P;
     CK(cudaGetLastError());
     return 0;

@@ -18,8 +18,8 @@ __global__ void __launch_bounds__(256)
 conv1_kernel(const float *__restrict__ mel, int frames, const float *__restrict__ w /*[480][9]*/,
              const float *__restrict__ b, const int *__restrict__ w0s, const int *__restrict__ mel0s,
              const int *__restrict__ off1, bf16_t *__restrict__ ohi, bf16_t *__restrict__ olo) {
-    pdl_wait();
     pdl_trigger();
+    pdl_wait();
     __shared__ float in_s[3][130]; // [kj][ih+1], zero padded
     __shared__ float w_s[480 * 9];
     __shared__ float b_s[480];
@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(256)
 im2col_stage_kernel(const bf16_t *__restrict__ src, bf16_t *__restrict__ dst, const int *__restrict__ w0s,
                     const int *__restrict__ off_in, const int *__restrict__ off_out, int n_chunks, int stage,
                     int total_out) {
-    pdl_wait();
     pdl_trigger();
+    pdl_wait();
     const int Hin = stage == 2 ? 64 : 32, Hout = Hin / 2;
     const long long n_items = (long long)total_out * 9 * 60;
     for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < n_items;

@@ -127,6 +127,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint64_t *tmem_full_bar = empty_bar + STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
 
+    pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
     const int num_kb = (p.K + TC_BK - 1) / TC_BK;
@@ -149,7 +150,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();    // barriers, tensor-map prefetch and the TMEM allocation above overlapped the previous grid
-    pdl_trigger();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -352,6 +352,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
     int *s_last = reinterpret_cast<int *>(tmem_slot + 1);
 
+    pdl_trigger(); // the next grid of the chain may be scheduled right away (it waits for this one where it must)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, split = blockIdx.y, n0 = tile * 128;
     const int total_kb = (p.K + TC_BK - 1) / TC_BK;
@@ -375,7 +376,6 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     // The weight producer (warp 0) does not wait for the previous grid: weights are constants, so its first STAGES
     // tiles stream from HBM while the previous kernel drains.  Every other warp (activation loads, MMAs that consume
     // them, output stores, split-K scratch) waits, so the grid as a whole still completes after its predecessor.
-    pdl_trigger();
     if (warp != 0) pdl_wait();
 
     if (warp == 0) {
@@ -631,7 +631,7 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
         if (!target_ctas) {
             const char *e = getenv("QASR_GEMM_TARGET_CTAS"), *m = getenv("QASR_GEMM_MIN_KB");
             target_ctas = e ? atoi(e) : 74;
-            min_kb = m ? atoi(m) : 4;
+            min_kb = m ? atoi(m) : 2;
         }
         int S = (target_ctas + n_tiles - 1) / n_tiles; // split K until ~target_ctas CTAs stream weights
         if (S > total_kb / min_kb) S = total_kb / min_kb;

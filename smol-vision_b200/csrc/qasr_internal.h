@@ -10,10 +10,12 @@ typedef uint16_t bf16_t; // raw bf16 bits on the host side / in signatures
 #include <stdlib.h>
 #include <utility>
 // Programmatic dependent launch for the encoder / prefill launch chains (~440 small dependent kernels per utterance):
-// every kernel of a chain starts with pdl_wait() - nothing it reads or writes is touched before the previous grid has
-// completed and flushed - and pdl_trigger(), so the NEXT grid's launch, CTA scheduling and (for the GEMMs) barrier /
-// TMEM set-up overlap this grid instead of following its drain.  Every kernel of a chain must wait, or completion
-// would stop being transitive.  QASR_PDL=0 launches the same kernels with ordinary stream order.
+// every kernel of a chain starts with pdl_trigger() - the NEXT grid may be scheduled as soon as all CTAs of this one
+// are resident, so its launch, CTA placement and (for the GEMMs) barrier / TMEM set-up and first weight tiles overlap
+// the grids before it - and pdl_wait(): nothing it reads or writes is touched before the previous grid has completed
+// and flushed.  Every kernel of a chain must wait, or completion would stop being transitive.  No deadlock: a grid
+// triggers only once all its CTAs are resident, so at any time only the newest launched grid can have CTAs waiting for
+// an SM, and the oldest unfinished grid always runs to completion.  QASR_PDL=0 = ordinary stream order.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 inline bool pdl_enabled() {
@@ -22,13 +24,22 @@ inline bool pdl_enabled() {
     return on != 0;
 }
 // cluster_y > 1: thread-block clusters of (1, cluster_y, 1) CTAs (gridDim.y must be a multiple)
+// Chains are captured per shape; the ones whose GEMMs take the large-tile kernel (more than 256 rows) measured slower
+// with early scheduling (30 s utterance: encoder 3.96 -> 4.23 ms) while the skinny-GEMM chains gain (3.6 s utterance:
+// encoder + prefill 4.67 -> 4.30 ms), so the caller scopes it by row count.
+inline int &pdl_scope() { static thread_local int on = 1; return on; }
+struct PdlScope {
+    int prev;
+    explicit PdlScope(bool on) : prev(pdl_scope()) { pdl_scope() = on; }
+    ~PdlScope() { pdl_scope() = prev; }
+};
 template <class... KA, class... A>
 inline cudaError_t launch_pdl_cluster(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, int cluster_y, A &&...args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute at[2];
     unsigned n = 0;
-    if (pdl_enabled()) {
+    if (pdl_enabled() && pdl_scope()) {
         at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[n].val.programmaticStreamSerializationAllowed = 1;
         n++;

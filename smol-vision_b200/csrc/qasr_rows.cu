@@ -35,8 +35,8 @@ __device__ __forceinline__ float norm_block_sum(float v, float *red) {
 __global__ void __launch_bounds__(NORM_THREADS)
 rmsnorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ gamma, float eps, int H, float *of, bf16_t *ohi,
                     bf16_t *olo) {
-    pdl_wait();
     pdl_trigger();
+    pdl_wait();
     __shared__ float red[NORM_THREADS / 32];
     const size_t base = (size_t)blockIdx.x * H;
     float v[NORM_MAX_PER];
@@ -64,8 +64,8 @@ void launch_rmsnorm(cudaStream_t s, const float *x, const float *gamma, float ep
 __global__ void __launch_bounds__(NORM_THREADS)
 layernorm_rows_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ b, float eps, int H,
                       float *of, bf16_t *ohi, bf16_t *olo) {
-    pdl_wait();
     pdl_trigger();
+    pdl_wait();
     __shared__ float red[NORM_THREADS / 32];
     const size_t base = (size_t)blockIdx.x * H;
     float v[NORM_MAX_PER];
@@ -121,8 +121,8 @@ __global__ void __launch_bounds__(128)
 qk_norm_rope_store_kernel(const float *__restrict__ qkv, const float *__restrict__ qn, const float *__restrict__ kn,
                           const float *__restrict__ rope_cos, const float *__restrict__ rope_sin, int start_pos,
                           float eps, float *__restrict__ q_out, float *__restrict__ kc, float *__restrict__ vc) {
-    pdl_wait();
     pdl_trigger();
+    pdl_wait();
     __shared__ float tmp[128];
     __shared__ float red[4];
     const int p = blockIdx.x, slot = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -277,8 +277,8 @@ __global__ void __launch_bounds__(256)
 attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, const float *__restrict__ vc,
                     int q_offset, int P, int seq_k, int n_heads, int n_kv_heads, float scale, float *of, bf16_t *ohi,
                     bf16_t *olo) {
-    pdl_wait();
     pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(16) uint8_t att_raw[];
     AttSmem<128> &sm = *reinterpret_cast<AttSmem<128> *>(att_raw);
     const int kvh = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -341,8 +341,8 @@ __global__ void __launch_bounds__(256)
 attn_windowed_kernel(const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v, int ld,
                      const int *__restrict__ window_starts, float scale, int out_ld, float *of, bf16_t *ohi,
                      bf16_t *olo) {
-    pdl_wait();
     pdl_trigger();
+    pdl_wait();
     __shared__ AttSmem<64> sm;
     const int h = blockIdx.x, w = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ws = window_starts[w], we = window_starts[w + 1];
@@ -402,8 +402,8 @@ void launch_split_f32(cudaStream_t s, const float *x, size_t n, bf16_t *hi, bf16
 
 // x[m, :] += table[row_idx[m], :]   (per-chunk sinusoidal PE, reference qwen_asr_encoder.c:280-284)
 __global__ void add_rows_kernel(float *x, const float *__restrict__ table, const int *__restrict__ row_idx, int d) {
-    pdl_wait();
     pdl_trigger();
+    pdl_wait();
     const int m = blockIdx.x;
     const float *t = table + (size_t)row_idx[m] * d;
     for (int i = threadIdx.x; i < d; i += blockDim.x) x[(size_t)m * d + i] += t[i];

@@ -61,7 +61,8 @@ grid-barrier kernel.
 
 The f32-activation reference is reproduced by issuing MMA(A_hi, W) and MMA(A_lo, W) per k-block: both are counted as
 tensor work; useful flops (2MNK) are half of that. At the single-utterance shapes of the bench (M = 47/61 rows) the GEMMs
-are weight streams with a fixed ~9 us of launch / prologue / split-K latency each. The epilogue transposes every 32 x 32
+are weight streams at 5-18 us each (split-K partials reduced across a thread-block cluster through distributed shared
+memory; programmatic dependent launch lets the next GEMM's weight tiles stream while the previous kernels finish). The epilogue transposes every 32 x 32
 accumulator block through shared memory so that stores are row-contiguous (thread-per-row stores bounded the medium-M
 GEMMs: 30 s gate/up 80 -> 58 us, 8192 x 8192 x 4096 845 -> 676 us).
 
