@@ -19,7 +19,7 @@ Regenerate: `python tools/update_profiles.py <prefix of the gpurun_out captures>
 
 {b[value]:.1f} x realtime device-timed, {b[e2e][value]:.1f} x end to end through the C ABI with host buffers ({b[ms_per_step]:.1f} ms per utterance:
 mel {b[stage_ms][mel_ms]:.2f} + encoder {b[stage_ms][enc_ms]:.2f} + prefill {b[stage_ms][prefill_ms]:.2f} + decode {b[stage_ms][decode_ms]:.2f} ms); the reference's CPU path on the box's 16 host cores:
-{ref[value]:.2f} x realtime ({ref[ms_per_step]:.0f} ms). Greedy ids identical (`cpu_baseline.ids_match_gpu`). 2 GPUs 252 x, 4 GPUs 495 x, 8 GPUs 1037 x (weak scaling 0.99 of linear).
+{ref[value]:.2f} x realtime ({ref[ms_per_step]:.0f} ms). Greedy ids identical (`cpu_baseline.ids_match_gpu`). 2 GPUs 252 x, 4 GPUs 495 x, 8 GPUs 1037 x (weak scaling 0.99 of linear; measured when one GPU ran 131 x).
 
 ## Decode step, Qwen3-ASR-1.7B (3 458 793 472 algorithmic bytes per step at ~78 cached positions)
 
