@@ -902,18 +902,22 @@ static int prefill_device(qasr_ctx_t *c, int P, int kv_len) {
     const size_t kvd = (size_t)c->kv_heads * c->hd;
     const float scale = 1.0f / sqrtf((float)c->hd);
     note_growth(c, c->ws_pre);
+    // QASR_PREFILL_ABLATE (timing experiments only, results are wrong): bit mask of launches to leave out of a layer -
+    // 1 RMSNorms, 2 q/k-norm+RoPE+KV store, 4 attention, 8 QKV, 16 WO, 32 gate/up, 64 down
+    static int ablate = -1;
+    if (ablate < 0) { const char *e = getenv("QASR_PREFILL_ABLATE"); ablate = e ? atoi(e) : 0; }
     auto enqueue = [&]() -> int {
     for (int l = 0; l < c->dec_layers; l++) {
         const DecLayerW &L = c->dec[l];
         float *kc = c->kv_k + (size_t)l * c->kv_max * kvd, *vc = c->kv_v + (size_t)l * c->kv_max * kvd;
-        launch_rmsnorm(s, x, L.in_norm, 1e-6f, P, H, nullptr, xn_hi, two ? xn_lo : nullptr);
-        CKR(gemm(c, xn_hi, xn_lo, P, H, L.wqkv, 4096, QASR_GEMM_F32, qkv, nullptr, nullptr, nullptr, 4096));
-        launch_qk_norm_rope_store(s, qkv, L.qn, L.kn, c->rope_cos, c->rope_sin, kv_len, P, 1e-6f, q, kc, vc);
-        launch_attn_prefill(s, q, kc, vc, kv_len, P, kv_len + P, c->heads, c->kv_heads, scale, nullptr, at_hi, two ? at_lo : nullptr);
-        CKR(gemm(c, at_hi, at_lo, P, 2048, L.wo, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H));
-        launch_rmsnorm(s, x, L.post_norm, 1e-6f, P, H, nullptr, xn_hi, two ? xn_lo : nullptr);
-        CKR(gemm(c, xn_hi, xn_lo, P, H, L.wgu, 2 * I, QASR_GEMM_SWIGLU_SPLIT, nullptr, ac_hi, ac_lo, nullptr, I));
-        CKR(gemm(c, ac_hi, ac_lo, P, I, L.wdown, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H));
+        if (!(ablate & 1)) launch_rmsnorm(s, x, L.in_norm, 1e-6f, P, H, nullptr, xn_hi, two ? xn_lo : nullptr);
+        if (!(ablate & 8)) CKR(gemm(c, xn_hi, xn_lo, P, H, L.wqkv, 4096, QASR_GEMM_F32, qkv, nullptr, nullptr, nullptr, 4096));
+        if (!(ablate & 2)) launch_qk_norm_rope_store(s, qkv, L.qn, L.kn, c->rope_cos, c->rope_sin, kv_len, P, 1e-6f, q, kc, vc);
+        if (!(ablate & 4)) launch_attn_prefill(s, q, kc, vc, kv_len, P, kv_len + P, c->heads, c->kv_heads, scale, nullptr, at_hi, two ? at_lo : nullptr);
+        if (!(ablate & 16)) CKR(gemm(c, at_hi, at_lo, P, 2048, L.wo, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H));
+        if (!(ablate & 1)) launch_rmsnorm(s, x, L.post_norm, 1e-6f, P, H, nullptr, xn_hi, two ? xn_lo : nullptr);
+        if (!(ablate & 32)) CKR(gemm(c, xn_hi, xn_lo, P, H, L.wgu, 2 * I, QASR_GEMM_SWIGLU_SPLIT, nullptr, ac_hi, ac_lo, nullptr, I));
+        if (!(ablate & 64)) CKR(gemm(c, ac_hi, ac_lo, P, I, L.wdown, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H));
         c->launches += 4;
     }
     return 0;
