@@ -273,6 +273,7 @@ struct SkParams {
     int M, N, K, nsplit, S, kb_per; // S = split-K factor, kb_per = k-blocks per split
     float *ws;                      // [n_tiles][S][MP][128] f32 partials (S > 1)
     unsigned *tickets;              // [n_tiles], zero between launches
+    int fuse_planes;                // 1 (MP <= 128, nsplit == 2): ONE N = 2*MP MMA per k-step over the [hi | lo] planes, two accumulators
     int cluster;                    // 1: the S splits of a tile form one thread-block cluster (1, S, 1) and reduce through DSMEM
     GemmEpilogue epi;
 };
@@ -345,6 +346,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     constexpr uint32_t W_BYTES = 128 * TC_BK * 2;  // 16 KB
     constexpr uint32_t A_BYTES = MP * TC_BK * 2;   // MP x 128 B
     constexpr uint32_t STAGE_BYTES = W_BYTES + 2 * A_BYTES;
+    constexpr int TMEM_COLS = MP <= 128 ? 2 * MP : MP; // room for separate hi / lo accumulators (fuse_planes)
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     uint64_t *empty_bar = full_bar + STAGES;
@@ -366,7 +368,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)MP) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -401,6 +403,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         if (lane == 0) {
             // M (instruction) = 128 weight rows, N (instruction) = MP activation rows
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * MP) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             for (int i = 0; i < num_kb; i++) {
                 const int s = i % STAGES;
                 mbar_wait(&full_bar[s], (i / STAGES) & 1);
@@ -409,13 +412,22 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                 const uint64_t dw = make_sw128_desc(w_addr);
                 const uint64_t dah = make_sw128_desc(w_addr + W_BYTES);
                 const uint64_t dal = make_sw128_desc(w_addr + W_BYTES + A_BYTES);
-#pragma unroll
-                for (int k = 0; k < TC_BK / 16; k++)
-                    tc_mma_bf16(tmem_base, dw + (uint64_t)(k * 2), dah + (uint64_t)(k * 2), idesc, (i | k) != 0);
-                if (p.nsplit == 2) {
+                if (MP <= 128 && p.fuse_planes) {
+                    // the lo plane follows the hi plane in the stage (MP x 128 B each, same swizzle atoms): together they
+                    // are one K-major operand of 2*MP rows, so one MMA reads the weight tile once for both planes;
+                    // columns [0, MP) accumulate W.hi, columns [MP, 2 MP) W.lo, added in the epilogue
 #pragma unroll
                     for (int k = 0; k < TC_BK / 16; k++)
-                        tc_mma_bf16(tmem_base, dw + (uint64_t)(k * 2), dal + (uint64_t)(k * 2), idesc, 1u);
+                        tc_mma_bf16(tmem_base, dw + (uint64_t)(k * 2), dah + (uint64_t)(k * 2), idesc2, (i | k) != 0);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++)
+                        tc_mma_bf16(tmem_base, dw + (uint64_t)(k * 2), dah + (uint64_t)(k * 2), idesc, (i | k) != 0);
+                    if (p.nsplit == 2) {
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; k++)
+                            tc_mma_bf16(tmem_base, dw + (uint64_t)(k * 2), dal + (uint64_t)(k * 2), idesc, 1u);
+                    }
                 }
                 tc_commit(&empty_bar[s]);
             }
@@ -433,6 +445,12 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             if (c0 >= p.M) break; // columns beyond M hold products with zero-filled rows
             uint32_t r[32];
             tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            if (MP <= 128 && p.fuse_planes) {
+                uint32_t r2[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(MP + c0), r2);
+#pragma unroll
+                for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            }
             if (p.S == 1) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) sk_epilogue_store<MP>(p, n, c0 + j, __uint_as_float(r[j]), lane);
@@ -447,7 +465,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)MP) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
     if (p.S == 1) return;
     if (p.cluster) {
@@ -651,6 +669,9 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
         sp.M = M; sp.N = N; sp.K = K; sp.nsplit = A_lo ? 2 : 1; sp.S = S; sp.kb_per = kb_per;
         sp.ws = sc.ws; sp.tickets = sc.tickets; sp.epi = epi;
         sp.cluster = sk_cluster && S > 1;
+        static int sk_fuse = -1;
+        if (sk_fuse < 0) { const char *ev = getenv("QASR_GEMM_SK_FUSE"); sk_fuse = !(ev && ev[0] == '0'); }
+        sp.fuse_planes = sk_fuse && A_lo && MP <= 128;
         if (A_lo && A_lo != A_hi + (size_t)M * K) {
             snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: lo plane must follow the hi plane (lo = hi + M*K)");
             return -1;
