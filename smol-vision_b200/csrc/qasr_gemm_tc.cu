@@ -656,7 +656,7 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
         if (S < 1) S = 1;
         static int sk_cluster = -1;
         if (sk_cluster < 0) { const char *ev = getenv("QASR_GEMM_SK_CLUSTER"); sk_cluster = !(ev && ev[0] == '0'); }
-        if (sk_cluster && S > 8) S = 8; // portable cluster size
+        if (S > 8) S = 8; // portable cluster size (also without clusters, so that QASR_GEMM_SK_CLUSTER only changes where the partials travel)
         const int kb_per = (total_kb + S - 1) / S;
         S = (total_kb + kb_per - 1) / kb_per;
         const size_t need = (size_t)n_tiles * S * MP * 128 * sizeof(float);

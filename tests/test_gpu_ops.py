@@ -151,3 +151,22 @@ def test_conv2d_stem_shape_vs_oracle(gpu06, oracle_lib):
     L.qo_conv2d.argtypes = [f32p, f32p, f32p, f32p] + [C.c_int] * 8
     L.qo_conv2d(ref, x, w, b, 8, 6, 64, 21, 3, 3, 2, 1)
     assert rel_err(gpu06.conv2d(x, w, b, 2, 1), ref) < F32
+
+
+def test_split_k_cluster_reduction_matches_workspace_reduction():
+    """The cluster / distributed-shared-memory split-K reduction adds the partials in the same fixed split order as the
+    global-workspace scheme it replaced (same split factors): bit-identical outputs, and the same
+    outputs with and without programmatic dependent launch (tools/gemm_ab.py prints one digest per shape)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def digests(**env):
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "gemm_ab.py")], capture_output=True, text=True,
+                             env=dict(os.environ, **env), timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return {tuple(l.split()[:3]): l.split()[3] for l in out.stdout.strip().splitlines()}
+
+    cluster, workspace, no_pdl = digests(), digests(QASR_GEMM_SK_CLUSTER="0"), digests(QASR_PDL="0")
+    assert len(cluster) == 9 and cluster == no_pdl
+    for k in cluster:
+        assert cluster[k] == workspace[k], k

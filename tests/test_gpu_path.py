@@ -343,3 +343,14 @@ def test_device_pcm_decode_and_resample_vs_oracle(gpu06, oracle_lib, channels, r
     ids_a = gpu06.transcribe_staged(5)[0].tolist()   # the resampled audio is left staged in HBM
     ids_b = gpu06.transcribe_ids(got, 5)[0].tolist()
     assert ids_a == ids_b
+
+
+def test_encoder_tables_cached_per_length(gpu06, pkg):
+    """The chunk / window tables of the encoder are uploaded once per frame count: alternating lengths must neither reuse
+    stale tables nor change a result."""
+    a, b = pkg.synth_audio(2.07, seed=21), pkg.synth_audio(8.3, seed=22)
+    first = [gpu06.transcribe_ids(x, 8)[0].tolist() for x in (a, a, b, b, a)]
+    assert first[0] == first[1] == first[4] and first[2] == first[3]
+    ea = gpu06.encode(gpu06.mel(a))
+    gpu06.encode(gpu06.mel(b))
+    assert np.array_equal(ea, gpu06.encode(gpu06.mel(a)))
