@@ -9,6 +9,7 @@
 | `r01_stream_ncu_summary.json`, `r01_stream_ncu_full_raw.csv.gz` | `ncu --set full` capture of one decode_stream_kernel launch (16 greedy steps): DRAM traffic, throughput, pipes | command inside the JSON; raw page = `ncu -i … --page raw --csv` |
 | `r01_gemm_tc_ncu_summary.json` | `ncu --set full` of the tcgen05 GEMM (128x256 tiles) at M=8192, K=4096, N=8192 | command inside the JSON |
 | `r01_launches_stream_cfg2.csv.gz`, `.summary.md` | ncu launch list (device time of every kernel) of 2 utterances of the bench workload | `ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/profile_utt.py 1.7b 2` after the same command exited 0 without ncu |
+| `r01_prefill_ablation.txt` | in-graph marginal cost of every launch class of the prefill chain (GEMMs, attention, norms) | `QASR_PREFILL_ABLATE=<mask> python tools/profile_utt.py 1.7b 6` |
 | `r01_stream_phase_breakdown.txt` | clock64 phase stamps of the decode kernel (CTA 0 / last CTA), per-unit trace | `tools/mega_prof.py`, `tools/mega_trace.py` |
 | `r01_stream_microbench.txt` | cluster-16 feasibility, 2-D TMA box streaming rate, all-to-all exchange latency (vs protocol, replicas, CTA count), tuning sweeps, 2-GPU lines | `tools/microbench/*.cu`, `tools/sk_sweep.sh`, `tools/sk_variants.sh` |
 | `r01_mega2_ncu_summary.json`, `r01_megakernel_phase_breakdown.txt`, `r01_bench_megakernel_v1.json`, `r01_bench_graph_decode.json`, `r01_launches_graph_decode_cfg2.csv.gz` | earlier decode paths of this round (per-phase kernels in a CUDA graph; grid-barrier megakernels), kept as the comparison | as named |
@@ -59,9 +60,9 @@ grid-barrier kernel.
 | {g[1][shape]} | {g[1][us]:.0f} us | {g[1][achieved]:.0f} TFLOP/s (hi+lo MMAs) | {g[1][frac]:.2f} of the measured bf16 peak ({g[1][peak]:.0f}, burst) |
 | {g[2][shape]} (128x256 tiles) | {g[2][us]:.0f} us | {g[2][achieved]:.0f} TFLOP/s (hi+lo MMAs) | {g[2][frac]:.2f} of the measured bf16 peak; ncu: {gemm_us:.0f} us, tensor pipe {gemm_pipe:.1f} % |
 
-The f32-activation reference is reproduced by issuing MMA(A_hi, W) and MMA(A_lo, W) per k-block: both are counted as
-tensor work; useful flops (2MNK) are half of that. At the single-utterance shapes of the bench (M = 47/61 rows) the GEMMs
-are weight streams at 5-18 us each (split-K partials reduced across a thread-block cluster through distributed shared
+The f32-activation reference is reproduced by issuing MMA(A_hi, W) and MMA(A_lo, W) per k-block (one MMA over the
+[hi | lo] planes in the skinny kernel): both are counted as tensor work; useful flops (2MNK) are half of that. At the single-utterance shapes of the bench (M = 47/61 rows) the GEMMs
+are weight streams at 5-21 us each (split-K partials reduced across a thread-block cluster through distributed shared
 memory; programmatic dependent launch lets the next GEMM's weight tiles stream while the previous kernels finish). The epilogue transposes every 32 x 32
 accumulator block through shared memory so that stores are row-contiguous (thread-per-row stores bounded the medium-M
 GEMMs: 30 s gate/up 80 -> 58 us, 8192 x 8192 x 4096 845 -> 676 us).
