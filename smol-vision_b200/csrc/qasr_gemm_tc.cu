@@ -631,6 +631,39 @@ int tc_encode_map(void *out_map64, const bf16_t *ptr, int rows, int K, int box_c
     return 0;
 }
 
+// Skinny path (M <= 256): activation columns MP, weight tiles of 128 rows, split factor S (<= 8 = the portable cluster
+// size, also without clusters so that QASR_GEMM_SK_CLUSTER only changes where the partials travel) and k-blocks per split.
+struct SkPlan { int MP, n_tiles, total_kb, S, kb_per; bool cluster_mode; };
+static SkPlan sk_plan(int M, int K, int N) {
+    static int target_ctas = 0, min_kb = 0, sk_cluster = -1;
+    if (!target_ctas) {
+        const char *e = getenv("QASR_GEMM_TARGET_CTAS"), *m = getenv("QASR_GEMM_MIN_KB"), *ev = getenv("QASR_GEMM_SK_CLUSTER");
+        target_ctas = e && atoi(e) > 0 ? atoi(e) : 74;
+        min_kb = m && atoi(m) > 0 ? atoi(m) : 2;
+        sk_cluster = !(ev && ev[0] == '0');
+    }
+    SkPlan pl;
+    pl.MP = M <= 64 ? 64 : (M <= 128 ? 128 : 256);
+    pl.n_tiles = (N + 127) / 128;
+    pl.total_kb = (K + TC_BK - 1) / TC_BK;
+    int S = (target_ctas + pl.n_tiles - 1) / pl.n_tiles; // split K until ~target_ctas CTAs stream weights
+    if (S > pl.total_kb / min_kb) S = pl.total_kb / min_kb;
+    if (S > 8) S = 8;
+    if (S < 1) S = 1;
+    pl.kb_per = (pl.total_kb + S - 1) / S;
+    pl.S = (pl.total_kb + pl.kb_per - 1) / pl.kb_per; // no empty split
+    pl.cluster_mode = sk_cluster != 0;
+    return pl;
+}
+// host-only debug hook (tests/test_host_logic.py): out = {path (0 skinny, 1 large-tile), MP, n_tiles, total_kb, S, kb_per}
+extern "C" int qasr_debug_gemm_plan(int M, int K, int N, int *out) {
+    if (!out || M <= 0 || K <= 0 || N <= 0) return -1;
+    if (M > 256) { out[0] = 1; out[1] = out[2] = out[3] = out[4] = out[5] = 0; return 0; }
+    const SkPlan pl = sk_plan(M, K, N);
+    out[0] = 0; out[1] = pl.MP; out[2] = pl.n_tiles; out[3] = pl.total_kb; out[4] = pl.S; out[5] = pl.kb_per;
+    return 0;
+}
+
 int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M, int K, const bf16_t *W, int N,
                    const GemmEpilogue &epi) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
@@ -643,22 +676,9 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
         int dev = 0;
         cudaGetDevice(&dev);
         SkScratch &sc = g_sk[dev & 15];
-        const int MP = M <= 64 ? 64 : (M <= 128 ? 128 : 256);
-        const int n_tiles = (N + 127) / 128, total_kb = (K + TC_BK - 1) / TC_BK;
-        static int target_ctas = 0, min_kb = 0;
-        if (!target_ctas) {
-            const char *e = getenv("QASR_GEMM_TARGET_CTAS"), *m = getenv("QASR_GEMM_MIN_KB");
-            target_ctas = e ? atoi(e) : 74;
-            min_kb = m ? atoi(m) : 2;
-        }
-        int S = (target_ctas + n_tiles - 1) / n_tiles; // split K until ~target_ctas CTAs stream weights
-        if (S > total_kb / min_kb) S = total_kb / min_kb;
-        if (S < 1) S = 1;
-        static int sk_cluster = -1;
-        if (sk_cluster < 0) { const char *ev = getenv("QASR_GEMM_SK_CLUSTER"); sk_cluster = !(ev && ev[0] == '0'); }
-        if (S > 8) S = 8; // portable cluster size (also without clusters, so that QASR_GEMM_SK_CLUSTER only changes where the partials travel)
-        const int kb_per = (total_kb + S - 1) / S;
-        S = (total_kb + kb_per - 1) / kb_per;
+        SkPlan pl = sk_plan(M, K, N);
+        const int MP = pl.MP, n_tiles = pl.n_tiles, S = pl.S, kb_per = pl.kb_per;
+        const bool sk_cluster = pl.cluster_mode;
         const size_t need = (size_t)n_tiles * S * MP * 128 * sizeof(float);
         if (!sk_cluster && (!sc.tickets || (S > 1 && need > sc.ws_bytes))) {
             snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: split-K scratch missing or too small (%zu B needed): call gemm_tc_prepare()", need);

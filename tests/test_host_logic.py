@@ -161,3 +161,33 @@ def test_common_prefix_rows_is_bitwise(pkg):
     b[2, 1] = np.nextafter(b[2, 1], np.float32(100))
     assert st.common_prefix_rows(a, b) == 2
     assert st.common_prefix_rows(a[:1], b) == 1
+
+
+def test_skinny_gemm_split_plan_invariants(pkg):
+    """Host-side plan of the weight-streaming GEMM (M <= 256): the split factor fits one portable thread-block cluster,
+    no split is empty, every k-block is covered exactly once, and the production shapes get the measured plans."""
+    import ctypes as C
+    lib = pkg.load_library()
+    plan = lib.qasr_debug_gemm_plan
+    plan.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    plan.restype = C.c_int
+    out = (C.c_int * 6)()
+
+    def get(M, K, N):
+        assert plan(M, K, N, out) == 0
+        return list(out)
+
+    for M in (1, 13, 47, 61, 64, 65, 128, 129, 143, 256):
+        for K in (8, 64, 72, 896, 1024, 2048, 3584, 4320, 6144, 7680):
+            for N in (40, 128, 480, 896, 1024, 2048, 4096, 12288, 151936):
+                path, MP, tiles, kb, S, per = get(M, K, N)
+                assert path == 0 and MP == (64 if M <= 64 else 128 if M <= 128 else 256)
+                assert tiles == -(-N // 128) and kb == -(-K // 64)
+                assert 1 <= S <= 8 and per >= 1
+                assert (S - 1) * per < kb <= S * per          # every split owns at least one k-block, all are covered
+                if kb >= 4:
+                    assert S == 1 or per >= 2                   # at least QASR_GEMM_MIN_KB k-blocks per split
+    assert get(257, 1024, 1024)[0] == 1 and get(6240, 1024, 4096)[0] == 1   # large-tile kernel
+    assert plan(0, 8, 8, out) != 0 and plan(8, 8, 8, None) != 0
+    # bench workload, Qwen3-ASR-1.7B: prefill QKV / WO / gate-up / down and encoder fc2 (tools/gemm_bench.py)
+    assert [get(61, 2048, 4096)[4], get(61, 2048, 2048)[4], get(61, 2048, 12288)[4], get(61, 6144, 2048)[4], get(47, 4096, 1024)[4]] == [3, 5, 1, 5, 8]
