@@ -9,6 +9,7 @@
 | `r01_stream_ncu_summary.json`, `r01_stream_ncu_full_raw.csv.gz` | `ncu --set full` capture of one decode_stream_kernel launch (16 greedy steps): DRAM traffic, throughput, pipes | command inside the JSON; raw page = `ncu -i … --page raw --csv` |
 | `r01_gemm_tc_ncu_summary.json` | `ncu --set full` of the tcgen05 GEMM (128x256 tiles) at M=8192, K=4096, N=8192 | command inside the JSON |
 | `r01_launches_stream_cfg2.csv.gz`, `.summary.md` | ncu launch list (device time of every kernel) of 2 utterances of the bench workload | `ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/profile_utt.py 1.7b 2` after the same command exited 0 without ncu |
+| `r01_gemm_skinny_sweeps.txt` | skinny split-K GEMM at the bench shapes: ticket vs cluster/DSMEM reduction, dependent launch, fused hi/lo MMA, split-target sweeps, dropped variants | `tools/gemm_bench.py` under the environment switches of DESIGN §9 |
 | `r01_prefill_ablation.txt` | in-graph marginal cost of every launch class of the prefill chain (GEMMs, attention, norms) | `QASR_PREFILL_ABLATE=<mask> python tools/profile_utt.py 1.7b 6` |
 | `r01_stream_phase_breakdown.txt` | clock64 phase stamps of the decode kernel (CTA 0 / last CTA), per-unit trace | `tools/mega_prof.py`, `tools/mega_trace.py` |
 | `r01_stream_microbench.txt` | cluster-16 feasibility, 2-D TMA box streaming rate, all-to-all exchange latency (vs protocol, replicas, CTA count), tuning sweeps, 2-GPU lines | `tools/microbench/*.cu`, `tools/sk_sweep.sh`, `tools/sk_variants.sh` |
