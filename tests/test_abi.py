@@ -92,3 +92,30 @@ def test_product_never_touches_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".c", ".h", "Makefile")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not bad.search(txt), f"{f} references the oracle"
+
+
+def test_hot_kernel_resource_budget(pkg):
+    """Static launch budget of the hot kernels, read from the built library: the persistent decode kernel runs 512 threads
+    per CTA, so more than 128 registers per thread cannot launch at all (65536 registers per SM) and spills would sit on
+    the per-unit critical path; the tcgen05 GEMMs keep one elected thread per role and must not spill either."""
+    r = subprocess.run(["cuobjdump", "--dump-resource-usage", pkg.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    usage = {}
+    name = None
+    for line in r.stdout.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+)", line)
+        if m and name:
+            usage[name] = (int(m.group(1)), int(m.group(2)))
+            name = None
+    decode = {k: v for k, v in usage.items() if "decode_stream_kernel" in k}
+    gemm = {k: v for k, v in usage.items() if "gemm_tc_kernel" in k or "gemm_tc_skinny_kernel" in k}
+    assert len(decode) == 3 and len(gemm) == 6, sorted(usage)
+    for k, (reg, stack) in decode.items():
+        assert reg <= 128 and stack <= 16, (k, reg, stack)
+    for k, (reg, stack) in gemm.items():
+        assert reg <= 128 and stack == 0, (k, reg, stack)
