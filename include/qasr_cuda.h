@@ -54,6 +54,24 @@ void qasr_cuda_free(qasr_ctx_t *ctx);
  * qwen_asr_decoder.c:50) and the variant probe detect_config (qwen_asr.c:135-215). */
 int qasr_cuda_load_dir(qasr_ctx_t *ctx, const char *model_dir);
 
+/* The same one-time upload from tensors the caller already holds in host memory (its own mmap of the checkpoint):
+ * exactly what the reference's loaders are handed - qwen_encoder_load / qwen_decoder_load receive a
+ * multi_safetensors_t (reference qwen_asr.c:125-128,243,251; qwen_asr_safetensors.h:24-49) - so the host shim can
+ * forward {name, data, dtype, shape} per tensor and qwen_asr.c needs no edit.  Tensor names are the checkpoint's
+ * ("thinker.audio_tower...", "thinker.model..."); tensors the path does not use are ignored.  The data is copied to
+ * HBM before the call returns. */
+#define QASR_DTYPE_F32 0  /* same numbering as the reference's safetensor_dtype_t, qwen_asr_safetensors.h:15-23 */
+#define QASR_DTYPE_F16 1
+#define QASR_DTYPE_BF16 2
+typedef struct {
+    const char *name;
+    const void *data;
+    int dtype;            /* QASR_DTYPE_* */
+    int ndim;
+    const int64_t *shape; /* [ndim] */
+} qasr_tensor_t;
+int qasr_cuda_upload_tensors(qasr_ctx_t *ctx, const qasr_tensor_t *tensors, int count);
+
 /* out[12] = enc_d_model, enc_layers, enc_heads, enc_ffn_dim, enc_output_dim, dec_hidden,
  * dec_layers, dec_heads, dec_kv_heads, dec_head_dim, dec_intermediate, vocab_size
  * (reference qwen_config_t, qwen_asr.h:46-76). */

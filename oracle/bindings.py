@@ -37,8 +37,16 @@ def ref_lib_path():
     return None
 
 
+def shim_lib_path():
+    """oracle/_ref/libqasr_ref_cuda.so: the unmodified reference host code linked against
+    shim/qwen_asr_cuda_shim.c + libqasr_cuda.so (the drop-in check), or None when it was not built."""
+    p = os.path.join(HERE, "_ref", "libqasr_ref_cuda.so")
+    return p if os.path.exists(p) else None
+
+
 class RefLib:
-    """The reference's own CPU implementation (kind = "reference")."""
+    """The reference's own CPU implementation (kind = "reference").  With path=shim_lib_path() the same
+    harness drives the reference's host code on top of the B200 path instead."""
 
     def __init__(self, path=None):
         path = path or ref_lib_path()
@@ -68,11 +76,24 @@ class RefLib:
         L.ref_read_kv.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, f32p]
         L.ref_transcribe_ids.restype = C.c_int
         L.ref_transcribe_ids.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int, i32p, f64p, C.POINTER(C.c_int)]
+        L.ref_transcribe_text.restype = C.c_void_p
+        L.ref_transcribe_text.argtypes = [C.c_void_p, f32p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_char_p]
         self.ctx = None
         self.cfg = None
 
     def threads_used(self, threads=0):
         return self.lib.ref_threads_used(threads)
+
+    def transcribe_text(self, samples, segment_sec=0.0, search_sec=3.0, stream=False, language=None):
+        """qwen_transcribe_audio (-S segment_sec -W search_sec) or qwen_transcribe_stream, unmodified; returns the text."""
+        samples = np.ascontiguousarray(samples, np.float32)
+        p = self.lib.ref_transcribe_text(self.ctx, samples, len(samples), float(segment_sec), float(search_sec),
+                                         1 if stream else 0, language.encode() if language else None)
+        if not p:
+            return None
+        txt = C.string_at(p).decode("utf-8", errors="replace")
+        self.lib.ref_free_buf(p)
+        return txt
 
     def load(self, model_dir, threads=0):
         self.ctx = self.lib.ref_load(model_dir.encode(), threads)

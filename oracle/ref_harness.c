@@ -13,6 +13,11 @@
  *   qwen_decoder_prefill                  qwen_asr_decoder.c:457
  *   qwen_decoder_forward                  qwen_asr_decoder.c:592
  *   qwen_decoder_forward_logits           qwen_asr_decoder.c:691
+ *   qwen_transcribe_audio / _stream       qwen_asr.c:900,2148 (ref_transcribe_text: sets the public
+ *                                         ctx fields the CLI sets, main.c:262-300, then forwards)
+ *
+ * The same file is linked into oracle/_ref/libqasr_ref_cuda.so, where the reference's encoder /
+ * decoder / mel translation units are replaced by shim/qwen_asr_cuda_shim.c (the drop-in test).
  *
  * ref_transcribe_ids() restates only the *driver* of transcribe_segment
  * (qwen_asr.c:649-818: prompt layout, prefill of total_seq-1 rows, greedy
@@ -152,4 +157,18 @@ int ref_transcribe_ids(void *c, const float *samples, int n_samples, int max_new
     }
     if (out_enc_tokens) *out_enc_tokens = T;
     return n;
+}
+
+/*
+ * The reference's own top-level entry points, unmodified: offline (-S segment_sec, -W search_sec) or
+ * --stream, optional forced language (its tokens + <asr_text> join the prompt, qwen_asr.c:581-603, so
+ * text is emitted from the first token even with random-init weights).  Returns the malloc'd text.
+ */
+char *ref_transcribe_text(void *c, const float *samples, int n_samples, float segment_sec, float search_sec,
+                          int stream, const char *language) {
+    qwen_ctx_t *ctx = (qwen_ctx_t *)c;
+    ctx->segment_sec = segment_sec;
+    ctx->search_sec = search_sec;
+    if (qwen_set_force_language(ctx, language) != 0) return NULL;
+    return stream ? qwen_transcribe_stream(ctx, samples, n_samples) : qwen_transcribe_audio(ctx, samples, n_samples);
 }

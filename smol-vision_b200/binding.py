@@ -32,6 +32,7 @@ SIGNATURES = {
     "qasr_cuda_init": (vp, [ci]),
     "qasr_cuda_free": (None, [vp]),
     "qasr_cuda_load_dir": (ci, [vp, C.c_char_p]),
+    "qasr_cuda_upload_tensors": (ci, [vp, vp, ci]),
     "qasr_cuda_config": (ci, [vp, i32p]),
     "qasr_cuda_set_gemm_split": (ci, [vp, ci]),
     "qasr_cuda_mel_frames": (ci, [ci]),
@@ -288,6 +289,26 @@ class QasrCuda:
         n, reused, rows = ci(0), ci(0), ci(0)
         self._ck(self.lib.qasr_cuda_stream_feed(self.ctx, samples, len(samples), max_new, ids, C.byref(n), C.byref(reused), C.byref(rows)))
         return dict(ids=[int(t) for t in ids[:n.value]], reused=reused.value, rows=rows.value)
+
+    # ---- test hooks of the batched decode kernel (exports outside the public header)
+    def debug_select_seq(self, q):
+        """Route prefill / read_kv / step of this context to the KV cache of sequence q (0..max_batch-1)."""
+        f = self.lib.qasr_debug_select_seq
+        f.restype, f.argtypes = ci, [vp, ci]
+        self._ck(f(self.ctx, int(q)))
+
+    def debug_stream_step(self, embeds, kv_lens, want_logits=True, want_hidden=True):
+        """ONE step of decode_stream_kernel<nseq> on sequences 0..nseq-1: (tokens, logits [nseq, V], hidden [nseq, H])."""
+        f = self.lib.qasr_debug_stream_step
+        f.restype, f.argtypes = ci, [vp, ci, f32p, i32p, i32p, vp, vp]
+        embeds = _f32(embeds)
+        nseq = embeds.shape[0]
+        kv = np.ascontiguousarray(kv_lens, np.int32)
+        toks = np.zeros(nseq, np.int32)
+        logits = np.empty((nseq, self.cfg["vocab_size"]), np.float32) if want_logits else None
+        hidden = np.empty((nseq, self.cfg["dec_hidden"]), np.float32) if want_hidden else None
+        self._ck(f(self.ctx, nseq, embeds, kv, toks, _opt(logits), _opt(hidden)))
+        return toks, logits, hidden
 
     # ---- benchmark plumbing
     def stage_audio(self, samples):

@@ -48,15 +48,15 @@ struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
     bool grew = false;
-    int reserve(size_t bytes) {
+    int reserve(size_t bytes) { // allocate before freeing: a failed grow leaves the old buffer (and the graphs that point into it) intact
         if (bytes <= cap) return 0;
-        grew = true;
+        const size_t want = bytes + bytes / 4;
+        void *np = nullptr;
+        if (cudaMalloc(&np, want) != cudaSuccess) { cudaGetLastError(); return -1; }
         if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 4;
-        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return -1; }
+        p = np;
         cap = want;
+        grew = true;
         return 0;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -114,12 +114,13 @@ struct qasr_ctx {
     cudaGraph_t graph = nullptr;
     int graph_nodes = 0;
     bool use_graph = true;
-    bool use_mega = true; // persistent cooperative decode kernel (QASR_DECODE=graph selects per-phase kernels)
-    bool use_stream = true; // qasr_stream.cu (default); QASR_DECODE=mega2 selects the earlier grid-barrier TMA-box kernel
+    bool use_stream = true; // persistent cooperative decode kernel of qasr_stream.cu (default); QASR_DECODE=graph selects the per-phase kernels
     uint8_t *sk_image = nullptr;           // decode weight image (pre-tiled, per-warp streams)
     unsigned long long *sk_cta_off = nullptr;
     unsigned long long *ll_qkv = nullptr, *ll_att = nullptr, *ll_xwo = nullptr, *ll_act = nullptr, *ll_xdn = nullptr, *ll_head = nullptr;
     unsigned sk_tag = 1;                   // next free exchange tag
+    float *dbg_logits = nullptr, *dbg_hidden = nullptr; // set around one launch by the logits entry points
+    float *hidden_buf = nullptr;           // [QASR_STREAM_MAX_SEQS][H] landing buffer of dbg_hidden
     // prompt around the audio rows used by the whole-segment entry points (reference qwen_asr.c:388-399,685-759): default = no system text, no forced language
     std::vector<int> pre_ids = {151644, 8948, 198, 151645, 198, 151644, 872, 198, 151669};
     std::vector<int> suf_ids = {151670, 151645, 198, 151644, 77091, 198};
@@ -129,14 +130,12 @@ struct qasr_ctx {
     int st_window = 0, st_max_windows = 0;      // samples per window, windows kept
     std::vector<long long> st_prev;             // window indices of the previous chunk's prompt, in order
     bool st_active = false, st_fed = false;     // session open / at least one chunk fed (the KV cache holds its prompt)
-    float *head_val = nullptr;
-    int *head_idx = nullptr;
-    unsigned *grid_bar = nullptr;
+    std::vector<int> st_pre, st_suf;            // prompt tokens the previous chunk was prefilled with
+    long long kv_epoch = 0, st_epoch = -1;      // bumped by every entry point that writes sequence 0's KV cache; value after the previous chunk
     long long *mega_prof = nullptr;
     struct GraphEntry { long long key[4]; cudaGraphExec_t exec; long long n_launch; };
     std::vector<GraphEntry> graph_cache; // captured encoder / prefill launch sequences, keyed by shape
     long long ws_gen = 0;                // bumped whenever a workspace the graphs point into is reallocated
-    void *mega_maps = nullptr; // device array of CUtensorMap (128 B each): decoder matrices in phase order + embedding
     // scratch
     DevBuf ws_samples, ws_meltmp, ws_mel, ws_enc, ws_encout, ws_pre, ws_ids, ws_geom, ws_pcm, ws_mono;
     int *d_gmax = nullptr;
@@ -182,10 +181,9 @@ qasr_ctx_t *qasr_cuda_init(int device) {
     const char *ng = getenv("QASR_NO_GRAPH");
     c->use_graph = !(ng && ng[0] == '1');
     const char *dm = getenv("QASR_DECODE");
-    c->use_mega = !(dm && strcmp(dm, "graph") == 0);
-    c->use_stream = c->use_mega && !(dm && strcmp(dm, "mega2") == 0);
-    if (c->use_mega && (c->use_stream ? stream_init() : mega_init()) != 0) {
-        set_err(QASR_ERR_CUDA, "%s", c->use_stream ? stream_error() : mega_error());
+    c->use_stream = !(dm && strcmp(dm, "graph") == 0);
+    if (c->use_stream && stream_init() != 0) {
+        set_err(QASR_ERR_CUDA, "%s", stream_error());
         cudaStreamDestroy(c->stream);
         delete c;
         return nullptr;
@@ -258,9 +256,10 @@ static const qst_tensor_t *need(qst_dir_t *st, const char *name, int *rc) {
 
 // f32-class tensor (norm weights, biases, conv1): BF16 upcast exactly, or F32 verbatim
 // (reference safetensors_get_f32, qwen_asr_safetensors.c:255-278)
-static float *up_f32(qasr_ctx_t *c, qst_dir_t *st, const char *name, int *rc) {
+static float *up_f32(qasr_ctx_t *c, qst_dir_t *st, const char *name, size_t expect_numel, int *rc) {
     const qst_tensor_t *t = need(st, name, rc);
     if (!t) return nullptr;
+    if (t->numel != expect_numel) { *rc = set_err(QASR_ERR_MODEL, "%s has %zu elements, expected %zu", name, t->numel, expect_numel); return nullptr; }
     std::vector<float> h(t->numel);
     if (t->dtype == QST_BF16) {
         const uint16_t *s = (const uint16_t *)t->data;
@@ -476,23 +475,32 @@ static int ensure_kv(qasr_ctx_t *c, int need_pos, int keep) {
     while (cap < need_pos) cap *= 2;
     const size_t bytes = (size_t)c->dec_layers * cap * kvd * 4;
     CK(cudaStreamSynchronize(c->stream));
-    for (int q = 0; q < QASR_STREAM_MAX_SEQS; q++) {
+    // allocate and fill every new cache first; the pointers and kv_max are committed together only when all succeeded
+    float *nk[QASR_STREAM_MAX_SEQS] = {}, *nv[QASR_STREAM_MAX_SEQS] = {};
+    bool grow[QASR_STREAM_MAX_SEQS] = {};
+    int rc = 0;
+    for (int q = 0; q < QASR_STREAM_MAX_SEQS && rc == 0; q++) {
         if (!c->kv_ks[q] && q != c->seq) continue;
         if (c->kv_ks[q] && cap == c->kv_max) continue;
-        float *nk = nullptr, *nv = nullptr;
-        if (cudaMalloc(&nk, bytes) != cudaSuccess || cudaMalloc(&nv, bytes) != cudaSuccess) {
-            cudaGetLastError(); cudaFree(nk);
-            return set_err(QASR_ERR_NOMEM, "KV cache allocation of %zu bytes failed", 2 * bytes);
+        grow[q] = true;
+        if (cudaMalloc(&nk[q], bytes) != cudaSuccess || cudaMalloc(&nv[q], bytes) != cudaSuccess) {
+            cudaGetLastError();
+            rc = set_err(QASR_ERR_NOMEM, "KV cache allocation of %zu bytes failed", 2 * bytes);
+            break;
         }
         const int rows = q == c->seq ? keep : c->kv_fill[q];
         if (c->kv_ks[q] && rows > 0)
-            for (int l = 0; l < c->dec_layers; l++) {
-                CK(cudaMemcpy(nk + (size_t)l * cap * kvd, c->kv_ks[q] + (size_t)l * c->kv_max * kvd, (size_t)rows * kvd * 4, cudaMemcpyDeviceToDevice));
-                CK(cudaMemcpy(nv + (size_t)l * cap * kvd, c->kv_vs[q] + (size_t)l * c->kv_max * kvd, (size_t)rows * kvd * 4, cudaMemcpyDeviceToDevice));
-            }
-        cudaFree(c->kv_ks[q]); cudaFree(c->kv_vs[q]);
-        c->kv_ks[q] = nk; c->kv_vs[q] = nv;
+            for (int l = 0; l < c->dec_layers && rc == 0; l++)
+                if (cudaMemcpy(nk[q] + (size_t)l * cap * kvd, c->kv_ks[q] + (size_t)l * c->kv_max * kvd, (size_t)rows * kvd * 4, cudaMemcpyDeviceToDevice) != cudaSuccess ||
+                    cudaMemcpy(nv[q] + (size_t)l * cap * kvd, c->kv_vs[q] + (size_t)l * c->kv_max * kvd, (size_t)rows * kvd * 4, cudaMemcpyDeviceToDevice) != cudaSuccess)
+                    rc = set_err(QASR_ERR_CUDA, "KV cache re-stride copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
+    if (rc != 0) { // nothing was committed: the context keeps running on the old caches
+        for (int q = 0; q < QASR_STREAM_MAX_SEQS; q++) { cudaFree(nk[q]); cudaFree(nv[q]); }
+        return rc;
+    }
+    for (int q = 0; q < QASR_STREAM_MAX_SEQS; q++)
+        if (grow[q]) { cudaFree(c->kv_ks[q]); cudaFree(c->kv_vs[q]); c->kv_ks[q] = nk[q]; c->kv_vs[q] = nv[q]; }
     c->kv_max = cap;
     select_seq(c, c->seq);
     c->ws_gen++;
@@ -500,12 +508,8 @@ static int ensure_kv(qasr_ctx_t *c, int need_pos, int keep) {
     return 0;
 }
 
-int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
-    if (!c || !model_dir) return set_err(QASR_ERR_ARG, "null argument");
-    if (c->loaded) return set_err(QASR_ERR_STATE, "context already holds a model");
-    CK(cudaSetDevice(c->device));
-    qst_dir_t *st = qst_open_dir(model_dir);
-    if (!st) return set_err(QASR_ERR_MODEL, "cannot open safetensors in %s", model_dir);
+// Upload every tensor of the checkpoint view `st` (closed here) and build the device-side state.
+static int load_from(qasr_ctx_t *c, qst_dir_t *st) {
     int rc = 0;
     Uploader up;
     if (!up.init(c->stream)) { qst_close(st); up.finish(); return set_err(QASR_ERR_NOMEM, "pinned staging buffers for the checkpoint upload"); }
@@ -523,8 +527,8 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
     const int d = c->d, F = c->F, H = c->H, I = c->I;
     char n0[256], n1[256], n2[256];
 #define E "thinker.audio_tower."
-    c->c1w = up_f32(c, st, E "conv2d1.weight", &rc); c->c1b = up_f32(c, st, E "conv2d1.bias", &rc);
-    c->c2b = up_f32(c, st, E "conv2d2.bias", &rc); c->c3b = up_f32(c, st, E "conv2d3.bias", &rc);
+    c->c1w = up_f32(c, st, E "conv2d1.weight", 480 * 9, &rc); c->c1b = up_f32(c, st, E "conv2d1.bias", 480, &rc);
+    c->c2b = up_f32(c, st, E "conv2d2.bias", 480, &rc); c->c3b = up_f32(c, st, E "conv2d3.bias", 480, &rc);
     for (int cv = 2; cv <= 3 && rc == 0; cv++) { // [oc][ic][ki][kj] -> [oc][(ki*3+kj)*480 + ic]
         snprintf(n0, sizeof n0, E "conv2d%d.weight", cv);
         const uint16_t *h = host_bf16(st, n0, (size_t)480 * 480 * 9, &rc);
@@ -557,21 +561,21 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
         snprintf(n1, sizeof n1, E "layers.%d.self_attn.k_proj.bias", l);
         snprintf(n2, sizeof n2, E "layers.%d.self_attn.v_proj.bias", l);
         L.bqkv = up_f32_cat(c, st, wn, 3, d, &rc);
-#define LN(field, suffix) snprintf(n0, sizeof n0, E "layers.%d." suffix, l); L.field = up_f32(c, st, n0, &rc)
+#define LN(field, suffix, n) snprintf(n0, sizeof n0, E "layers.%d." suffix, l); L.field = up_f32(c, st, n0, (size_t)(n), &rc)
         snprintf(n0, sizeof n0, E "layers.%d.self_attn.out_proj.weight", l); L.wo = up_bf16(c, st, n0, (size_t)d * d, &rc);
-        LN(bo, "self_attn.out_proj.bias");
-        LN(ln1w, "self_attn_layer_norm.weight"); LN(ln1b, "self_attn_layer_norm.bias");
+        LN(bo, "self_attn.out_proj.bias", d);
+        LN(ln1w, "self_attn_layer_norm.weight", d); LN(ln1b, "self_attn_layer_norm.bias", d);
         snprintf(n0, sizeof n0, E "layers.%d.fc1.weight", l); L.fc1 = up_bf16(c, st, n0, (size_t)F * d, &rc);
-        LN(fc1b, "fc1.bias");
+        LN(fc1b, "fc1.bias", F);
         snprintf(n0, sizeof n0, E "layers.%d.fc2.weight", l); L.fc2 = up_bf16(c, st, n0, (size_t)d * F, &rc);
-        LN(fc2b, "fc2.bias");
-        LN(ln2w, "final_layer_norm.weight"); LN(ln2b, "final_layer_norm.bias");
+        LN(fc2b, "fc2.bias", d);
+        LN(ln2w, "final_layer_norm.weight", d); LN(ln2b, "final_layer_norm.bias", d);
 #undef LN
     }
     if (rc == 0) {
-        c->lnpw = up_f32(c, st, E "ln_post.weight", &rc); c->lnpb = up_f32(c, st, E "ln_post.bias", &rc);
-        c->p1w = up_bf16(c, st, E "proj1.weight", (size_t)d * d, &rc); c->p1b = up_f32(c, st, E "proj1.bias", &rc);
-        c->p2w = up_bf16(c, st, E "proj2.weight", (size_t)H * d, &rc); c->p2b = up_f32(c, st, E "proj2.bias", &rc);
+        c->lnpw = up_f32(c, st, E "ln_post.weight", d, &rc); c->lnpb = up_f32(c, st, E "ln_post.bias", d, &rc);
+        c->p1w = up_bf16(c, st, E "proj1.weight", (size_t)d * d, &rc); c->p1b = up_f32(c, st, E "proj1.bias", d, &rc);
+        c->p2w = up_bf16(c, st, E "proj2.weight", (size_t)H * d, &rc); c->p2b = up_f32(c, st, E "proj2.bias", H, &rc);
     }
 #undef E
     if (rc == 0) c->emb = up_bf16(c, st, "thinker.model.embed_tokens.weight", (size_t)c->V * H, &rc);
@@ -586,10 +590,10 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
         L.wqkv = up_bf16_cat(c, st, wn, ne, 3, &rc);
         snprintf(n0, sizeof n0, P "self_attn.o_proj.weight", l); L.wo = up_bf16(c, st, n0, (size_t)H * 2048, &rc);
         snprintf(n0, sizeof n0, P "mlp.down_proj.weight", l); L.wdown = up_bf16(c, st, n0, (size_t)H * I, &rc);
-        snprintf(n0, sizeof n0, P "self_attn.q_norm.weight", l); L.qn = up_f32(c, st, n0, &rc);
-        snprintf(n0, sizeof n0, P "self_attn.k_norm.weight", l); L.kn = up_f32(c, st, n0, &rc);
-        snprintf(n0, sizeof n0, P "input_layernorm.weight", l); L.in_norm = up_f32(c, st, n0, &rc);
-        snprintf(n0, sizeof n0, P "post_attention_layernorm.weight", l); L.post_norm = up_f32(c, st, n0, &rc);
+        snprintf(n0, sizeof n0, P "self_attn.q_norm.weight", l); L.qn = up_f32(c, st, n0, 128, &rc);
+        snprintf(n0, sizeof n0, P "self_attn.k_norm.weight", l); L.kn = up_f32(c, st, n0, 128, &rc);
+        snprintf(n0, sizeof n0, P "input_layernorm.weight", l); L.in_norm = up_f32(c, st, n0, H, &rc);
+        snprintf(n0, sizeof n0, P "post_attention_layernorm.weight", l); L.post_norm = up_f32(c, st, n0, H, &rc);
         // gate/up rows interleaved [g0,u0,g1,u1,...] (reference qwen_asr_decoder.c:140-152) so SwiGLU
         // pairs are adjacent GEMV rows / GEMM columns and fuse into the epilogue
         snprintf(n0, sizeof n0, P "mlp.gate_proj.weight", l);
@@ -602,7 +606,7 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
         if (!L.wgu) { rc = set_err(QASR_ERR_NOMEM, "cudaMalloc failed: gate/up"); break; }
         g_up->put_interleaved(L.wgu, g, u, (size_t)I, (size_t)H * 2);
     }
-    if (rc == 0) c->final_norm = up_f32(c, st, "thinker.model.norm.weight", &rc);
+    if (rc == 0) c->final_norm = up_f32(c, st, "thinker.model.norm.weight", H, &rc);
     const bool up_ok = up.finish(); // every staged copy has landed before the mmap goes away
     g_up = nullptr;
     qst_close(st);
@@ -614,6 +618,7 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
     auto dalloc = [&](size_t bytes) -> void * { void *p = dev_alloc(c, bytes); if (p) cudaMemset(p, 0, bytes); return p; };
     c->n_parts = argmax_num_parts(c->V);
     c->x = (float *)dalloc((size_t)QASR_STREAM_MAX_SEQS * H * 4); c->pending = (float *)dalloc((size_t)H * 4);
+    c->hidden_buf = (float *)dalloc((size_t)QASR_STREAM_MAX_SEQS * H * 4);
     c->qkv = (float *)dalloc(4096 * 4); c->attn = (float *)dalloc(2048 * 4); c->act = (float *)dalloc((size_t)I * 4);
     c->attn_part = (float *)dalloc((size_t)8 * QASR_ATTN_SPLITS * 2 * QASR_ATTN_PART_STRIDE * 4);
     c->logits = (float *)dalloc((size_t)c->V * 4);
@@ -622,25 +627,6 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
     c->d_pos = (int *)dalloc(4 * QASR_STREAM_MAX_SEQS); c->d_done = (int *)dalloc(4); c->d_step = (int *)dalloc(4);
     c->d_tokens = (int *)dalloc((size_t)c->max_steps * QASR_STREAM_MAX_SEQS * 4);
     c->d_gmax = (int *)dalloc(4);
-    c->head_val = (float *)dalloc(1024 * 4); c->head_idx = (int *)dalloc(1024 * 4);
-    c->grid_bar = (unsigned *)dalloc(64 * 4);
-    { // TMA descriptors of the decode weight stream: [layer][QKV, WO, GU, DOWN] + tied embedding
-        const size_t MS = 128; // sizeof(CUtensorMap)
-        std::vector<uint8_t> maps((size_t)(c->dec_layers * 4 + 1) * MS);
-        int mrc = 0;
-        for (int l = 0; l < c->dec_layers; l++) {
-            const DecLayerW &L = c->dec[l];
-            mrc |= tc_encode_map(&maps[(size_t)(l * 4 + 0) * MS], L.wqkv, 4096, H, 64, 16);
-            mrc |= tc_encode_map(&maps[(size_t)(l * 4 + 1) * MS], L.wo, H, 2048, 64, 16);
-            mrc |= tc_encode_map(&maps[(size_t)(l * 4 + 2) * MS], L.wgu, 2 * I, H, 64, 16);
-            mrc |= tc_encode_map(&maps[(size_t)(l * 4 + 3) * MS], L.wdown, H, I, 64, 16);
-        }
-        mrc |= tc_encode_map(&maps[(size_t)(c->dec_layers * 4) * MS], c->emb, c->V, H, 64, 16);
-        if (mrc) return set_err(QASR_ERR_CUDA, "%s", gemm_tc_error());
-        c->mega_maps = dalloc(maps.size());
-        if (!c->mega_maps) return set_err(QASR_ERR_NOMEM, "tensor map allocation failed");
-        CK(cudaMemcpy(c->mega_maps, maps.data(), maps.size(), cudaMemcpyHostToDevice));
-    } // count and generation live in separate 128-byte lines
     if (c->use_stream) { // decode weight image: every decoder matrix + the tied lm_head re-tiled into per-warp streams
         const int G = stream_grid();
         std::vector<unsigned long long> off((size_t)G + 1);
@@ -672,6 +658,41 @@ int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
     CKR(ensure_rope(c, 4096));
     c->loaded = true;
     return 0;
+}
+
+int qasr_cuda_load_dir(qasr_ctx_t *c, const char *model_dir) {
+    if (!c || !model_dir) return set_err(QASR_ERR_ARG, "null argument");
+    if (c->loaded) return set_err(QASR_ERR_STATE, "context already holds a model");
+    CK(cudaSetDevice(c->device));
+    qst_dir_t *st = qst_open_dir(model_dir);
+    if (!st) return set_err(QASR_ERR_MODEL, "cannot open safetensors in %s", model_dir);
+    return load_from(c, st);
+}
+
+// The same upload from tensors the caller already holds in host memory - what the reference's loaders receive
+// (multi_safetensors_t: name, dtype, shape, pointer into its own mmap; qwen_asr_safetensors.h:24-49), so
+// qwen_encoder_load / qwen_decoder_load can forward them without knowing the checkpoint directory.
+int qasr_cuda_upload_tensors(qasr_ctx_t *c, const qasr_tensor_t *tensors, int count) {
+    if (!c || !tensors || count <= 0) return set_err(QASR_ERR_ARG, "null argument");
+    if (c->loaded) return set_err(QASR_ERR_STATE, "context already holds a model");
+    CK(cudaSetDevice(c->device));
+    std::vector<qst_tensor_t> tab((size_t)count);
+    for (int i = 0; i < count; i++) {
+        const qasr_tensor_t &t = tensors[i];
+        qst_tensor_t &o = tab[i];
+        memset(&o, 0, sizeof o);
+        if (!t.name || !t.data || t.ndim < 0 || t.ndim > 8 || (t.ndim > 0 && !t.shape)) return set_err(QASR_ERR_ARG, "tensor %d: null name / data / shape", i);
+        snprintf(o.name, sizeof o.name, "%s", t.name);
+        o.dtype = t.dtype == QASR_DTYPE_F32 ? QST_F32 : t.dtype == QASR_DTYPE_F16 ? QST_F16 : t.dtype == QASR_DTYPE_BF16 ? QST_BF16 : QST_OTHER;
+        o.ndim = t.ndim;
+        o.numel = 1;
+        for (int k = 0; k < t.ndim; k++) { if (t.shape[k] < 0) return set_err(QASR_ERR_ARG, "tensor %s: negative extent", t.name); o.shape[k] = t.shape[k]; o.numel *= (size_t)t.shape[k]; }
+        o.data = t.data;
+        o.nbytes = o.numel * qst_elem_size(o.dtype);
+    }
+    qst_dir_t *st = qst_from_table(tab.data(), count);
+    if (!st) return set_err(QASR_ERR_NOMEM, "tensor table");
+    return load_from(c, st);
 }
 
 // Launch sequences of the encoder / prefill are captured once per shape into a CUDA graph and replayed:
@@ -939,6 +960,7 @@ static int reserve_prefill(qasr_ctx_t *c, int P) {
 }
 
 int qasr_cuda_prefill_embeds(qasr_ctx_t *c, const float *embeds, int seq_len, int kv_len) {
+    if (c) c->kv_epoch++;
     if (!c || !embeds) return set_err(QASR_ERR_ARG, "null argument");
     if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
     if (seq_len <= 0) return 0;
@@ -973,6 +995,7 @@ static int prefill_prompt_device(qasr_ctx_t *c, const int *pre, int n_pre, int n
 }
 
 int qasr_cuda_prefill_prompt(qasr_ctx_t *c, const int *pre_ids, int n_pre, int n_audio, const int *suf_ids, int n_suf, int kv_len) {
+    if (c) c->kv_epoch++;
     if (!c || (n_pre > 0 && !pre_ids) || (n_suf > 0 && !suf_ids)) return set_err(QASR_ERR_ARG, "null argument");
     if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
     if (n_pre < 0 || n_audio < 0 || n_suf < 0 || kv_len < 0) return set_err(QASR_ERR_ARG, "negative count");
@@ -1022,7 +1045,7 @@ static int ensure_graph(qasr_ctx_t *c) {
 static int enqueue_steps(qasr_ctx_t *c, int n, int nseq = 1) {
     if (nseq != 1 && !c->use_stream) return set_err(QASR_ERR_STATE, "batched decode needs the stream kernel (unset QASR_DECODE)");
     if (c->use_stream) { // one persistent cooperative launch runs all n steps (stops itself after an EOS token)
-        StreamParams p;
+        StreamParams p = {};
         p.image = c->sk_image; p.cta_off = c->sk_cta_off;
         p.n_layers = c->dec_layers; p.H = c->H; p.I = c->I; p.V = c->V; p.n_steps = n; p.eps = 1e-6f;
         p.emb = c->emb; p.final_norm = c->final_norm;
@@ -1052,31 +1075,8 @@ static int enqueue_steps(qasr_ctx_t *c, int n, int nseq = 1) {
         { const char *tc = getenv("QASR_MEGA_TRACE_CTA"); p.trace_cta = tc ? atoi(tc) : 0; }
         { const char *e = getenv("QASR_SK_L2AHEAD"); p.l2_ahead_units = e ? atoi(e) : 8; }
         { const char *e = getenv("QASR_SK_L2ISSUE"); p.l2_issue = e ? atoi(e) : 2; }
+        p.dbg_logits = c->dbg_logits; p.dbg_hidden = c->dbg_hidden; // test hooks, NULL outside qasr_cuda_step_logits / qasr_debug_stream_step
         if (launch_decode_stream(c->stream, p) != 0) return set_err(QASR_ERR_CUDA, "%s", stream_error());
-        c->launches += 1;
-        return 0;
-    }
-    if (c->use_mega) { // earlier kernel of this round (QASR_DECODE=mega2): 2-D TMA boxes + grid barriers
-        if (c->dec_layers > 28) return set_err(QASR_ERR_ARG, "decode megakernel supports up to 28 decoder layers");
-        MegaParams p;
-        p.maps = (const CUtensorMap_st *)c->mega_maps;
-        for (int l = 0; l < c->dec_layers; l++) {
-            const DecLayerW &L = c->dec[l];
-            p.layers[l] = MegaLayer{L.wqkv, L.wo, L.wgu, L.wdown, L.qn, L.kn, L.in_norm, L.post_norm};
-        }
-        p.n_layers = c->dec_layers; p.H = c->H; p.I = c->I; p.V = c->V; p.n_steps = n; p.eps = 1e-6f;
-        p.emb = c->emb; p.final_norm = c->final_norm;
-        p.x = c->x; p.qkv = c->qkv; p.act = c->act; p.attn_part = c->attn_part;
-        p.kv_k = c->kv_k; p.kv_v = c->kv_v; p.kv_layer_stride = (size_t)c->kv_max * c->kv_heads * c->hd;
-        p.rope_cos = c->rope_cos; p.rope_sin = c->rope_sin;
-        p.head_val = c->head_val; p.head_idx = c->head_idx;
-        p.d_pos = c->d_pos; p.d_step = c->d_step; p.d_tokens = c->d_tokens; p.h_tokens = c->dh_tokens;
-        p.bar_count = c->grid_bar; p.bar_gen = c->grid_bar + 32;
-        p.prof = c->mega_prof; p.prof_cap = 4096;
-        { const char *dbg = getenv("QASR_MEGA_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
-        { const char *tc = getenv("QASR_MEGA_TRACE_CTA"); p.trace_cta = tc ? atoi(tc) : 0; }
-        CK(cudaMemsetAsync(c->grid_bar, 0, 4, c->stream)); // arrival counter of the grid barrier
-        if (launch_decode_mega(c->stream, p) != 0) return set_err(QASR_ERR_CUDA, "%s", mega_error());
         c->launches += 1;
         return 0;
     }
@@ -1092,6 +1092,7 @@ static int enqueue_steps(qasr_ctx_t *c, int n, int nseq = 1) {
 }
 
 static int step_common(qasr_ctx_t *c, int kv_len, int *out_token) {
+    if (c) c->kv_epoch++;
     CKR(ensure_kv(c, kv_len + 2, kv_len));
     CKR(ensure_rope(c, kv_len + 2));
     launch_set_state(c->stream, c->d_pos, kv_len, c->d_done, 0, c->d_step, 0);
@@ -1148,7 +1149,11 @@ int qasr_cuda_step_pending(qasr_ctx_t *c, int kv_len, int *out_token) {
     return step_common(c, kv_len, out_token);
 }
 
+// Full logits of one step.  The default route is the SAME kernel the greedy path runs (decode_stream_kernel, one step,
+// with its HEAD phase also storing y * rsqrt(mean x^2 + eps) per vocab row), so every logits-level parity test pins the
+// production kernel; QASR_DECODE=graph takes the per-phase kernels + the lm_head GEMV instead.
 int qasr_cuda_step_logits(qasr_ctx_t *c, const float *embed, int kv_len, float *logits) {
+    if (c) c->kv_epoch++;
     if (!c || !embed || !logits) return set_err(QASR_ERR_ARG, "null argument");
     if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
     if (kv_len < 0) return set_err(QASR_ERR_ARG, "negative kv_len");
@@ -1157,13 +1162,66 @@ int qasr_cuda_step_logits(qasr_ctx_t *c, const float *embed, int kv_len, float *
     CKR(ensure_rope(c, kv_len + 2));
     CK(cudaMemcpyAsync(c->x, embed, (size_t)c->H * 4, cudaMemcpyHostToDevice, c->stream));
     launch_set_state(c->stream, c->d_pos, kv_len, c->d_done, 0, c->d_step, 0);
-    enqueue_layers(c, c->stream);
-    // final RMSNorm fused into the lm_head GEMV (reference qwen_asr_decoder.c:781-782)
-    launch_gemv_bf16(c->stream, c->emb, c->x, c->final_norm, 1e-6f, c->logits, nullptr, nullptr, c->V, c->H, QASR_EPI_STORE, nullptr);
-    c->launches += 28 * 5 + 2;
+    if (c->use_stream) {
+        c->dbg_logits = c->logits;
+        const int rc = enqueue_steps(c, 1);
+        c->dbg_logits = nullptr;
+        CKR(rc);
+        c->launches += 1;
+    } else {
+        enqueue_layers(c, c->stream);
+        // final RMSNorm fused into the lm_head GEMV (reference qwen_asr_decoder.c:781-782)
+        launch_gemv_bf16(c->stream, c->emb, c->x, c->final_norm, 1e-6f, c->logits, nullptr, nullptr, c->V, c->H, QASR_EPI_STORE, nullptr);
+        c->launches += 28 * 5 + 2;
+    }
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(logits, c->logits, (size_t)c->V * 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    c->kv_fill[c->seq] = kv_len + 1;
+    c->x_token = -1;
+    return 0;
+}
+
+// ---- test hooks of the batched decode kernel (not part of the public header; bound by tests only)
+// qasr_debug_select_seq: route the single-sequence entry points (prefill_embeds, read_kv, ...) to KV cache `q`, so a test
+// can fill several sequence caches with different prompts.
+extern "C" int qasr_debug_select_seq(qasr_ctx_t *c, int q) {
+    if (!c || !c->loaded || q < 0 || q >= QASR_STREAM_MAX_SEQS) return set_err(QASR_ERR_ARG, "bad sequence index");
+    CK(cudaSetDevice(c->device));
+    select_seq(c, q);
+    CKR(ensure_kv(c, c->kv_max > 0 ? c->kv_max : 2048, c->kv_fill[q]));
+    return 0;
+}
+// qasr_debug_stream_step: ONE step of decode_stream_kernel<nseq> (nseq = 1, 2, 4) on the caches of sequences 0..nseq-1:
+// embeds [nseq][H] in, greedy tokens [nseq], full logits [nseq][V] and the post-final-norm hidden states [nseq][H] out
+// (reference twin: qwen_decoder_forward_logits, qwen_asr_decoder.c:691-783, called once per sequence).
+extern "C" int qasr_debug_stream_step(qasr_ctx_t *c, int nseq, const float *embeds, const int *kv_lens, int *tokens, float *logits, float *hidden) {
+    if (c) c->kv_epoch++;
+    if (!c || !embeds || !kv_lens) return set_err(QASR_ERR_ARG, "null argument");
+    if (!c->loaded || !c->use_stream) return set_err(QASR_ERR_STATE, "needs a loaded model and the stream decode kernel");
+    if (nseq != 1 && nseq != 2 && nseq != 4) return set_err(QASR_ERR_ARG, "nseq must be 1, 2 or 4");
+    if (nseq > qasr_cuda_max_batch(c)) return set_err(QASR_ERR_ARG, "nseq exceeds qasr_cuda_max_batch");
+    CK(cudaSetDevice(c->device));
+    int cap = 0;
+    for (int q = 0; q < nseq; q++) if (kv_lens[q] + 2 > cap) cap = kv_lens[q] + 2;
+    for (int q = 0; q < nseq; q++) { select_seq(c, q); CKR(ensure_kv(c, cap, kv_lens[q])); }
+    select_seq(c, 0);
+    CKR(ensure_rope(c, cap));
+    float *d_logits = nullptr;
+    if (logits) CK(cudaMalloc(&d_logits, (size_t)nseq * c->V * 4));
+    CK(cudaMemcpyAsync(c->x, embeds, (size_t)nseq * c->H * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_set_state(c->stream, c->d_pos, kv_lens[0], c->d_done, 0, c->d_step, 0);
+    CK(cudaMemcpyAsync(c->d_pos, kv_lens, sizeof(int) * nseq, cudaMemcpyHostToDevice, c->stream));
+    c->dbg_logits = d_logits; c->dbg_hidden = hidden ? c->hidden_buf : nullptr;
+    const int rc = enqueue_steps(c, 1, nseq);
+    c->dbg_logits = nullptr; c->dbg_hidden = nullptr;
+    if (rc == 0 && logits) cudaMemcpyAsync(logits, d_logits, (size_t)nseq * c->V * 4, cudaMemcpyDeviceToHost, c->stream);
+    if (rc == 0 && hidden) cudaMemcpyAsync(hidden, c->hidden_buf, (size_t)nseq * c->H * 4, cudaMemcpyDeviceToHost, c->stream);
+    const cudaError_t se = cudaStreamSynchronize(c->stream);
+    if (d_logits) cudaFree(d_logits);
+    if (rc != 0) return rc;
+    if (se != cudaSuccess) return set_err(QASR_ERR_CUDA, "stream step failed: %s", cudaGetErrorString(se));
+    for (int q = 0; q < nseq; q++) { if (tokens) tokens[q] = c->h_tokens[q]; c->kv_fill[q] = kv_lens[q] + 1; }
     c->x_token = -1;
     return 0;
 }
@@ -1211,6 +1269,7 @@ static int generate_device(qasr_ctx_t *c, int first_token, int kv_len, int max_n
 }
 
 int qasr_cuda_generate(qasr_ctx_t *c, int first_token, int kv_len, int max_new, int *out_ids, int *out_n, int *out_kv_len) {
+    if (c) c->kv_epoch++;
     if (!c || !out_ids || !out_n) return set_err(QASR_ERR_ARG, "null argument");
     if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
     if (kv_len < 0) return set_err(QASR_ERR_ARG, "negative kv_len");
@@ -1221,6 +1280,7 @@ int qasr_cuda_generate(qasr_ctx_t *c, int first_token, int kv_len, int max_new, 
 // Whole offline segment. reference transcribe_segment, qwen_asr.c:649-842
 static int transcribe_impl(qasr_ctx_t *c, const float *samples, int n_samples, int max_new, int *out_ids, int *out_n,
                            double *timings_ms, int *out_enc_tokens) {
+    if (c) c->kv_epoch++;
     const int *PRE = c ? c->pre_ids.data() : nullptr, *SUF = c ? c->suf_ids.data() : nullptr; // qwen_asr.c:388-396 (+ prompt / language tokens)
     const int n_pre = c ? (int)c->pre_ids.size() : 0, n_suf = c ? (int)c->suf_ids.size() : 0;
     if (!c || !out_ids || !out_n) return set_err(QASR_ERR_ARG, "null argument");
@@ -1347,6 +1407,7 @@ static int transcribe_group(qasr_ctx_t *c, const float *const *samples, const in
 
 int qasr_cuda_transcribe_batch(qasr_ctx_t *c, const float *const *samples, const int *n_samples, int count, const int *max_new,
                                int ids_stride, int *out_ids, int *out_n, double *timings_ms) {
+    if (c) c->kv_epoch++;
     if (!c || !samples || !n_samples || !max_new || !out_ids || !out_n || count < 0) return set_err(QASR_ERR_ARG, "null argument");
     if (!c->loaded) return set_err(QASR_ERR_STATE, "no model loaded");
     for (int i = 0; i < count; i++)
@@ -1421,7 +1482,13 @@ int qasr_cuda_stream_feed(qasr_ctx_t *c, const float *samples, int n_samples, in
     // (2) partial tail (re-encoded on every chunk); stays in ws_encout
     int T_tail = 0;
     const int tail_n = n_samples - (int)(n_full * W);
-    if (tail_n >= 400) {
+    if (tail_n > 0 && tail_n < 160) { // the reference's mel returns NULL below one frame and the chunk is skipped (qwen_asr.c:1643-1665)
+        *out_n = 0;
+        if (out_reused) *out_reused = 0;
+        if (out_rows) *out_rows = 0;
+        return 0;
+    }
+    if (tail_n >= 160) {
         int frames = 0;
         CKR(mel_device(c, samples + (size_t)n_full * W, tail_n, &frames));
         CKR(encode_device(c, c->ws_mel.as<float>(), frames, &T_tail));
@@ -1431,7 +1498,15 @@ int qasr_cuda_stream_feed(qasr_ctx_t *c, const float *samples, int n_samples, in
     std::vector<long long> cur;
     int total = n_pre + T_tail + n_suf, reused = n_pre;
     for (long long w = first; w < n_full; w++) { cur.push_back(w); total += c->st_win[w % MW].T; }
-    if (!c->st_fed) reused = 0; // first chunk of the session: the KV cache holds nothing of this prompt yet
+    if (total - n_pre - n_suf <= 0) { // no encoder rows at all: skipped like the reference (qwen_asr.c:1686-1691)
+        *out_n = 0;
+        if (out_reused) *out_reused = 0;
+        if (out_rows) *out_rows = 0;
+        return 0;
+    }
+    // The prefix is reusable only if the cache still holds the previous chunk's rows: same prompt tokens, and no other entry
+    // point wrote sequence 0's KV cache in between (the reference compares the embedding rows themselves, qwen_asr.c:1811-1823).
+    if (!c->st_fed || c->kv_epoch != c->st_epoch || c->st_pre != c->pre_ids || c->st_suf != c->suf_ids) reused = 0;
     else
         for (size_t i = 0; i < cur.size() && i < c->st_prev.size() && cur[i] == c->st_prev[i]; i++) reused += c->st_win[cur[i] % MW].T;
     if (reused > total - 1) reused = total - 1;
@@ -1479,6 +1554,8 @@ int qasr_cuda_stream_feed(qasr_ctx_t *c, const float *samples, int n_samples, in
     CKR(generate_device(c, first_tok, kv0 + 1, max_new, out_ids, out_n, &kv_out));
     c->st_prev = cur;
     c->st_fed = true;
+    c->st_pre = c->pre_ids; c->st_suf = c->suf_ids;
+    c->st_epoch = ++c->kv_epoch;
     if (out_reused) *out_reused = reused;
     if (out_rows) *out_rows = total;
     return 0;

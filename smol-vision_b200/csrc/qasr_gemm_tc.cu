@@ -551,17 +551,24 @@ static constexpr size_t sk_smem_bytes() {
 struct SkScratch { float *ws = nullptr; size_t ws_bytes = 0; unsigned *tickets = nullptr; };
 static SkScratch g_sk[16]; // per device
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the (function, device) pair: the opt-in is repeated for every
+// device a context is created on (bit per device), the driver entry point is resolved once per process.
+static unsigned g_tc_attr_dev = 0;
 int gemm_tc_init(void) {
-    if (g_encode) return 0;
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
-        snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
-        return -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (g_encode && (g_tc_attr_dev >> (dev & 31) & 1u)) return 0;
+    if (!g_encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+            snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled unavailable: %s", cudaGetErrorString(e));
+            return -1;
+        }
+        g_encode = (PFN_encodeTiled)fn;
     }
-    g_encode = (PFN_encodeTiled)fn;
-    e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128>());
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64>());
@@ -573,9 +580,9 @@ int gemm_tc_init(void) {
         e = cudaFuncSetAttribute(gemm_tc_skinny_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk_smem_bytes<256, 2>());
     if (e != cudaSuccess) {
         snprintf(g_tc_err, sizeof g_tc_err, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(e));
-        g_encode = nullptr;
         return -1;
     }
+    g_tc_attr_dev |= 1u << (dev & 31);
     return 0;
 }
 

@@ -91,37 +91,6 @@ void launch_attn_decode(cudaStream_t s, const float *qkv, const float *qn, const
 void launch_set_state(cudaStream_t s, int *d_pos, int pos, int *d_done, int done, int *d_step, int step);
 void launch_embed_gather(cudaStream_t s, const bf16_t *E, const int *d_ids, int n, int H, float *out);
 
-// ---- persistent cooperative decode kernel (qasr_mega.cu)
-struct MegaLayer {
-    const bf16_t *wqkv, *wo, *wgu, *wdown;
-    const float *qn, *kn, *in_norm, *post_norm;
-};
-struct CUtensorMap_st;
-struct MegaParams {
-    const CUtensorMap_st *maps;            // [n_layers*4 + 1] 2-D maps (box 64 cols x 16 rows, 128B swizzle), device memory
-    MegaLayer layers[28];
-    int n_layers, H, I, V, n_steps;
-    float eps;
-    const bf16_t *emb;
-    const float *final_norm;
-    float *x, *qkv, *act, *attn_part;      // [H], [4096], [I], [8][16][2][132]
-    float *kv_k, *kv_v;
-    size_t kv_layer_stride;                // elements between layers of the KV cache
-    const float *rope_cos, *rope_sin;      // [pos][64]
-    float *head_val;                       // [grid] per-CTA argmax winners
-    int *head_idx;
-    int *d_pos, *d_step, *d_tokens;
-    volatile int *h_tokens;                // mapped pinned ring (may be NULL)
-    unsigned *bar_count, *bar_gen;         // grid barrier state (zero-initialised once)
-    long long *prof;                       // optional clock64 stamps [2][prof_cap] (CTA 0, last CTA) or NULL
-    int prof_cap;
-    int debug;                             // bit0: skip grid barriers (timing experiments only)
-    int trace_cta;                         // CTA whose warp 0 writes the per-unit trace (debug bit 6)
-};
-int mega_init(void);
-int launch_decode_mega(cudaStream_t s, const MegaParams &p);
-const char *mega_error(void);
-
 // ---- streaming decode kernel (qasr_stream.cu): pre-tiled weight image + flag-in-data exchanges
 struct StreamParams {
     const uint8_t *image;                  // decode weight image (units of 16x64 bf16 in A-fragment order, per-warp streams)
@@ -146,6 +115,8 @@ struct StreamParams {
     int trace_cta;                         // CTA whose warp 0 writes the per-unit trace (debug bit 6)
     int l2_issue;                          // units prefetched per poll iteration
     int l2_ahead_units;                    // second-level prefetch distance into L2, in 2 KB units per warp (0 = off)
+    float *dbg_logits;                     // test hook (NULL in production): [nseq][V] logits of the LAST step of the launch
+    float *dbg_hidden;                     // test hook (NULL in production): [nseq][H] post-final-norm hidden state
 };
 int stream_init(void);
 int stream_grid(void);

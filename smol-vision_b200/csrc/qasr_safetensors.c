@@ -20,6 +20,8 @@ struct qst_dir {
     int n, cap;
 };
 
+size_t qst_elem_size(int dtype) { return dtype == QST_F32 ? 4 : (dtype == QST_F16 || dtype == QST_BF16) ? 2 : 0; }
+
 static void skip_ws(const char **p, const char *end) {
     while (*p < end && (**p == ' ' || **p == '\n' || **p == '\r' || **p == '\t')) (*p)++;
 }
@@ -82,7 +84,7 @@ static int parse_shard(qst_dir_t *d, const char *path) {
 
     uint64_t hlen;
     memcpy(&hlen, m, 8);
-    if (hlen + 8 > (uint64_t)st.st_size) return -1;
+    if (hlen > (uint64_t)st.st_size - 8) return -1; /* written so a huge hlen cannot wrap */
     const char *p = (const char *)m + 8, *end = p + hlen;
     const unsigned char *data0 = (const unsigned char *)m + 8 + hlen;
 
@@ -142,11 +144,13 @@ static int parse_shard(qst_dir_t *d, const char *path) {
                 skip_value(&p, end);
             }
         }
-        if (o1 < o0 || 8 + hlen + o1 > (uint64_t)st.st_size) return -1;
+        if (o1 < o0 || o1 > (uint64_t)st.st_size - 8 - hlen) return -1;
         t.data = data0 + o0;
         t.nbytes = o1 - o0;
         t.numel = 1;
         for (int i = 0; i < t.ndim; i++) t.numel *= (size_t)t.shape[i];
+        /* a header whose byte range disagrees with shape x dtype would make the upload read past the mmap */
+        if (t.dtype != QST_OTHER && t.nbytes != t.numel * qst_elem_size(t.dtype)) return -1;
         if (d->n == d->cap) {
             d->cap = d->cap ? d->cap * 2 : 1024;
             d->tensors = (qst_tensor_t *)realloc(d->tensors, (size_t)d->cap * sizeof(qst_tensor_t));
@@ -162,6 +166,20 @@ static int cmp_name(const void *a, const void *b) {
 }
 
 static int cmp_path(const void *a, const void *b) { return strcmp(*(char *const *)a, *(char *const *)b); }
+
+/* A directory view over tensors the caller already holds in memory (the reference's own mmap): nothing is mapped or
+ * copied here, the entries are sorted by name for qst_find. */
+qst_dir_t *qst_from_table(const qst_tensor_t *tensors, int n) {
+    if (!tensors || n <= 0) return NULL;
+    qst_dir_t *d = (qst_dir_t *)calloc(1, sizeof(qst_dir_t));
+    if (!d) return NULL;
+    d->tensors = (qst_tensor_t *)malloc((size_t)n * sizeof(qst_tensor_t));
+    if (!d->tensors) { free(d); return NULL; }
+    memcpy(d->tensors, tensors, (size_t)n * sizeof(qst_tensor_t));
+    d->n = d->cap = n;
+    qsort(d->tensors, (size_t)d->n, sizeof(qst_tensor_t), cmp_name);
+    return d;
+}
 
 qst_dir_t *qst_open_dir(const char *model_dir) {
     DIR *dir = opendir(model_dir);

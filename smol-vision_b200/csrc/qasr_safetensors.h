@@ -31,6 +31,9 @@ typedef struct {
 typedef struct qst_dir qst_dir_t;
 
 qst_dir_t *qst_open_dir(const char *model_dir);
+/* view over caller-held tensors (entries copied, data not); close with qst_close */
+qst_dir_t *qst_from_table(const qst_tensor_t *tensors, int n);
+size_t qst_elem_size(int dtype);
 void qst_close(qst_dir_t *d);
 const qst_tensor_t *qst_find(const qst_dir_t *d, const char *name);
 int qst_count(const qst_dir_t *d);

@@ -803,7 +803,13 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
         stage_norm(p.ll_xdn, htag - 1, g_fin); // argmax is invariant under the positive RMSNorm scale: not applied
         float bv = -1e30f;
         int bi = 0x7fffffff;
-        run_phase(p.V, H, [&](int s, int row, int r, auto &&rowsum) { const float y = rowsum(r); if (sk_better(y, row, bv, bi)) { bv = y; bi = row; } });
+        if (p.dbg_hidden && b == 0) // test hook: the post-final-norm hidden state of this step (reference qwen_asr_decoder.c:683,781)
+            for (int e = tid; e < NSEQ * H; e += SK_THREADS) p.dbg_hidden[e] = sm_x[e] * norm_scale(e / H) * __ldg(p.final_norm + (e % H));
+        run_phase(p.V, H, [&](int s, int row, int r, auto &&rowsum) {
+            const float y = rowsum(r);
+            if (p.dbg_logits) p.dbg_logits[(size_t)s * p.V + row] = y * norm_scale(s); // test hook: full logits of the kernel the product runs
+            if (sk_better(y, row, bv, bi)) { bv = y; bi = row; }
+        });
         // epilogue thread t holds the winner of sequence t / CH_ROWS over rows == t (mod CH_ROWS): reduce per sequence
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -891,7 +897,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
 // ---- host side ---------------------------------------------------------------------------------
 static char g_sk_err[256] = "";
 const char *stream_error(void) { return g_sk_err; }
-static int g_sk_grid = 0;
+static int g_sk_grid_dev[32] = {}; // CTAs of the decode kernel per device (0 = not initialised there): the shared-memory opt-in belongs to the (function, device) pair
 
 template <int NSEQ, int SLOTS>
 static cudaError_t sk_prepare_variant(int *per_sm, int kmax, int hmax) {
@@ -902,9 +908,9 @@ static cudaError_t sk_prepare_variant(int *per_sm, int kmax, int hmax) {
 }
 
 int stream_init(void) {
-    if (g_sk_grid) return 0;
     int dev = 0, sms = 0, coop = 0, per_sm = 0;
     cudaGetDevice(&dev);
+    if (g_sk_grid_dev[dev & 31]) return 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     cudaError_t e = sk_prepare_variant<1, 5>(&per_sm, SK_MAX_K, SK_MAX_H);
@@ -916,11 +922,23 @@ int stream_init(void) {
         cudaGetLastError();
         return -1;
     }
-    g_sk_grid = sms;
-    { const char *e = getenv("QASR_SK_GRID"); if (e && atoi(e) >= 16 && atoi(e) <= sms) g_sk_grid = atoi(e); } // fewer CTAs = cheaper exchanges, less streaming headroom
+    int grid = sms;
+    // fewer CTAs = cheaper exchanges, less streaming headroom.  At least 16 CTAs per sequence: the attention roles are
+    // (sequence, head, split) CTAs and S = min(S, G / (16 * NSEQ)) must stay >= 1.
+    { const char *e = getenv("QASR_SK_GRID"); if (e && atoi(e) >= 16 * QASR_STREAM_MAX_SEQS && atoi(e) <= sms) grid = atoi(e); }
+    if (grid < 16 * QASR_STREAM_MAX_SEQS) {
+        snprintf(g_sk_err, sizeof g_sk_err, "decode stream kernel needs at least %d SMs (device has %d)", 16 * QASR_STREAM_MAX_SEQS, sms);
+        return -1;
+    }
+    g_sk_grid_dev[dev & 31] = grid;
     return 0;
 }
-int stream_grid(void) { return stream_init() == 0 ? g_sk_grid : 0; }
+int stream_grid(void) {
+    if (stream_init() != 0) return 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return g_sk_grid_dev[dev & 31];
+}
 
 static bool sk_dims_ok(int L, int H, int I, int V) {
     return L >= 1 && L <= 28 && (H == 1024 || H == 2048) && I % 1024 == 0 && I <= SK_MAX_K && V % 16 == 0;
@@ -929,7 +947,7 @@ static bool sk_dims_ok(int L, int H, int I, int V) {
 // Size of the image and the per-CTA byte offsets (host array of grid+1 entries).
 size_t stream_image_layout(int L, int H, int I, int V, unsigned long long *cta_off_host) {
     if (stream_init() != 0 || !sk_dims_ok(L, H, I, V)) return 0;
-    SkDims d{L, H, I, V, g_sk_grid};
+    SkDims d{L, H, I, V, stream_grid()};
     u64 off = 0;
     for (int b = 0; b < d.G; b++) {
         cta_off_host[b] = off;
@@ -948,7 +966,7 @@ int stream_build_image(cudaStream_t s, int L, int H, int I, int V, const bf16_t 
     RetileArgs a;
     for (int i = 0; i < 4 * L; i++) a.src[i] = layer_mats[i];
     a.src[4 * L] = emb;
-    SkDims d{L, H, I, V, g_sk_grid};
+    SkDims d{L, H, I, V, stream_grid()};
     sk_retile_kernel<<<dim3(d.G, 4 * L + 1), SK_THREADS, 0, s>>>(a, d, d_cta_off, image);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_sk_err, sizeof g_sk_err, "re-tile launch: %s", cudaGetErrorString(e)); return -1; }
@@ -966,14 +984,15 @@ int launch_decode_stream(cudaStream_t s, const StreamParams &p) {
         return -1;
     }
     void *args[] = {(void *)&p};
+    const int grid = stream_grid();
     const int kmax = p.I > 2048 ? p.I : 2048;
     cudaError_t e;
     if (p.nseq == 1)
-        e = cudaLaunchCooperativeKernel((const void *)decode_stream_kernel<1, 5>, dim3(g_sk_grid), dim3(SK_THREADS), args, SkLayout<1, 5>::total(kmax, p.H), s);
+        e = cudaLaunchCooperativeKernel((const void *)decode_stream_kernel<1, 5>, dim3(grid), dim3(SK_THREADS), args, SkLayout<1, 5>::total(kmax, p.H), s);
     else if (p.nseq == 2)
-        e = cudaLaunchCooperativeKernel((const void *)decode_stream_kernel<2, 4>, dim3(g_sk_grid), dim3(SK_THREADS), args, SkLayout<2, 4>::total(kmax, p.H), s);
+        e = cudaLaunchCooperativeKernel((const void *)decode_stream_kernel<2, 4>, dim3(grid), dim3(SK_THREADS), args, SkLayout<2, 4>::total(kmax, p.H), s);
     else
-        e = cudaLaunchCooperativeKernel((const void *)decode_stream_kernel<4, 4>, dim3(g_sk_grid), dim3(SK_THREADS), args, SkLayout<4, 4>::total(kmax, p.H), s);
+        e = cudaLaunchCooperativeKernel((const void *)decode_stream_kernel<4, 4>, dim3(grid), dim3(SK_THREADS), args, SkLayout<4, 4>::total(kmax, p.H), s);
     if (e != cudaSuccess) {
         snprintf(g_sk_err, sizeof g_sk_err, "decode stream kernel launch: %s", cudaGetErrorString(e));
         return -1;

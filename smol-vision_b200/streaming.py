@@ -49,7 +49,7 @@ class StreamSession:
 
     def _encode_span(self, span):
         """mel on the span alone (dynamic max of that span), then the encoder (stream_encode_span :1122-1126)."""
-        if len(span) < 400:  # fewer than one STFT frame: nothing to encode
+        if len(span) < 160:  # fewer than one frame: the reference's mel returns NULL (qwen_asr_audio.c:313-317)
             return None
         mel = self.eng.mel(np.ascontiguousarray(span, np.float32))
         if mel is None or mel.shape[1] == 0:
@@ -69,9 +69,14 @@ class StreamSession:
         parts = [self.pre]
         for w in range(max(0, n_full - self.max_windows), n_full):
             parts.append(self.win_rows[w])
+        tail_n = len(samples) - n_full * self.window
+        if 0 < tail_n < 160:  # the reference skips the chunk when the partial span cannot be encoded (qwen_asr.c:1643-1665)
+            return dict(ids=[], reused=0, prefilled=0, rows=0, new_windows=new_windows)
         tail = self._encode_span(samples[n_full * self.window:])
         if tail is not None:
             parts.append(tail)
+        if len(parts) == 1:   # no encoder rows at all: skipped as well (qwen_asr.c:1686-1691)
+            return dict(ids=[], reused=0, prefilled=0, rows=0, new_windows=new_windows)
         parts.append(self.suf)
         embeds = np.ascontiguousarray(np.concatenate(parts, axis=0), np.float32)
         total = len(embeds)
