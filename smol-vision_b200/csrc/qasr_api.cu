@@ -2,8 +2,7 @@
 // upload of the safetensors checkpoint, the level-1 entry points (mel / encoder / prefill /
 // decode step / greedy loop) and their CUDA-graph plumbing.  No CPU fallback anywhere: every
 // path either launches sm_100a kernels or fails with an error code.
-#include "../../include/qasr_cuda.h"
-#include "qasr_internal.h"
+#include "qasr_ctx.h"
 #include "qasr_safetensors.h"
 
 #include <math.h>
@@ -22,7 +21,7 @@
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_err[512] = "";
-static int set_err(int code, const char *fmt, ...) {
+int set_err(int code, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof g_err, fmt, ap);
@@ -30,128 +29,6 @@ static int set_err(int code, const char *fmt, ...) {
     return code;
 }
 const char *qasr_cuda_last_error(void) { return g_err; }
-
-#define CK(call)                                                                                         \
-    do {                                                                                                 \
-        cudaError_t e__ = (call);                                                                        \
-        if (e__ != cudaSuccess)                                                                          \
-            return set_err(QASR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
-    } while (0)
-#define CKR(expr)              \
-    do {                       \
-        int r__ = (expr);      \
-        if (r__ != 0) return r__; \
-    } while (0)
-
-// ------------------------------------------------------------------ context
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    bool grew = false;
-    int reserve(size_t bytes) { // allocate before freeing: a failed grow leaves the old buffer (and the graphs that point into it) intact
-        if (bytes <= cap) return 0;
-        const size_t want = bytes + bytes / 4;
-        void *np = nullptr;
-        if (cudaMalloc(&np, want) != cudaSuccess) { cudaGetLastError(); return -1; }
-        if (p) cudaFree(p);
-        p = np;
-        cap = want;
-        grew = true;
-        return 0;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
-};
-
-struct EncLayerW {
-    bf16_t *wqkv, *wo, *fc1, *fc2;
-    float *bqkv, *bo, *fc1b, *fc2b, *ln1w, *ln1b, *ln2w, *ln2b;
-};
-struct DecLayerW {
-    bf16_t *wqkv, *wo, *wgu, *wdown;
-    float *qn, *kn, *in_norm, *post_norm;
-};
-
-struct qasr_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool loaded = false;
-    int nsplit = 2;
-    // config (reference qwen_config_t)
-    int d = 0, enc_layers = 0, enc_heads = 0, F = 0, H = 0, dec_layers = 0, heads = 16, kv_heads = 8, hd = 128, I = 0,
-        V = 151936;
-    // weights
-    std::vector<void *> owned; // every cudaMalloc'd weight block
-    float *c1w = nullptr, *c1b = nullptr, *c2b = nullptr, *c3b = nullptr;
-    bf16_t *c2w = nullptr, *c3w = nullptr, *conv_out = nullptr, *p1w = nullptr, *p2w = nullptr;
-    float *lnpw = nullptr, *lnpb = nullptr, *p1b = nullptr, *p2b = nullptr;
-    EncLayerW enc[32];
-    DecLayerW dec[48];
-    bf16_t *emb = nullptr;
-    float *final_norm = nullptr;
-    size_t weight_bytes = 0;
-    // constant tables
-    float *mel_cos = nullptr, *mel_sin = nullptr, *mel_win = nullptr, *mel_fb = nullptr, *pe = nullptr;
-    float *rope_cos = nullptr, *rope_sin = nullptr;
-    int rope_cap = 0;
-    // KV cache f32 [layers][kv_max][kv_heads*hd]
-    float *kv_k = nullptr, *kv_v = nullptr; // cache of the CURRENT sequence (kv_ks[seq]); seq 0 = the single-sequence API
-    float *kv_ks[QASR_STREAM_MAX_SEQS] = {}, *kv_vs[QASR_STREAM_MAX_SEQS] = {}; // batched decode: one cache per sequence, same capacity
-    int kv_fill[QASR_STREAM_MAX_SEQS] = {};  // valid rows per sequence (what a growth has to preserve)
-    int seq = 0;
-    int kv_max = 0;
-    // decode-step state
-    float *x = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr, *attn_part = nullptr, *logits = nullptr,
-          *pending = nullptr, *part_val = nullptr;
-    int *part_idx = nullptr, *d_pos = nullptr, *d_done = nullptr, *d_step = nullptr, *d_tokens = nullptr;
-    unsigned *counters = nullptr;
-    int *h_tokens = nullptr, *dh_tokens = nullptr; // mapped pinned ring
-    int max_steps = 64;
-    int n_parts = 0;
-    bool has_pending = false;
-    int x_token = -1; // token whose embedding currently sits in x (or -1)
-    cudaGraphExec_t graph_exec = nullptr;
-    cudaGraph_t graph = nullptr;
-    int graph_nodes = 0;
-    bool use_graph = true;
-    bool use_stream = true; // persistent cooperative decode kernel of qasr_stream.cu (default); QASR_DECODE=graph selects the per-phase kernels
-    uint8_t *sk_image = nullptr;           // decode weight image (pre-tiled, per-warp streams)
-    unsigned long long *sk_cta_off = nullptr;
-    unsigned long long *ll_qkv = nullptr, *ll_att = nullptr, *ll_xwo = nullptr, *ll_act = nullptr, *ll_xdn = nullptr, *ll_head = nullptr;
-    unsigned sk_tag = 1;                   // next free exchange tag
-    float *dbg_logits = nullptr, *dbg_hidden = nullptr; // set around one launch by the logits entry points
-    float *hidden_buf = nullptr;           // [QASR_STREAM_MAX_SEQS][H] landing buffer of dbg_hidden
-    // prompt around the audio rows used by the whole-segment entry points (reference qwen_asr.c:388-399,685-759): default = no system text, no forced language
-    std::vector<int> pre_ids = {151644, 8948, 198, 151645, 198, 151644, 872, 198, 151669};
-    std::vector<int> suf_ids = {151670, 151645, 198, 151644, 77091, 198};
-    // streaming session (qasr_cuda_stream_*): encoder rows of the completed windows stay in HBM
-    struct StreamWin { long long index = -1; int T = 0; DevBuf rows; };
-    StreamWin st_win[8];
-    int st_window = 0, st_max_windows = 0;      // samples per window, windows kept
-    std::vector<long long> st_prev;             // window indices of the previous chunk's prompt, in order
-    bool st_active = false, st_fed = false;     // session open / at least one chunk fed (the KV cache holds its prompt)
-    std::vector<int> st_pre, st_suf;            // prompt tokens the previous chunk was prefilled with
-    long long kv_epoch = 0, st_epoch = -1;      // bumped by every entry point that writes sequence 0's KV cache; value after the previous chunk
-    long long *mega_prof = nullptr;
-    struct GraphEntry { long long key[4]; cudaGraphExec_t exec; long long n_launch; };
-    std::vector<GraphEntry> graph_cache; // captured encoder / prefill launch sequences, keyed by shape
-    long long ws_gen = 0;                // bumped whenever a workspace the graphs point into is reallocated
-    // scratch
-    DevBuf ws_samples, ws_meltmp, ws_mel, ws_enc, ws_encout, ws_pre, ws_ids, ws_geom, ws_pcm, ws_mono;
-    int *d_gmax = nullptr;
-    int mel_frames = 0, enc_T = 0;
-    int geom_frames = 0; // frame count whose chunk / window tables sit in ws_geom
-    cudaEvent_t ev[5] = {};
-    cudaEvent_t tev[2] = {};
-    double last_decode_ms = 0.0;
-    double decode_ms_total = 0.0;
-    long long decode_steps_total = 0;
-    int staged_samples = 0;
-    long long launches = 0;
-};
-
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-static void note_growth(qasr_ctx_t *c, DevBuf &b) { if (b.grew) { c->ws_gen++; b.grew = false; } }
 
 // ------------------------------------------------------------------ lifecycle
 int qasr_cuda_device_count(void) {
@@ -212,6 +89,7 @@ void qasr_cuda_free(qasr_ctx_t *c) {
     c->ws_encout.release(); c->ws_pre.release(); c->ws_ids.release(); c->ws_geom.release();
     for (auto &w : c->st_win) w.rows.release();
     c->ws_pcm.release(); c->ws_mono.release();
+    batch_release(c);
     for (int i = 0; i < 5; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; i++) if (c->tev[i]) cudaEventDestroy(c->tev[i]);
     cudaStreamDestroy(c->stream);
@@ -436,7 +314,7 @@ static int build_tables(qasr_ctx_t *c) {
 }
 
 // RoPE cos/sin [pos][64] with the reference's f32 formula (qwen_asr_decoder.c:253-302)
-static int ensure_rope(qasr_ctx_t *c, int need_pos) {
+int ensure_rope(qasr_ctx_t *c, int need_pos) {
     if (need_pos <= c->rope_cap) return 0;
     int cap = c->rope_cap ? c->rope_cap : 4096;
     while (cap < need_pos) cap *= 2;
@@ -626,7 +504,7 @@ static int load_from(qasr_ctx_t *c, qst_dir_t *st) {
     c->counters = (unsigned *)dalloc(8 * 4);
     c->d_pos = (int *)dalloc(4 * QASR_STREAM_MAX_SEQS); c->d_done = (int *)dalloc(4); c->d_step = (int *)dalloc(4);
     c->d_tokens = (int *)dalloc((size_t)c->max_steps * QASR_STREAM_MAX_SEQS * 4);
-    c->d_gmax = (int *)dalloc(4);
+    c->d_gmax = (int *)dalloc(4 * 512); // one slot per unit of a batched front end
     if (c->use_stream) { // decode weight image: every decoder matrix + the tied lm_head re-tiled into per-warp streams
         const int G = stream_grid();
         std::vector<unsigned long long> off((size_t)G + 1);
@@ -695,35 +573,6 @@ int qasr_cuda_upload_tensors(qasr_ctx_t *c, const qasr_tensor_t *tensors, int co
     return load_from(c, st);
 }
 
-// Launch sequences of the encoder / prefill are captured once per shape into a CUDA graph and replayed:
-// at these sizes the ~230 + ~170 launches of one utterance are CPU-launch-bound otherwise (each
-// tensor-core GEMM launch also encodes two TMA descriptors on the host).
-template <class F>
-static int run_cached_graph(qasr_ctx_t *c, long long k0, long long k1, long long k2, F &&enqueue) {
-    if (!c->use_graph) return enqueue();
-    const long long key[4] = {k0, k1, k2, c->ws_gen};
-    for (auto &ge : c->graph_cache)
-        if (!memcmp(ge.key, key, sizeof key)) { CK(cudaGraphLaunch(ge.exec, c->stream)); c->launches += ge.n_launch; return 0; }
-    const long long launches_before = c->launches;
-    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue();
-    cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
-    if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (ce != cudaSuccess) return set_err(QASR_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-    cudaGraphExec_t exec = nullptr;
-    CK(cudaGraphInstantiate(&exec, graph, 0));
-    cudaGraphDestroy(graph);
-    if (c->graph_cache.size() >= 16) { cudaGraphExecDestroy(c->graph_cache.front().exec); c->graph_cache.erase(c->graph_cache.begin()); }
-    qasr_ctx::GraphEntry ge;
-    memcpy(ge.key, key, sizeof key);
-    ge.exec = exec;
-    ge.n_launch = c->launches - launches_before;
-    c->graph_cache.push_back(ge);
-    CK(cudaGraphLaunch(exec, c->stream));
-    return 0;
-}
-
 // ------------------------------------------------------------------ mel
 int qasr_cuda_mel_frames(int n_samples) { return n_samples / 160; }
 
@@ -745,7 +594,7 @@ static int mel_device(qasr_ctx_t *c, const float *samples, int n, int *frames_ou
         return set_err(QASR_ERR_NOMEM, "mel workspace allocation failed");
     if (samples) CK(cudaMemcpyAsync(c->ws_samples.p, samples, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
     launch_mel(c->stream, c->ws_samples.as<float>(), n, frames, c->mel_cos, c->mel_sin, c->mel_win, c->mel_fb,
-               c->ws_meltmp.as<float>(), c->d_gmax, c->ws_mel.as<float>());
+               c->ws_meltmp.as<float>(), c->d_gmax, c->ws_mel.as<float>(), frames, 0);
     c->launches += 3;
     CK(cudaGetLastError());
     c->mel_frames = frames;
@@ -766,7 +615,7 @@ int qasr_cuda_mel(qasr_ctx_t *c, const float *samples, int n_samples, float *mel
 }
 
 // ------------------------------------------------------------------ encoder
-static int gemm(qasr_ctx_t *c, const bf16_t *a_hi, const bf16_t *a_lo, int M, int K, const bf16_t *W, int N, int mode,
+int gemm(qasr_ctx_t *c, const bf16_t *a_hi, const bf16_t *a_lo, int M, int K, const bf16_t *W, int N, int mode,
                 float *of, bf16_t *ohi, bf16_t *olo, const float *bias, int ldo) {
     GemmEpilogue e;
     e.mode = mode; e.out_f32 = of; e.out_hi = ohi; e.out_lo = (c->nsplit == 2) ? olo : nullptr; e.bias = bias; e.ldo = ldo;
@@ -776,36 +625,56 @@ static int gemm(qasr_ctx_t *c, const bf16_t *a_hi, const bf16_t *a_lo, int M, in
     return 0;
 }
 
-// mel (device, [128, frames]) -> encoder output rows in c->ws_encout ([T, H] f32)
-static int encode_device(qasr_ctx_t *c, const float *d_mel, int frames, int *T_out) {
+// mel (device, [128, frames_total]) -> encoder output rows ([T, H] f32).  The mel may hold several independent units side
+// by side along the frame axis (unit_frames[0..n_units)): chunking, per-chunk conv padding, positional rows and the
+// attention windows restart at every unit boundary (reference qwen_asr_encoder.c:188-297 applied per unit), while every
+// GEMM runs over the rows of all units at once.  mel_stride = row stride of d_mel (0: the units' frames fill it exactly).
+// out = NULL writes c->ws_encout.  One unit: the launch chain is captured
+// per frame count in a CUDA graph.
+int encode_units_device(qasr_ctx_t *c, const float *d_mel, int mel_stride, const int *unit_frames, int n_units, float *out, int *T_out) {
     const int d = c->d, F = c->F, H = c->H;
-    const int nc = (frames + 99) / 100;
+    int frames = 0, nc = 0;
+    for (int u = 0; u < n_units; u++) { frames += unit_frames[u]; nc += (unit_frames[u] + 99) / 100; }
     std::vector<int> geom((size_t)nc * 2 + 3 * (nc + 1));
     int *w0 = geom.data(), *m0 = w0 + nc, *o1 = m0 + nc, *o2 = o1 + nc + 1, *o3 = o2 + nc + 1;
     o1[0] = o2[0] = o3[0] = 0;
-    for (int i = 0; i < nc; i++) {
-        const int w = frames - i * 100 < 100 ? frames - i * 100 : 100;
-        const int w1 = (w - 1) / 2 + 1, w2 = (w1 - 1) / 2 + 1, w3 = (w2 - 1) / 2 + 1;
-        w0[i] = w; m0[i] = i * 100;
-        o1[i + 1] = o1[i] + w1 * 64; o2[i + 1] = o2[i] + w2 * 32; o3[i + 1] = o3[i] + w3 * 16;
+    {
+        int i = 0, f0 = 0;
+        for (int u = 0; u < n_units; u++) {
+            for (int s0 = 0; s0 < unit_frames[u]; s0 += 100, i++) {
+                const int w = unit_frames[u] - s0 < 100 ? unit_frames[u] - s0 : 100;
+                const int w1 = (w - 1) / 2 + 1, w2 = (w1 - 1) / 2 + 1, w3 = (w2 - 1) / 2 + 1;
+                w0[i] = w; m0[i] = f0 + s0;
+                o1[i + 1] = o1[i] + w1 * 64; o2[i + 1] = o2[i] + w2 * 32; o3[i + 1] = o3[i] + w3 * 16;
+            }
+            f0 += unit_frames[u];
+        }
     }
     const int tot1 = o1[nc], tot2 = o2[nc], tot3 = o3[nc], T = tot3 / 16;
-    const int nwin = (T + 103) / 104; // 13 * (800/100) tokens per window, reference qwen_asr_encoder.c:291-297
-    std::vector<int> aux((size_t)T + nwin + 1);
-    { // per-token PE row (position restarts in every chunk) and window starts
-        int t = 0;
-        for (int i = 0; i < nc; i++) { const int w3 = (o3[i + 1] - o3[i]) / 16; for (int k = 0; k < w3; k++) aux[t++] = k; }
-        for (int w = 0; w < nwin; w++) aux[T + w] = w * 104;
-        aux[T + nwin] = T;
+    // per-token PE row (position restarts in every chunk) and window starts: 13 * (800/100) = 104 tokens per window, counted
+    // from the first token of each unit (reference qwen_asr_encoder.c:291-297)
+    std::vector<int> aux;
+    aux.reserve((size_t)T + T / 104 + n_units + 2);
+    for (int i = 0; i < nc; i++) { const int w3 = (o3[i + 1] - o3[i]) / 16; for (int k = 0; k < w3; k++) aux.push_back(k); }
+    int nwin = 0;
+    {
+        int t0 = 0;
+        for (int u = 0; u < n_units; u++) {
+            const int Tu = qasr_cuda_encoder_tokens(unit_frames[u]);
+            for (int w = 0; w * 104 < Tu; w++) { aux.push_back(t0 + w * 104); nwin++; }
+            t0 += Tu;
+        }
+        aux.push_back(T);
     }
     if (c->ws_geom.reserve((geom.size() + aux.size()) * 4)) return set_err(QASR_ERR_NOMEM, "geom alloc");
     int *dg = c->ws_geom.as<int>();
-    if (c->geom_frames != frames || c->ws_geom.grew) { // the tables depend on `frames` only: same length, nothing to upload and no host sync
+    const int geom_key = n_units == 1 ? frames : -1; // the tables of a single unit depend on its frame count only: same length, nothing to upload and no host sync
+    if (geom_key < 0 || c->geom_frames != geom_key || c->ws_geom.grew) {
         c->geom_frames = 0;
         CK(cudaMemcpyAsync(dg, geom.data(), geom.size() * 4, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(dg + geom.size(), aux.data(), aux.size() * 4, cudaMemcpyHostToDevice, c->stream));
         CK(cudaStreamSynchronize(c->stream)); // host vectors go out of scope below
-        c->geom_frames = frames;
+        c->geom_frames = geom_key < 0 ? 0 : geom_key;
     }
     ConvGeom g;
     g.n_chunks = nc; g.d_w0 = dg; g.d_mel0 = dg + nc; g.d_off1 = dg + 2 * nc; g.d_off2 = g.d_off1 + nc + 1; g.d_off3 = g.d_off2 + nc + 1;
@@ -820,8 +689,9 @@ static int encode_device(qasr_ctx_t *c, const float *d_mel, int frames, int *T_o
                  o_act3 = carve((size_t)tot3 * 480 * 2 * 2), o_x = carve((size_t)T * d * 4),
                  o_xn = carve((size_t)T * d * 2 * 2), o_qkv = carve((size_t)T * 3 * d * 4),
                  o_att = carve((size_t)T * d * 2 * 2), o_mid = carve((size_t)T * F * 2 * 2);
-    if (c->ws_enc.reserve(off) || c->ws_encout.reserve((size_t)T * H * 4)) return set_err(QASR_ERR_NOMEM, "encoder workspace (%zu bytes)", off);
+    if (c->ws_enc.reserve(off) || (!out && c->ws_encout.reserve((size_t)T * H * 4))) return set_err(QASR_ERR_NOMEM, "encoder workspace (%zu bytes)", off);
     note_growth(c, c->ws_enc); note_growth(c, c->ws_encout); note_growth(c, c->ws_geom); note_growth(c, c->ws_mel);
+    if (!out) out = c->ws_encout.as<float>();
     uint8_t *B = c->ws_enc.as<uint8_t>();
     auto enqueue = [&]() -> int {
 #define HI(o) reinterpret_cast<bf16_t *>(B + (o))
@@ -829,7 +699,7 @@ static int encode_device(qasr_ctx_t *c, const float *d_mel, int frames, int *T_o
     cudaStream_t s = c->stream;
     const bool two = c->nsplit == 2;
     // conv stem, reference qwen_asr_encoder.c:221-276
-    launch_conv1(s, d_mel, frames, c->c1w, c->c1b, g, HI(o_act1), two ? LO(o_act1, (size_t)tot1 * 480) : nullptr);
+    launch_conv1(s, d_mel, mel_stride > 0 ? mel_stride : frames, c->c1w, c->c1b, g, HI(o_act1), two ? LO(o_act1, (size_t)tot1 * 480) : nullptr);
     launch_im2col_stage(s, HI(o_act1), HI(o_col2), g, 2);
     if (two) launch_im2col_stage(s, LO(o_act1, (size_t)tot1 * 480), LO(o_col2, (size_t)tot2 * 4320), g, 2);
     c->launches += two ? 3 : 2;
@@ -862,13 +732,14 @@ static int encode_device(qasr_ctx_t *c, const float *d_mel, int frames, int *T_o
     // tail, reference qwen_asr_encoder.c:350-361
     launch_layernorm(s, x, c->lnpw, c->lnpb, 1e-5f, T, d, nullptr, xn_hi, two ? xn_lo : nullptr);
     CKR(gemm(c, xn_hi, xn_lo, T, d, c->p1w, d, QASR_GEMM_GELU_SPLIT, nullptr, at_hi, at_lo, c->p1b, d));
-    CKR(gemm(c, at_hi, at_lo, T, d, c->p2w, H, QASR_GEMM_F32, c->ws_encout.as<float>(), nullptr, nullptr, c->p2b, H));
+    CKR(gemm(c, at_hi, at_lo, T, d, c->p2w, H, QASR_GEMM_F32, out, nullptr, nullptr, c->p2b, H));
     c->launches += 1;
     return 0;
     };
     {
         PdlScope pdl(T <= 256);
-        CKR(run_cached_graph(c, 1, frames, c->nsplit, enqueue));
+        if (n_units == 1 && out == c->ws_encout.as<float>()) CKR(run_cached_graph(c, 1, frames, c->nsplit, enqueue));
+        else CKR(enqueue());
     }
 #undef HI
 #undef LO
@@ -877,6 +748,7 @@ static int encode_device(qasr_ctx_t *c, const float *d_mel, int frames, int *T_o
     *T_out = T;
     return 0;
 }
+static int encode_device(qasr_ctx_t *c, const float *d_mel, int frames, int *T_out) { return encode_units_device(c, d_mel, 0, &frames, 1, nullptr, T_out); }
 
 int qasr_cuda_encode(qasr_ctx_t *c, const float *mel, int mel_frames, float *enc_out, int *out_tokens) {
     if (!c || !out_tokens) return set_err(QASR_ERR_ARG, "null argument");
@@ -1415,6 +1287,15 @@ int qasr_cuda_transcribe_batch(qasr_ctx_t *c, const float *const *samples, const
     CK(cudaSetDevice(c->device));
     if (timings_ms) timings_ms[0] = timings_ms[1] = timings_ms[2] = timings_ms[3] = 0.0;
     const int maxb = qasr_cuda_max_batch(c);
+    // more units than the persistent decode kernel carries per launch (4 / 2): the GEMM-batched throughput path (qasr_batch.cu)
+    static int batch_mode = -1; // QASR_BATCH=stream keeps every group on the persistent kernel (A/B runs)
+    if (batch_mode < 0) { const char *e = getenv("QASR_BATCH"); batch_mode = e && !strcmp(e, "stream") ? 0 : (e && !strcmp(e, "gemm") ? 2 : 1); }
+    if ((batch_mode == 1 && count > maxb) || (batch_mode == 2 && count > 1)) {
+        const int rc = batch_transcribe(c, samples, n_samples, count, max_new, ids_stride, out_ids, out_n, timings_ms);
+        select_seq(c, 0);
+        c->x_token = -1;
+        return rc;
+    }
     int i = 0;
     while (i < count) {
         int B = count - i >= 4 && maxb >= 4 ? 4 : (count - i >= 2 && maxb >= 2 ? 2 : 1);

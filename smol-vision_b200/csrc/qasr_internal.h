@@ -142,6 +142,18 @@ void launch_attn_prefill(cudaStream_t s, const float *q, const float *kc, const 
 void launch_attn_windowed(cudaStream_t s, const float *q, const float *k, const float *v, int ld, int n_heads,
                           const int *d_window_starts, int n_windows, int max_window, float scale, int out_ld,
                           float *out_f32, bf16_t *out_hi, bf16_t *out_lo);
+// batched path (qasr_batch.cu): per-unit KV caches inside one pool, unit u's block of a layer at pool + u * unit_stride
+void launch_qk_norm_rope_store_rows(cudaStream_t s, const float *qkv, const float *qn, const float *kn, const float *rope_cos,
+                                    const float *rope_sin, const int *d_row_unit, const int *d_row_pos, int R, float eps, float *q_out,
+                                    float *kpool, float *vpool, size_t unit_stride);
+void launch_attn_prefill_batch(cudaStream_t s, const float *q, const float *kpool, const float *vpool, size_t unit_stride, const int *d_row0,
+                               const int *d_P, int n_units, int max_P, int n_heads, int n_kv_heads, float scale, bf16_t *out_hi, bf16_t *out_lo);
+void launch_attn_decode_batch(cudaStream_t s, const float *qkv, const float *qn, const float *kn, const float *rope_cos, const float *rope_sin,
+                              float *kpool, float *vpool, size_t unit_stride, const int *d_pos, int B, float eps, float scale, bf16_t *ohi, bf16_t *olo);
+void launch_argmax_next(cudaStream_t s, const float *logits, int V, const bf16_t *E, int H, float *x_next, int *d_pos, int *d_step,
+                        int *d_tokens, volatile int *h_tokens, int B, int max_steps);
+void launch_assemble_prompts(cudaStream_t s, const bf16_t *E, int H, const int *d_pre, int n_pre, const int *d_suf, int n_suf, const float *enc,
+                             const int *d_enc0, const int *d_T, const int *d_row0, int n_units, int max_total, float *X, float *x_first);
 void launch_split_f32(cudaStream_t s, const float *x, size_t n, bf16_t *hi, bf16_t *lo);
 void launch_add_rows(cudaStream_t s, float *x, const float *table, const int *d_row_idx, int M, int d);
 void launch_eltwise(cudaStream_t s, int op, float *a, const float *b, float scalar, size_t n);
@@ -168,8 +180,9 @@ void launch_conv1(cudaStream_t s, const float *mel, int frames, const float *w, 
 void launch_im2col_stage(cudaStream_t s, const bf16_t *src, bf16_t *dst, const ConvGeom &g, int stage /*2 or 3*/);
 
 // ---- mel (qasr_mel.cu)
+// mel_out is [128][out_stride]; columns [out_off, out_off + frames) are written (single unit: out_stride = frames, out_off = 0)
 void launch_mel(cudaStream_t s, const float *samples, int n, int frames, const float *d_cos, const float *d_sin,
-                const float *d_win, const float *d_fb, float *mel_tmp, int *d_gmax, float *mel_out);
+                const float *d_win, const float *d_fb, float *mel_tmp, int *d_gmax, float *mel_out, int out_stride, int out_off);
 
 void launch_pcm16_to_mono(cudaStream_t s, const int16_t *pcm, int n, int channels, float *out);
 void launch_resample_sinc(cudaStream_t s, const float *in, int n, int rate, float *out, int new_n);

@@ -87,28 +87,30 @@ mel_pass1_kernel(const float *__restrict__ samples, int n, int frames, const flo
     }
 }
 
+// mel is [128][out_stride]; this call fills columns [out_off, out_off + frames) (out_stride == frames, out_off == 0 for a
+// single unit; the batched path lays the units of a group side by side along the frame axis)
 __global__ void mel_pass2_kernel(const float *__restrict__ mel_tmp, const int *__restrict__ gmax, int frames,
-                                 float *__restrict__ mel /*[128][frames]*/) {
+                                 float *__restrict__ mel, int out_stride, int out_off) {
     const float lo = ordered_to_float(*gmax) - 8.0f;
     const size_t total = (size_t)128 * frames;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
         const int m = (int)(e / frames), t = (int)(e % frames);
         float v = mel_tmp[(size_t)t * 128 + m];
         if (v < lo) v = lo;
-        mel[e] = (v + 4.0f) / 4.0f;
+        mel[(size_t)m * out_stride + out_off + t] = (v + 4.0f) / 4.0f;
     }
 }
 
 __global__ void mel_init_kernel(int *gmax) { *gmax = float_to_ordered(-1e30f); }
 
 void launch_mel(cudaStream_t s, const float *samples, int n, int frames, const float *d_cos, const float *d_sin,
-                const float *d_win, const float *d_fb, float *mel_tmp, int *d_gmax, float *mel_out) {
+                const float *d_win, const float *d_fb, float *mel_tmp, int *d_gmax, float *mel_out, int out_stride, int out_off) {
     mel_init_kernel<<<1, 1, 0, s>>>(d_gmax);
     mel_pass1_kernel<<<(frames + MEL_FPB - 1) / MEL_FPB, 256, 0, s>>>(samples, n, frames, d_cos, d_sin, d_win, d_fb,
                                                                      mel_tmp, d_gmax);
     const size_t total = (size_t)128 * frames;
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    mel_pass2_kernel<<<blocks, 256, 0, s>>>(mel_tmp, d_gmax, frames, mel_out);
+    mel_pass2_kernel<<<blocks, 256, 0, s>>>(mel_tmp, d_gmax, frames, mel_out, out_stride, out_off);
 }
 
 

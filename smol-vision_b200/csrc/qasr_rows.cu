@@ -150,6 +150,42 @@ void launch_qk_norm_rope_store(cudaStream_t s, const float *qkv, const float *qn
     if (P > 0) launch_pdl(qk_norm_rope_store_kernel, dim3(P, 32), 128, 0, s, qkv, qn, kn, rope_cos, rope_sin, start_pos, eps, q_out, kc, vc);
 }
 
+// Batched variant (qasr_batch.cu): row r belongs to unit row_unit[r] at position row_pos[r]; K/V rows go to that unit's
+// cache kpool + unit * unit_stride (this layer's [cap][1024] block).
+__global__ void __launch_bounds__(128)
+qk_norm_rope_store_rows_kernel(const float *__restrict__ qkv, const float *__restrict__ qn, const float *__restrict__ kn,
+                               const float *__restrict__ rope_cos, const float *__restrict__ rope_sin, const int *__restrict__ row_unit,
+                               const int *__restrict__ row_pos, float eps, float *__restrict__ q_out, float *__restrict__ kpool,
+                               float *__restrict__ vpool, size_t unit_stride) {
+    __shared__ float tmp[128];
+    __shared__ float red[4];
+    const int p = blockIdx.x, slot = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int pos = row_pos[p];
+    const size_t ub = (size_t)row_unit[p] * unit_stride;
+    const float v = qkv[(size_t)p * 4096 + slot * 128 + t];
+    if (slot >= 24) {
+        vpool[ub + (size_t)pos * 1024 + (slot - 24) * 128 + t] = v;
+        return;
+    }
+    float ss = warp_sum(v * v);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    ss = red[0] + red[1] + red[2] + red[3];
+    const float *w = slot < 16 ? qn : kn;
+    tmp[t] = v * (1.0f / sqrtf(ss / 128.0f + eps)) * w[t];
+    __syncthreads();
+    const int d = t & 63;
+    const float c = rope_cos[(size_t)pos * 64 + d], sn = rope_sin[(size_t)pos * 64 + d];
+    const float r = t < 64 ? tmp[t] * c - tmp[t + 64] * sn : tmp[t] * c + tmp[t - 64] * sn;
+    if (slot < 16) q_out[(size_t)p * 2048 + slot * 128 + t] = r;
+    else kpool[ub + (size_t)pos * 1024 + (slot - 16) * 128 + t] = r;
+}
+void launch_qk_norm_rope_store_rows(cudaStream_t s, const float *qkv, const float *qn, const float *kn, const float *rope_cos,
+                                    const float *rope_sin, const int *d_row_unit, const int *d_row_pos, int R, float eps, float *q_out,
+                                    float *kpool, float *vpool, size_t unit_stride) {
+    if (R > 0) qk_norm_rope_store_rows_kernel<<<dim3(R, 32), 128, 0, s>>>(qkv, qn, kn, rope_cos, rope_sin, d_row_unit, d_row_pos, eps, q_out, kpool, vpool, unit_stride);
+}
+
 // ------------------------------------------------------------------ online-softmax helpers
 template <int NV>
 __device__ __forceinline__ void soft_update(float sc, float &m, float &l, float (&acc)[NV], const float (&v)[NV]) {
@@ -273,16 +309,12 @@ __device__ __forceinline__ void att_store_tile(AttSmem<HD> &sm, const AttRegs<HD
 // reference qwen_asr_kernels.c:1101-1148.  head_dim = 128.  CTA = (kv head, 16 query positions) = 32 queries (both
 // query heads of the kv head share every K/V tile); warp w owns queries 4w..4w+3 = positions p0+2w, p0+2w+1 x 2 heads.
 // Query position i attends keys [0, q_offset + i].
-__global__ void __launch_bounds__(256)
-attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, const float *__restrict__ vc,
-                    int q_offset, int P, int seq_k, int n_heads, int n_kv_heads, float scale, float *of, bf16_t *ohi,
-                    bf16_t *olo) {
-    pdl_trigger();
-    pdl_wait();
+__device__ __forceinline__ void attn_prefill_body(const float *__restrict__ q, const float *__restrict__ kc, const float *__restrict__ vc,
+                                                  int q_offset, int P, int seq_k, int n_heads, int n_kv_heads, float scale, float *of, bf16_t *ohi,
+                                                  bf16_t *olo, size_t out_row0, int kvh, int ib) {
     extern __shared__ __align__(16) uint8_t att_raw[];
     AttSmem<128> &sm = *reinterpret_cast<AttSmem<128> *>(att_raw);
-    const int kvh = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ib = blockIdx.y * 16;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = n_heads / n_kv_heads; // 2
     const size_t qld = (size_t)n_heads * 128, kld = (size_t)n_kv_heads * 128;
     const int kmax_cta = min(q_offset + min(ib + 16, P), seq_k); // keys needed by the last position of the CTA
@@ -315,23 +347,57 @@ attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, c
         const int qi = warp * 4 + j, pos = ib + (qi >> 1), hh = kvh * per + (qi & 1);
         if (pos >= P) continue;
         const float inv = l[j] > 0.0f ? 1.0f / l[j] : 0.0f;
-        const size_t base = (size_t)pos * qld + hh * 128 + lane * 4;
+        const size_t base = (out_row0 + (size_t)pos) * qld + hh * 128 + lane * 4;
 #pragma unroll
         for (int c = 0; c < 4; c++) store_out(acc[j][c] * inv, base + c, of, ohi, olo);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, const float *__restrict__ vc,
+                    int q_offset, int P, int seq_k, int n_heads, int n_kv_heads, float scale, float *of, bf16_t *ohi,
+                    bf16_t *olo) {
+    pdl_trigger();
+    pdl_wait();
+    attn_prefill_body(q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, of, ohi, olo, 0, blockIdx.x, blockIdx.y * 16);
+}
+
+// Batched variant (qasr_batch.cu): blockIdx.z = unit.  Unit u owns rows [row0[u], row0[u] + P[u]) of the concatenated
+// q / output matrices and its own KV cache kpool + u * unit_stride (this layer's [cap][1024] block); every unit starts at
+// position 0 (a fresh segment / utterance, reference qwen_asr.c:763).
+__global__ void __launch_bounds__(256)
+attn_prefill_batch_kernel(const float *__restrict__ q, const float *__restrict__ kpool, const float *__restrict__ vpool, size_t unit_stride,
+                          const int *__restrict__ row0, const int *__restrict__ Ps, int n_heads, int n_kv_heads, float scale,
+                          bf16_t *ohi, bf16_t *olo) {
+    const int u = blockIdx.z, P = Ps[u], ib = blockIdx.y * 16;
+    if (ib >= P) return;
+    const size_t r0 = (size_t)row0[u];
+    attn_prefill_body(q + r0 * n_heads * 128, kpool + u * unit_stride, vpool + u * unit_stride, 0, P, P, n_heads, n_kv_heads, scale,
+                      nullptr, ohi, olo, r0, blockIdx.x, ib);
+}
+static void attn_prefill_opt_in() { // per-device bit: the attribute belongs to the (function, device) pair
+    static unsigned attr_set = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_set >> (dev & 31) & 1u)) {
+        cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttSmem<128>));
+        cudaFuncSetAttribute(attn_prefill_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttSmem<128>));
+        attr_set |= 1u << (dev & 31);
     }
 }
 void launch_attn_prefill(cudaStream_t s, const float *q, const float *kc, const float *vc, int q_offset, int P, int seq_k,
                          int n_heads, int n_kv_heads, float scale, float *out_f32, bf16_t *out_hi, bf16_t *out_lo) {
     if (P <= 0) return;
-    static unsigned attr_set = 0; // per-device bit: the attribute belongs to the (function, device) pair
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!(attr_set >> (dev & 31) & 1u)) {
-        cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttSmem<128>));
-        attr_set |= 1u << (dev & 31);
-    }
+    attn_prefill_opt_in();
     dim3 grid(n_kv_heads, (P + 15) / 16);
     launch_pdl(attn_prefill_kernel, grid, 256, sizeof(AttSmem<128>), s, q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, out_f32, out_hi, out_lo);
+}
+void launch_attn_prefill_batch(cudaStream_t s, const float *q, const float *kpool, const float *vpool, size_t unit_stride, const int *d_row0,
+                               const int *d_P, int n_units, int max_P, int n_heads, int n_kv_heads, float scale, bf16_t *out_hi, bf16_t *out_lo) {
+    if (n_units <= 0 || max_P <= 0) return;
+    attn_prefill_opt_in();
+    dim3 grid(n_kv_heads, (max_P + 15) / 16, n_units);
+    attn_prefill_batch_kernel<<<grid, 256, sizeof(AttSmem<128>), s>>>(q, kpool, vpool, unit_stride, d_row0, d_P, n_heads, n_kv_heads, scale, out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------ windowed bidirectional attention (encoder)
@@ -578,4 +644,199 @@ void launch_transpose_bias(cudaStream_t s, const float *in, const float *bias, f
     if (S <= 0 || C <= 0) return;
     dim3 grid((S + 31) / 32, (C + 31) / 32), block(32, 8);
     transpose_bias_kernel<<<grid, block, 0, s>>>(in, bias, out, S, C);
+}
+
+// ------------------------------------------------------------------ batched decode step kernels (qasr_batch.cu)
+// One new token per sequence.  CTA = (kv head, sequence): per-head RMSNorm + split-half RoPE of the two query heads and of
+// the new key (reference qwen_asr_decoder.c:632-646), append of the new K/V row to this sequence's cache at pos[u], then
+// GQA attention of both query heads over keys [0, pos[u]] with the reference's online softmax (qwen_asr_kernels.c:1101-1148):
+// warp w owns keys w, w+8, ...; a lane holds 4 dims of q (both heads) and of the key / value row; the 8 per-warp states are
+// merged in fixed order.  Positions come from device memory so one captured CUDA graph serves every step.
+#define ATTD_KEYS 4 /* keys per warp in flight */
+__global__ void __launch_bounds__(256)
+attn_decode_batch_kernel(const float *__restrict__ qkv /*[B][4096]*/, const float *__restrict__ qn, const float *__restrict__ kn,
+                         const float *__restrict__ rope_cos, const float *__restrict__ rope_sin, float *__restrict__ kpool,
+                         float *__restrict__ vpool, size_t unit_stride, const int *__restrict__ d_pos, float eps, float scale,
+                         bf16_t *__restrict__ ohi, bf16_t *__restrict__ olo /*[B][2048] planes*/) {
+    __shared__ float4 s_new[3][32];        // roped q0, q1, k_new (4 dims per lane)
+    __shared__ float4 s_vnew[32];
+    __shared__ float s_acc[8][2][128];
+    __shared__ float s_ml[8][2][2];
+    pdl_trigger();
+    pdl_wait();
+    const int kvh = blockIdx.x, u = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pos = d_pos[u];
+    const float *row = qkv + (size_t)u * 4096;
+    float *kc = kpool + (size_t)u * unit_stride, *vc = vpool + (size_t)u * unit_stride;
+    const size_t hoff = (size_t)kvh * 128 + lane * 4;
+    if (warp < 3) { // warps 0, 1: the two query heads of this kv head; warp 2: the new key
+        const float *src = warp < 2 ? row + (2 * kvh + warp) * 128 : row + 2048 + kvh * 128;
+        float4 v = *reinterpret_cast<const float4 *>(src + lane * 4);
+        const float4 nw = *reinterpret_cast<const float4 *>((warp < 2 ? qn : kn) + lane * 4);
+        const float s2 = warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+        const float inv = 1.0f / sqrtf(s2 / 128.0f + eps);
+        v.x = v.x * inv * nw.x; v.y = v.y * inv * nw.y; v.z = v.z * inv * nw.z; v.w = v.w * inv * nw.w;
+        float4 o; // dims d and d +- 64 live in lanes l and l ^ 16
+        o.x = __shfl_xor_sync(0xffffffffu, v.x, 16); o.y = __shfl_xor_sync(0xffffffffu, v.y, 16);
+        o.z = __shfl_xor_sync(0xffffffffu, v.z, 16); o.w = __shfl_xor_sync(0xffffffffu, v.w, 16);
+        const float4 rc = *reinterpret_cast<const float4 *>(rope_cos + (size_t)pos * 64 + (lane & 15) * 4);
+        const float4 rs = *reinterpret_cast<const float4 *>(rope_sin + (size_t)pos * 64 + (lane & 15) * 4);
+        const float sgn = lane < 16 ? -1.0f : 1.0f;
+        const float4 r = make_float4(v.x * rc.x + sgn * o.x * rs.x, v.y * rc.y + sgn * o.y * rs.y, v.z * rc.z + sgn * o.z * rs.z, v.w * rc.w + sgn * o.w * rs.w);
+        s_new[warp][lane] = r;
+        if (warp == 2) *reinterpret_cast<float4 *>(kc + (size_t)pos * 1024 + hoff) = r;
+    } else if (warp == 3) {
+        const float4 v = *reinterpret_cast<const float4 *>(row + 3072 + kvh * 128 + lane * 4);
+        s_vnew[lane] = v;
+        *reinterpret_cast<float4 *>(vc + (size_t)pos * 1024 + hoff) = v;
+    }
+    __syncthreads();
+    const float4 q0 = s_new[0][lane], q1 = s_new[1][lane];
+    float m0 = -1e30f, l0 = 0.0f, m1 = -1e30f, l1 = 0.0f;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    const int n_keys = pos + 1;
+    for (int base = warp; base < n_keys; base += 8 * ATTD_KEYS) {
+        float4 kr[ATTD_KEYS], vr[ATTD_KEYS];
+#pragma unroll
+        for (int i = 0; i < ATTD_KEYS; i++) {
+            const int j = base + 8 * i;
+            if (j < pos) {
+                kr[i] = __ldcg(reinterpret_cast<const float4 *>(kc + (size_t)j * 1024 + hoff));
+                vr[i] = __ldcg(reinterpret_cast<const float4 *>(vc + (size_t)j * 1024 + hoff));
+            } else if (j == pos) { kr[i] = s_new[2][lane]; vr[i] = s_vnew[lane]; } // never read the row being appended from the cache
+        }
+        float d0[ATTD_KEYS], d1[ATTD_KEYS];
+#pragma unroll
+        for (int i = 0; i < ATTD_KEYS; i++) {
+            const bool ok = base + 8 * i < n_keys;
+            d0[i] = ok ? q0.x * kr[i].x + q0.y * kr[i].y + q0.z * kr[i].z + q0.w * kr[i].w : 0.0f;
+            d1[i] = ok ? q1.x * kr[i].x + q1.y * kr[i].y + q1.z * kr[i].z + q1.w * kr[i].w : 0.0f;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < ATTD_KEYS; i++) {
+                d0[i] += __shfl_xor_sync(0xffffffffu, d0[i], o);
+                d1[i] += __shfl_xor_sync(0xffffffffu, d1[i], o);
+            }
+#pragma unroll
+        for (int i = 0; i < ATTD_KEYS; i++) {
+            if (base + 8 * i >= n_keys) continue;
+            float acc0[4] = {a0.x, a0.y, a0.z, a0.w}, acc1[4] = {a1.x, a1.y, a1.z, a1.w};
+            const float vv[4] = {vr[i].x, vr[i].y, vr[i].z, vr[i].w};
+            soft_update<4>(d0[i] * scale, m0, l0, acc0, vv);
+            soft_update<4>(d1[i] * scale, m1, l1, acc1, vv);
+            a0 = make_float4(acc0[0], acc0[1], acc0[2], acc0[3]);
+            a1 = make_float4(acc1[0], acc1[1], acc1[2], acc1[3]);
+        }
+    }
+    *reinterpret_cast<float4 *>(&s_acc[warp][0][lane * 4]) = a0;
+    *reinterpret_cast<float4 *>(&s_acc[warp][1][lane * 4]) = a1;
+    if (lane == 0) { s_ml[warp][0][0] = m0; s_ml[warp][0][1] = l0; s_ml[warp][1][0] = m1; s_ml[warp][1][1] = l1; }
+    __syncthreads();
+    { // 256 threads = 2 heads x 128 dims: merge the 8 warps in fixed order
+        const int h = tid >> 7, dim = tid & 127;
+        float M = -1e30f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) M = fmaxf(M, s_ml[w][h][0]);
+        float L = 0.0f, A = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const float e = expf(s_ml[w][h][0] - M);
+            L += s_ml[w][h][1] * e;
+            A += s_acc[w][h][dim] * e;
+        }
+        store_out(L > 0.0f ? A / L : 0.0f, (size_t)u * 2048 + (2 * kvh + h) * 128 + dim, nullptr, ohi, olo);
+    }
+}
+void launch_attn_decode_batch(cudaStream_t s, const float *qkv, const float *qn, const float *kn, const float *rope_cos, const float *rope_sin,
+                              float *kpool, float *vpool, size_t unit_stride, const int *d_pos, int B, float eps, float scale, bf16_t *ohi, bf16_t *olo) {
+    if (B > 0) launch_pdl(attn_decode_batch_kernel, dim3(8, B), 256, 0, s, qkv, qn, kn, rope_cos, rope_sin, kpool, vpool, unit_stride, d_pos, eps, scale, ohi, olo);
+}
+
+// Greedy head of the batched step: argmax over the f32 logits row of sequence u (strict >, ties -> lowest index,
+// reference qwen_asr_kernels.c:536-541), token bookkeeping, and the gather of the next input row (exact bf16 -> f32
+// upcast, qwen_asr.c:412-419,816).  One CTA per sequence.
+__global__ void __launch_bounds__(1024)
+argmax_next_kernel(const float *__restrict__ logits, int V, const bf16_t *__restrict__ E, int H, float *__restrict__ x_next,
+                   int *__restrict__ d_pos, const int *__restrict__ d_step, int *__restrict__ d_tokens, volatile int *h_tokens, int B, int max_steps) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    __shared__ int s_tok;
+    const int u = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *row = logits + (size_t)u * V;
+    float bv = -1e30f;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < V; i += 1024) { // ascending per thread: strict > keeps the lowest index
+        const float v = row[i];
+        if (v > bv) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        bv = sv[lane]; bi = si[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            if (bi < 0 || bi >= V) bi = 0; // a row of NaNs never compares greater: keep the index in range
+            s_tok = bi;
+            const int st = *d_step;
+            if (st < max_steps) {
+                d_tokens[st * B + u] = bi;
+                if (h_tokens) h_tokens[st * B + u] = bi;
+            }
+            d_pos[u] += 1;
+        }
+    }
+    __syncthreads();
+    const int tok = s_tok;
+    for (int e = tid; e < H; e += 1024) x_next[(size_t)u * H + e] = __uint_as_float(((uint32_t)E[(size_t)tok * H + e]) << 16);
+}
+__global__ void advance_step_kernel(int *d_step) {
+    pdl_trigger();
+    pdl_wait();
+    *d_step += 1;
+}
+void launch_argmax_next(cudaStream_t s, const float *logits, int V, const bf16_t *E, int H, float *x_next, int *d_pos, int *d_step,
+                        int *d_tokens, volatile int *h_tokens, int B, int max_steps) {
+    if (B <= 0) return;
+    launch_pdl(argmax_next_kernel, B, 1024, 0, s, logits, V, E, H, x_next, d_pos, (const int *)d_step, d_tokens, h_tokens, B, max_steps);
+    launch_pdl(advance_step_kernel, 1, 1, 0, s, d_step);
+}
+
+// Prompt rows of a group of units (reference qwen_asr.c:685-759): unit u's sequence is embed(pre) | its T[u] encoder rows
+// (enc rows [enc0[u], enc0[u] + T[u])) | embed(suf).  Rows 0 .. total-2 go to the prefill matrix at row0[u] + i, the last
+// row becomes the unit's first decode input x_first[u] (the reference prefills total_seq - 1 rows and steps on the last, :764-769).
+__global__ void __launch_bounds__(256)
+assemble_prompts_kernel(const bf16_t *__restrict__ E, int H, const int *__restrict__ pre, int n_pre, const int *__restrict__ suf, int n_suf,
+                        const float *__restrict__ enc, const int *__restrict__ enc0, const int *__restrict__ Ts, const int *__restrict__ row0,
+                        float *__restrict__ X, float *__restrict__ x_first) {
+    const int u = blockIdx.y, i = blockIdx.x, T = Ts[u], total = n_pre + T + n_suf;
+    if (i >= total) return;
+    float *dst = i < total - 1 ? X + ((size_t)row0[u] + i) * H : x_first + (size_t)u * H;
+    if (i >= n_pre && i < n_pre + T) {
+        const float *src = enc + ((size_t)enc0[u] + (i - n_pre)) * H;
+        for (int e = threadIdx.x; e < H; e += 256) dst[e] = src[e];
+    } else {
+        const int tok = i < n_pre ? pre[i] : suf[i - n_pre - T];
+        const bf16_t *src = E + (size_t)tok * H;
+        for (int e = threadIdx.x; e < H; e += 256) dst[e] = __uint_as_float(((uint32_t)src[e]) << 16);
+    }
+}
+void launch_assemble_prompts(cudaStream_t s, const bf16_t *E, int H, const int *d_pre, int n_pre, const int *d_suf, int n_suf, const float *enc,
+                             const int *d_enc0, const int *d_T, const int *d_row0, int n_units, int max_total, float *X, float *x_first) {
+    if (n_units > 0 && max_total > 0)
+        assemble_prompts_kernel<<<dim3(max_total, n_units), 256, 0, s>>>(E, H, d_pre, n_pre, d_suf, n_suf, enc, d_enc0, d_T, d_row0, X, x_first);
 }
