@@ -109,9 +109,113 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 struct TcParams {
     int M, N, K;
     int nsplit; // 1 or 2 A planes
+    int tiles_m, tiles_n; // persistent tile loop: tile t -> (m = t / tiles_n, n = t % tiles_n), n fastest so the CTAs running
+                          // at the same time share A tiles (and the few W tiles of their column range) in L2
     GemmEpilogue epi;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void st_v4(void *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_hi2(float a, float b, float &ra, float &rb) { // bf16 pair of (a, b) and the residuals a - hi, b - hi
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    ra = a - __bfloat162float(ha); rb = b - __bfloat162float(hb);
+    return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+}
+__device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
+    return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(a)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(b)) << 16);
+}
+
+// Epilogue of one 32-row x 32-column block held as "thread = row, registers = 32 consecutive columns" (the layout
+// tcgen05.ld delivers).  Every thread writes its own row with 16-byte vector stores: 8 (f32), 4 + 4 (bf16 hi / lo planes) or
+// 2 + 2 (SwiGLU halves the width) store instructions per block instead of 32 / 64 scalar ones through a shared-memory
+// transpose.  `vec` = the output row pitch and base allow aligned 16-byte accesses and the block lies inside [0, N).
+__device__ __forceinline__ void tc_epilogue_block(const GemmEpilogue &e, const float (&v)[32], int row, int n, int N, bool row_ok, bool vec) {
+    if (!row_ok) return;
+    if (e.mode == QASR_GEMM_F32 || e.mode == QASR_GEMM_RESIDUAL) {
+        float *o = e.out_f32 + (size_t)row * e.ldo + n;
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 r = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (e.bias) { const float4 bb = __ldg(reinterpret_cast<const float4 *>(e.bias + n + j)); r.x += bb.x; r.y += bb.y; r.z += bb.z; r.w += bb.w; }
+                if (e.mode == QASR_GEMM_RESIDUAL) { const float4 old = *reinterpret_cast<const float4 *>(o + j); r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w; }
+                *reinterpret_cast<float4 *>(o + j) = r;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (n + j < N) {
+                    float r = v[j] + (e.bias ? e.bias[n + j] : 0.0f);
+                    if (e.mode == QASR_GEMM_RESIDUAL) r += o[j];
+                    o[j] = r;
+                }
+        }
+    } else if (e.mode == QASR_GEMM_GELU_SPLIT) {
+        bf16_t *oh = e.out_hi + (size_t)row * e.ldo + n, *ol = e.out_lo ? e.out_lo + (size_t)row * e.ldo + n : nullptr;
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const float a = gelu_tanh(v[j + 2 * t] + (e.bias ? __ldg(e.bias + n + j + 2 * t) : 0.0f));
+                    const float b = gelu_tanh(v[j + 2 * t + 1] + (e.bias ? __ldg(e.bias + n + j + 2 * t + 1) : 0.0f));
+                    float ra, rb;
+                    h[t] = pack_hi2(a, b, ra, rb);
+                    l[t] = pack_bf2(ra, rb);
+                }
+                st_v4(oh + j, h[0], h[1], h[2], h[3]);
+                if (ol) st_v4(ol + j, l[0], l[1], l[2], l[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (n + j < N) {
+                    const float a = gelu_tanh(v[j] + (e.bias ? e.bias[n + j] : 0.0f));
+                    __nv_bfloat16 hi, lo;
+                    split_bf16(a, hi, lo);
+                    oh[j] = __bfloat16_as_ushort(hi);
+                    if (ol) ol[j] = __bfloat16_as_ushort(lo);
+                }
+        }
+    } else { // SWIGLU: columns (2j, 2j+1) = (gate_j, up_j), reference qwen_asr_decoder.c:140-152; output column (n >> 1) + j
+        bf16_t *oh = e.out_hi + (size_t)row * e.ldo + (n >> 1), *ol = e.out_lo ? e.out_lo + (size_t)row * e.ldo + (n >> 1) : nullptr;
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 8) {
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const float a = silu(v[2 * (j + 2 * t)]) * v[2 * (j + 2 * t) + 1];
+                    const float b = silu(v[2 * (j + 2 * t + 1)]) * v[2 * (j + 2 * t + 1) + 1];
+                    float ra, rb;
+                    h[t] = pack_hi2(a, b, ra, rb);
+                    l[t] = pack_bf2(ra, rb);
+                }
+                st_v4(oh + j, h[0], h[1], h[2], h[3]);
+                if (ol) st_v4(ol + j, l[0], l[1], l[2], l[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++)
+                if (n + 2 * j + 1 < N) {
+                    const float a = silu(v[2 * j]) * v[2 * j + 1];
+                    __nv_bfloat16 hi, lo;
+                    split_bf16(a, hi, lo);
+                    oh[j] = __bfloat16_as_ushort(hi);
+                    if (ol) ol[j] = __bfloat16_as_ushort(lo);
+                }
+        }
+    }
+}
+
+// Persistent kernel: one CTA per SM walks the tile list; the accumulator is double-buffered in TMEM (2 x BN columns), so
+// the epilogue of tile i (warps 2-5) overlaps the mainloop of tile i+1 (warps 0-1) and the operand ring never drains
+// between tiles.
 template <int BN, int STAGES = (BN > 128 ? 3 : TC_STAGES)>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -124,24 +228,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     uint64_t *empty_bar = full_bar + STAGES;
-    uint64_t *tmem_full_bar = empty_bar + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
+    uint64_t *tmem_full_bar = empty_bar + STAGES;   // [2] accumulator stage complete (MMA -> epilogue)
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;   // [2] accumulator stage drained (4 epilogue warps -> MMA)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
 
     pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
     const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+    const int total_tiles = p.tiles_m * p.tiles_n;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         if (p.nsplit == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
         for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) { // TMEM allocation: BN f32 columns x 128 lanes
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN)
+    if (warp == 1) { // TMEM allocation: two accumulator stages of BN f32 columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -155,15 +260,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         // ===== TMA producer =====
         if (lane == 0) {
             const uint32_t tx = (p.nsplit == 2 ? 2 * A_BYTES : A_BYTES) + B_BYTES;
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t *st = smem + s * STAGE_BYTES;
-                mbar_expect_tx(&full_bar[s], tx);
-                tma_load_2d(st, &tmA_hi, &full_bar[s], kb * TC_BK, m0);
-                if (p.nsplit == 2) tma_load_2d(st + A_BYTES, &tmA_lo, &full_bar[s], kb * TC_BK, m0);
-                tma_load_2d(st + 2 * A_BYTES, &tmB, &full_bar[s], kb * TC_BK, n0);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int m0 = (t / p.tiles_n) * TC_BM, n0 = (t % p.tiles_n) * BN;
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                    uint8_t *st = smem + s * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[s], tx);
+                    tma_load_2d(st, &tmA_hi, &full_bar[s], kb * TC_BK, m0);
+                    if (p.nsplit == 2) tma_load_2d(st + A_BYTES, &tmA_lo, &full_bar[s], kb * TC_BK, m0);
+                    tma_load_2d(st + 2 * A_BYTES, &tmB, &full_bar[s], kb * TC_BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -173,86 +281,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             // B=bf16 [10,13)=1, A/B K-major [15],[16]=0, N>>3 [17,23), M>>4 [24,29)
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(TC_BM >> 4) << 24);
-            for (int kb = 0; kb < num_kb; kb++) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            uint32_t it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++) {
+                const uint32_t as = lt & 1;
+                mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1) ^ 1); // the epilogue has drained this accumulator stage
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t dah = make_sw128_desc(a_hi);
-                const uint64_t dal = make_sw128_desc(a_hi + A_BYTES);
-                const uint64_t db = make_sw128_desc(a_hi + 2 * A_BYTES);
+                const uint32_t tacc = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int s = it % STAGES;
+                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t dah = make_sw128_desc(a_hi);
+                    const uint64_t dal = make_sw128_desc(a_hi + A_BYTES);
+                    const uint64_t db = make_sw128_desc(a_hi + 2 * A_BYTES);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; k++) // +32 bytes (16 bf16) along K inside the swizzle atom
-                    tc_mma_bf16(tmem_base, dah + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                if (p.nsplit == 2) {
+                    for (int k = 0; k < TC_BK / 16; k++) // +32 bytes (16 bf16) along K inside the swizzle atom
+                        tc_mma_bf16(tacc, dah + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    if (p.nsplit == 2) {
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 16; k++)
-                        tc_mma_bf16(tmem_base, dal + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+                        for (int k = 0; k < TC_BK / 16; k++)
+                            tc_mma_bf16(tacc, dal + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+                    }
+                    tc_commit(&empty_bar[s]); // frees the ring slot once the MMAs above have read it
                 }
-                tc_commit(&empty_bar[s]); // frees the ring slot once the MMAs above have read it
+                tc_commit(&tmem_full_bar[as]); // accumulator of this tile complete
             }
-            tc_commit(tmem_full_bar); // accumulator complete
         }
     } else {
-        // ===== epilogue warps 2..5 =====
-        // tcgen05.ld hands thread i the 32 columns of ROW i; storing from that layout makes every store instruction touch
-        // 32 different rows (32 memory transactions for 128 bytes, and 2-byte scattered stores for the bf16 planes), which
-        // bounded the medium-M GEMMs.  Each 32 x 32 block is transposed through shared memory (the operand ring is free:
-        // the accumulator barrier fires only after every MMA has read it) so that a warp stores 32 consecutive columns of
-        // one row per instruction.
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const int q = warp & 3; // TMEM lane quarter this warp may access
-        float *stage = reinterpret_cast<float *>(smem) + q * (32 * 33);
+        // ===== epilogue warps 2..5: TMEM lane quarter q = rows m0 + 32 q .. + 31, thread = row =====
+        const int q = warp & 3;
         const GemmEpilogue &e = p.epi;
+        const int width = e.mode == QASR_GEMM_SWIGLU_SPLIT ? 2 : 1;
+        const bool aligned = (e.ldo % 8 == 0) && ((e.mode == QASR_GEMM_F32 || e.mode == QASR_GEMM_RESIDUAL)
+                                 ? (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0 && (!e.bias || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0)
+                                 : (reinterpret_cast<uintptr_t>(e.out_hi) & 15) == 0 && (!e.out_lo || (reinterpret_cast<uintptr_t>(e.out_lo) & 15) == 0));
+        uint32_t lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, lt++) {
+            const int m0 = (t / p.tiles_n) * TC_BM, n0 = (t % p.tiles_n) * BN;
+            const uint32_t as = lt & 1;
+            mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < p.M;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int n = n0 + c0;
+                if (n >= p.N) break;
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + (uint32_t)c0, r);
+                float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; j++) stage[lane * 33 + j] = __uint_as_float(r[j]);
-            __syncwarp();
-            const int n = n0 + c0 + lane;
-            const float bias = (e.bias && n < p.N) ? e.bias[n] : 0.0f;
-            const int rows = min(32, p.M - (m0 + q * 32));
-            for (int rr = 0; rr < rows; rr++) {
-                const int row = m0 + q * 32 + rr;
-                float v = stage[rr * 33 + lane];
-                if (e.mode == QASR_GEMM_F32 || e.mode == QASR_GEMM_RESIDUAL) {
-                    if (n < p.N) {
-                        float *o = e.out_f32 + (size_t)row * e.ldo + n;
-                        v += bias;
-                        if (e.mode == QASR_GEMM_RESIDUAL) v += *o;
-                        *o = v;
-                    }
-                } else if (e.mode == QASR_GEMM_GELU_SPLIT) {
-                    if (n < p.N) {
-                        v = gelu_tanh(v + bias);
-                        __nv_bfloat16 hi, lo;
-                        split_bf16(v, hi, lo);
-                        e.out_hi[(size_t)row * e.ldo + n] = __bfloat16_as_ushort(hi);
-                        if (e.out_lo) e.out_lo[(size_t)row * e.ldo + n] = __bfloat16_as_ushort(lo);
-                    }
-                } else { // SWIGLU: columns (2j, 2j+1) = (gate_j, up_j) sit in neighbouring lanes, reference qwen_asr_decoder.c:140-152
-                    const float u = __shfl_down_sync(0xffffffffu, v, 1);
-                    if (!(lane & 1) && n + 1 < p.N) {
-                        const float w = silu(v) * u;
-                        __nv_bfloat16 hi, lo;
-                        split_bf16(w, hi, lo);
-                        e.out_hi[(size_t)row * e.ldo + (n >> 1)] = __bfloat16_as_ushort(hi);
-                        if (e.out_lo) e.out_lo[(size_t)row * e.ldo + (n >> 1)] = __bfloat16_as_ushort(lo);
-                    }
-                }
+                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+                tc_epilogue_block(e, v, row, n, p.N, row_ok, aligned && n + 32 <= p.N && (width == 1 || (p.N & 1) == 0));
             }
+            tc_fence_before();
             __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
         }
-        tc_fence_before();
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
     }
 }
 
@@ -737,20 +828,21 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
     p.M = M; p.N = N; p.K = K;
     p.nsplit = A_lo ? 2 : 1;
     p.epi = epi;
+    const int bn = bn64 ? 64 : (bn256 ? 256 : 128);
+    p.tiles_m = (M + TC_BM - 1) / TC_BM;
+    p.tiles_n = (N + bn - 1) / bn;
     CUtensorMap ma, ml, mb;
     if (make_map(&ma, A_hi, M, K, TC_BM) != 0) return -1;
     if (make_map(&ml, A_lo ? A_lo : A_hi, M, K, TC_BM) != 0) return -1;
-    if (make_map(&mb, W, N, K, bn64 ? 64 : (bn256 ? 256 : 128)) != 0) return -1;
-    if (bn256) {
-        dim3 grid((N + 255) / 256, (M + TC_BM - 1) / TC_BM);
-        launch_pdl(gemm_tc_kernel<256>, grid, TC_THREADS, tc_smem_bytes<256>(), s, ma, ml, mb, p);
-    } else if (bn64) {
-        dim3 grid((N + 63) / 64, (M + TC_BM - 1) / TC_BM);
-        launch_pdl(gemm_tc_kernel<64>, grid, TC_THREADS, tc_smem_bytes<64>(), s, ma, ml, mb, p);
-    } else {
-        dim3 grid((N + 127) / 128, (M + TC_BM - 1) / TC_BM);
-        launch_pdl(gemm_tc_kernel<128>, grid, TC_THREADS, tc_smem_bytes<128>(), s, ma, ml, mb, p);
-    }
+    if (make_map(&mb, W, N, K, bn) != 0) return -1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    { static int sm_count[32] = {}; if (!sm_count[dev & 31]) cudaDeviceGetAttribute(&sm_count[dev & 31], cudaDevAttrMultiProcessorCount, dev); sms = sm_count[dev & 31] > 0 ? sm_count[dev & 31] : 148; }
+    const long long total = (long long)p.tiles_m * p.tiles_n;
+    dim3 grid((unsigned)(total < sms ? total : sms)); // persistent: one CTA per SM walks the tile list
+    if (bn256) launch_pdl(gemm_tc_kernel<256>, grid, TC_THREADS, tc_smem_bytes<256>(), s, ma, ml, mb, p);
+    else if (bn64) launch_pdl(gemm_tc_kernel<64>, grid, TC_THREADS, tc_smem_bytes<64>(), s, ma, ml, mb, p);
+    else launch_pdl(gemm_tc_kernel<128>, grid, TC_THREADS, tc_smem_bytes<128>(), s, ma, ml, mb, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc launch: %s", cudaGetErrorString(e));

@@ -5,6 +5,7 @@
 #include "../../include/qasr_cuda.h"
 #include "qasr_internal.h"
 
+#include <cuda_bf16.h>
 #include <math.h>
 #include <vector>
 
@@ -282,6 +283,15 @@ int qasr_op_apply_rope_neox(qasr_ctx_t *c, float *x, const float *cos_vals, cons
 // debug / tuning hook (not part of the public header): device-time one tensor-core GEMM shape.
 // `iters` launches over NW rotating weight matrices (so weights come from HBM, not L2) are captured
 // into one CUDA graph and the graph launch is timed: no host launch overhead in the number.
+// bench operands: a deterministic hash -> bf16 in (-1, 1) (all-zero operands draw less power than real data and flatter the clocks)
+__global__ void fill_hash_bf16_kernel(bf16_t *p, size_t n, unsigned seed) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        unsigned h = (unsigned)i * 2654435761u + seed;
+        h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+        const float v = ((float)(h >> 8) / 8388608.0f - 1.0f) * 0.5f;
+        p[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    }
+}
 extern "C" int qasr_debug_gemm_bench(qasr_ctx_t *c, int M, int K, int N, int iters, int mode, double *out_us) {
     OP_BEGIN(c);
     const int NW = 8;
@@ -290,7 +300,7 @@ extern "C" int qasr_debug_gemm_bench(qasr_ctx_t *c, int M, int K, int N, int ite
     float *y = sc.alloc<float>((size_t)M * N);
     bf16_t *oh = sc.alloc<bf16_t>((size_t)2 * M * N);
     if (!sc.ok) return finish(c, sc, s);
-    cudaMemsetAsync(a, 0, 2 * na * 2, s); cudaMemsetAsync(w, 0, nw * NW * 2, s); cudaMemsetAsync(y, 0, (size_t)M * N * 4, s);
+    fill_hash_bf16_kernel<<<1184, 256, 0, s>>>(a, 2 * na, 1u); fill_hash_bf16_kernel<<<1184, 256, 0, s>>>(w, nw * NW, 2u); cudaMemsetAsync(y, 0, (size_t)M * N * 4, s);
     GemmEpilogue e;
     e.mode = mode; e.out_f32 = y; e.out_hi = oh; e.out_lo = oh + (size_t)M * N; e.bias = nullptr; e.ldo = (mode == QASR_GEMM_SWIGLU_SPLIT) ? N / 2 : N;
     const bool two = qasr_internal_nsplit(c) == 2;

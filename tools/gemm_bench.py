@@ -18,8 +18,20 @@ if len(sys.argv) > 1 and sys.argv[1] == "medium":
               ("17.pre.qkv", 404, 2048, 4096), ("17.pre.wo", 404, 2048, 2048), ("17.pre.gu", 404, 2048, 12288), ("17.pre.down", 404, 6144, 2048),
               ("17.enc.qkv", 390, 1024, 3072), ("17.enc.wo", 390, 1024, 1024), ("17.enc.fc1", 390, 1024, 4096), ("17.enc.fc2", 390, 4096, 1024),
               ("conv2.30s", 48000, 4320, 480), ("conv3.30s", 12000, 4320, 480)]
+if len(sys.argv) > 1 and sys.argv[1] == "batch":   # the batched throughput path: 8 / 64 units of 30 s (1.7B), 60 segments of 20 s (0.6B)
+    shapes = [("17.pre.qkv", 25856, 2048, 4096), ("17.pre.wo", 25856, 2048, 2048), ("17.pre.gu", 25856, 2048, 12288), ("17.pre.down", 25856, 6144, 2048),
+              ("17.enc.qkv", 3120, 1024, 3072), ("17.enc.wo", 3120, 1024, 1024), ("17.enc.fc1", 3120, 1024, 4096), ("17.enc.fc2", 3120, 4096, 1024),
+              ("conv2.8x30", 192000, 4320, 480), ("conv3.8x30", 48000, 4320, 480), ("convout", 3120, 7680, 1024),
+              ("06.pre.gu", 16440, 1024, 6144), ("06.pre.down", 16440, 3072, 1024), ("06.enc.fc1", 3120, 896, 3584),
+              ("dec.qkv.b64", 64, 2048, 4096), ("dec.wo.b64", 64, 2048, 2048), ("dec.gu.b64", 64, 2048, 12288), ("dec.down.b64", 64, 6144, 2048), ("dec.head.b64", 64, 2048, 151936),
+              ("dec06.gu.b60", 60, 1024, 6144), ("dec06.head.b60", 60, 1024, 151936), ("big", 8192, 4096, 8192)]
+def pipeline_mode(name):   # the epilogue each shape has in the pipeline: 0 f32 store, 1 residual add, 2 GELU -> hi/lo planes, 3 SwiGLU -> hi/lo planes
+    if ".gu" in name: return 3
+    if "fc1" in name or name.startswith("conv2") or name.startswith("conv3"): return 2
+    if ".wo" in name or ".down" in name or "fc2" in name: return 1
+    return 0
 for name, M, K, N in shapes:
     us = C.c_double(0)
-    rc = f(eng.ctx, M, K, N, 64, 0, C.byref(us))
+    rc = f(eng.ctx, M, K, N, 64, pipeline_mode(name), C.byref(us))
     mb = 2.0 * N * K / 1e6
-    print(f"{name:9s} M={M:4d} K={K:5d} N={N:5d}  {us.value:8.1f} us   weights {mb:6.1f} MB -> {mb / us.value * 1e3 / 1e3:6.2f} TB/s   {2.0*M*N*K*2/us.value/1e6:7.1f} TFLOP/s(hi+lo)" if rc == 0 else f"{name} failed {eng._err()}")
+    print(f"{name:14s} M={M:6d} K={K:5d} N={N:5d}  {us.value:8.1f} us   weights {mb:6.1f} MB -> {mb / us.value * 1e3 / 1e3:6.2f} TB/s   {2.0*M*N*K/us.value/1e6:7.1f} TFLOP/s algorithmic (x2 issued)" if rc == 0 else f"{name} failed {eng._err()}")
