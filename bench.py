@@ -14,6 +14,10 @@ prefill -> greedy decode of `max_new` tokens (mel + encode + prefill + decode = 
   roofline  decode-step launch: algorithmic bytes (decoder weights + lm_head + KV read) / device time
   cpu_baseline  the reference's own CPU implementation (oracle/_ref) timed on this host, rank 0
 
+  roofline_0p6b  the same decode roofline on the north-star's target model (0.6B, configs[0] workload)
+  extra.strong   the splits BASELINE.json names, on the same N ranks: configs[2] (1 h recording, -S 20 segments sharded)
+                 and configs[4] (256 x 30 s utterances sharded), strong scaling, through qasr_cuda_transcribe_batch
+
 `--impl reference` times the reference's CPU implementation instead (rank 0 only).
 Multi-GPU: utterances are independent -> one process per GPU, no data-path collective (weak scaling).
 """
@@ -59,19 +63,23 @@ def peaks():
 
 
 def ncu_traffic_per_step(variant):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel per greedy step, from the committed
-    `ncu --set full` capture (profiles/r01_stream_ncu_summary.json, taken on the 1.7B workload); None otherwise."""
+    """(dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel per greedy step, where that number comes from).
+    It is NOT measured in this run: it is read from the committed `ncu --set full` capture of the same kernel on the 1.7B
+    workload (profiles/r01_stream_ncu_summary.json); None for other models."""
     p = os.path.join(ROOT, "profiles", "r01_stream_ncu_summary.json")
     if variant != "1.7b" or not os.path.exists(p):
-        return None
-    return float(json.load(open(p))["dram_bytes_per_step"])
+        return None, None
+    return float(json.load(open(p))["dram_bytes_per_step"]), "profiles/r01_stream_ncu_summary.json (committed ncu --set full capture, not re-measured in this run)"
 
 
 def gemm_rooflines(eng):
-    """Secondary rooflines of the tcgen05 GEMM path (north_star items 2-3), device-timed by the library's own hook
-    (CUDA-graph replay of 64 launches): the prefill GEMM of this workload against the HBM roofline (a weight stream at
-    M = 61) and a batched-encoder / large shape against the measured (burst) bf16 tensor peak (hi+lo operand planes: two
-    MMAs per k-block are issued and counted)."""
+    """Secondary rooflines of the tcgen05 GEMM path (north_star items 2-3), device-timed by the library's own hook (CUDA
+    -graph replay of 64 launches, hashed non-zero operands, the epilogue the shape has in the pipeline).  Shapes are ones
+    the API launches: the prefill gate/up GEMM of this workload (M = 61: a weight stream, HBM roofline) and GEMMs of
+    qasr_cuda_transcribe_batch on 30 s utterances (1.7B): encoder fc1 of one 8-utterance encoder pass (M = 3120) and the
+    prefill gate/up / down of a 64-utterance group (M = 25856).  Tensor-bound shapes report BOTH fractions of the measured
+    bf16 peak: `frac_algorithmic` counts 2*M*N*K, `frac_issued` counts the two MMAs per k-block that the
+    hi/lo split of the f32 activations issues (ids parity with the f32-activation reference costs exactly that factor)."""
     import ctypes as C
     f = eng.lib.qasr_debug_gemm_bench
     f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
@@ -79,17 +87,20 @@ def gemm_rooflines(eng):
     peaks_d = json.load(open(p)) if os.path.exists(p) else {}
     hbm, tf = float(peaks_d.get("hbm_gbs", 6650.0)), float(peaks_d.get("bf16_tflops", 2250.0))  # burst figure: these kernels are timed alone
     out = []
-    for name, M, K, N, bound in (("prefill gate/up, M=61", 61, 2048, 12288, "hbm"), ("encoder fc1, 16 x 30 s batched, M=6240", 6240, 1024, 4096, "tensor"),
-                                 ("8192 x 8192 x 4096", 8192, 4096, 8192, "tensor")):
+    for name, M, K, N, mode, bound in (("prefill gate/up, M=61", 61, 2048, 12288, 3, "hbm"),
+                                       ("batched encoder fc1 (8 x 30 s), M=3120", 3120, 1024, 4096, 2, "tensor"),
+                                       ("batched prefill gate/up (64 x 30 s), M=25856", 25856, 2048, 12288, 3, "tensor"),
+                                       ("batched prefill down (64 x 30 s), M=25856", 25856, 6144, 2048, 1, "tensor")):
         us = C.c_double(0)
-        if f(eng.ctx, M, K, N, 64, 0, C.byref(us)) != 0 or us.value <= 0:
+        if f(eng.ctx, M, K, N, 64, mode, C.byref(us)) != 0 or us.value <= 0:
             continue
         if bound == "hbm":
             ach = 2.0 * N * K / us.value / 1e3
             out.append({"shape": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "us": us.value})
         else:
-            ach = 2.0 * 2.0 * M * N * K / us.value / 1e6
-            out.append({"shape": name, "bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s (hi+lo MMAs)", "frac": ach / tf, "us": us.value})
+            alg = 2.0 * M * N * K / us.value / 1e6
+            out.append({"shape": name, "bound": "tensor", "achieved": alg, "peak": tf, "unit": "TFLOP/s (2MNK)", "frac": alg / tf,
+                        "frac_algorithmic": alg / tf, "frac_issued": 2.0 * alg / tf, "us": us.value})
     return out
 
 
@@ -218,6 +229,24 @@ def main_multi(args, rank, local_rank, world):
     if dist is not None:
         dist.barrier()
     eng = pkg.QasrCuda(local_rank).load(pkg.ensure_model_dir(variant))
+    out = measure_multi(pkg, eng, args.workload, rank, local_rank, world, dist, recording_sec=args.recording_sec, utterances=args.utterances,
+                        no_batch=args.no_batch, steps=max(1, min(args.steps, 3)))
+    if rank == 0:
+        print(json.dumps(out))
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def measure_multi(pkg, eng, workload, rank, local_rank, world, dist, recording_sec=3600.0, utterances=256, no_batch=False, steps=1):
+    """One of configs[2..4] on the `world` ranks of this job (units sharded, no data-path collective); returns the result
+    dict on rank 0 (None elsewhere).  Strong scaling for configs[2] / [4] (a fixed job split over the ranks), weak for
+    configs[3] (one stream per rank).  Timing: max over ranks of the device time (CUDA events on the library's stream) and
+    of the wall clock around the same host-buffer calls."""
+    variant, desc = MULTI[workload]
+    seg = pkg.segments
 
     def barrier():
         if dist is not None:
@@ -226,70 +255,70 @@ def main_multi(args, rank, local_rank, world):
             torch.cuda.synchronize()
 
     extra = {}
-    if args.workload == "cfg3":
-        rec = pkg.synth_audio(args.recording_sec, seed=0)
+    lat = []
+    if workload == "cfg3":
+        rec = pkg.synth_audio(recording_sec, seed=0)
         ranges = seg.split_segments(rec, 20.0, 3.0, max_splits=None)  # the reference stops at 127 splits (qwen_asr.c:968): lifted
         lo, hi = seg.shard_range(len(ranges), rank, world)
         mine = ranges[lo:hi]
         audio_total = len(rec) / 16000.0
         units = len(ranges)
-
         units_mine = [seg.pad_short(np.ascontiguousarray(rec[a:b], np.float32)) for a, b in mine]
         caps_mine = [seg.tokens_cap(b - a) for a, b in mine]
 
         def one_pass():
-            if args.no_batch:
-                return seg.transcribe_segments(eng, rec, mine)
+            if no_batch:
+                return [r[0] for r in seg.transcribe_segments(eng, rec, mine)]
             return eng.transcribe_batch(units_mine, caps_mine)[0]
         scaling = "strong"
         h2d = sum(b - a for a, b in mine) * 4
-        d2h = sum(seg.tokens_cap(b - a) for a, b in mine) * 4
+        d2h = sum(caps_mine) * 4
+        kv_avg = 9 + 260 + 6 + 44.0
         extra["segments"] = units
-    elif args.workload == "cfg5":
-        n_utt = args.utterances
+    elif workload == "cfg5":
+        n_utt = utterances
         lo, hi = seg.shard_range(n_utt, rank, world)
-        utts = [pkg.synth_audio(30.0, seed=i)[:480000] for i in range(lo, hi)]
+        units_mine = [pkg.synth_audio(30.0, seed=i)[:480000] for i in range(lo, hi)]
         audio_total = 30.0 * n_utt
         units = n_utt
 
         def one_pass():
-            if args.no_batch:
-                return [eng.transcribe_ids(u, 128) for u in utts]
-            return eng.transcribe_batch(utts, 128)[0]
+            if no_batch:
+                return [eng.transcribe_ids(u, 128)[0] for u in units_mine]
+            return eng.transcribe_batch(units_mine, 128)[0]
         scaling = "strong"
-        h2d = sum(u.nbytes for u in utts)
-        d2h = len(utts) * 128 * 4
+        h2d = sum(u.nbytes for u in units_mine)
+        d2h = len(units_mine) * 128 * 4
+        kv_avg = 9 + 390 + 6 + 64.0
         extra["utterances"] = units
     else:  # cfg4: one stream per rank (sequential data dependence: replicas only)
         rec = pkg.synth_audio(60.0, seed=rank)
         audio_total = 60.0 * world
         units = 30 * world
-        lat = []
+        units_mine = [rec]
 
         def one_pass():
-            if args.no_batch:   # host-driven session (encoder rows and prompt embeddings cross PCIe every chunk)
+            if no_batch:   # host-driven session (encoder rows and prompt embeddings cross PCIe every chunk)
                 sess = pkg.streaming.StreamSession(eng)
                 feed = sess.feed
             else:               # device-resident session: samples in, ids out
                 eng.stream_begin(8.0, 4)
                 feed = eng.stream_feed
-            out = []
+            res = []
             for end in range(32000, len(rec) + 1, 32000):
                 t0 = time.perf_counter()
-                out.append(feed(rec[:end]))
+                res.append(feed(rec[:end]))
                 lat.append((time.perf_counter() - t0) * 1e3)
-            return out
+            return res
         scaling = "weak"
         h2d = int(rec.nbytes)
         d2h = 30 * 32 * 4
+        kv_avg = 300.0
 
-    for _ in range(max(1, min(args.warmup, 1))):  # one full warm-up pass (captures the CUDA graphs of every shape)
-        one_pass()
-    if args.workload == "cfg4":
-        lat.clear()
+    one_pass()  # one full warm-up pass (captures the CUDA graphs of every shape, sizes every workspace)
+    lat.clear()
     eng.decode_stats(reset=True)
     launches0 = eng.launch_count
-    steps = max(1, min(args.steps, 3))
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -303,44 +332,99 @@ def main_multi(args, rank, local_rank, world):
     clocks = sampler.stop()
     launches = eng.launch_count - launches0
     dec_steps, dec_ms = eng.decode_stats(reset=True)
+    if workload == "cfg4":
+        n_tokens = sum(len(r["ids"]) for r in res)   # ids of the last pass; every pass produces the same count
+        groups, group = 1, 1
+    else:
+        n_tokens = sum(len(r) for r in res)
+        groups, group = (len(units_mine), 1) if no_batch else eng.batch_plan(len(units_mine))
+    mine_ms = dev_ms
     if dist is not None:
         import torch
-        t = torch.tensor([dev_ms, wall_ms, float(launches), dec_ms / max(dec_steps, 1)], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_ms, wall_ms, float(launches), float(n_tokens) * steps / max(dec_ms, 1e-9) * 1e3, dec_ms / max(dec_steps, 1), float(group), -dev_ms],
+                         device="cuda", dtype=torch.float64)
         mx, sm = t.clone(), t.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms, wall_ms, launches, dec_ms_per_step = float(mx[0]), float(mx[1]), int(sm[2]), float(mx[3])
+        dev_ms, wall_ms, launches, tok_s, dec_ms_per_step, group, fastest_ms = float(mx[0]), float(mx[1]), int(sm[2]), float(sm[3]), float(mx[4]), int(mx[5]), -float(mx[6])
+        mean_ms = float(sm[0]) / world
     else:
-        dec_ms_per_step = dec_ms / max(dec_steps, 1)
-    seqs_per_step = 1 if (args.no_batch or args.workload == "cfg4") else eng.max_batch
-    if rank == 0:
-        peak, peak_src = peaks()
-        kv_avg = 300.0 if args.workload != "cfg5" else 470.0
-        step_bytes = decode_bytes_per_step(eng.cfg, kv_avg)
-        achieved = step_bytes / (dec_ms_per_step * 1e-3) / 1e9
-        out = {"metric": "realtime_factor", "value": audio_total * steps / (dev_ms / 1e3), "unit": "x realtime (audio s / wall s)", "n_gpus": world,
-               "steps": steps, "warmup": 1, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-               "dtype": "bf16", "data": "synthetic",
-               "config": {"workload": desc, "audio_seconds": audio_total, "units": units, "parallelism": f"dp{world} (independent units, no collective)",
-                          "l2": "inputs larger than L2: every decode step streams >= 1.19 GB of weights", "weights": "random-init synthetic checkpoint (seed 1234)", **extra},
-               "clocks": clocks,
-               "e2e": {"value": audio_total * steps / (wall_ms / 1e3), "unit": "x realtime (audio s / wall s)", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                       "ms_per_step": wall_ms / steps},
-               "gpu_launches": launches, "decoder_tok_s": world * 1000.0 / dec_ms_per_step * seqs_per_step,
-               "sequences_per_decode_step": seqs_per_step,
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                            "kernel": "one greedy step of decode_stream_kernel", "bytes_per_launch": step_bytes, "ms_per_launch": dec_ms_per_step}}
-        if args.workload == "cfg4":
-            l = sorted(lat)
-            out["chunk_latency_ms"] = {"p50": l[len(l) // 2], "p95": l[min(len(l) - 1, int(0.95 * len(l)))], "max": l[-1], "chunks": len(l)}
-            out["tokens_per_chunk"] = float(np.mean([len(r["ids"]) for r in res]))
-            out["reused_rows_mean"] = float(np.mean([r["reused"] for r in res]))
-        print(json.dumps(out))
-    eng.close()
+        tok_s, dec_ms_per_step, fastest_ms, mean_ms = n_tokens * steps / max(dec_ms, 1e-9) * 1e3, dec_ms / max(dec_steps, 1), dev_ms, dev_ms
+    if rank != 0:
+        return None
+    peak, peak_src = peaks()
+    w_bytes = decode_bytes_per_step(eng.cfg, 0)
+    kv_bytes = decode_bytes_per_step(eng.cfg, kv_avg) - w_bytes
+    step_bytes = w_bytes + group * kv_bytes          # one pass over the weights + the KV rows of every sequence of the group
+    achieved = step_bytes / (dec_ms_per_step * 1e-3) / 1e9
+    kernel = ("one greedy step of decode_stream_kernel" if group <= eng.max_batch else
+              "one decode step of the batched path: 28 x (4 skinny tcgen05 GEMMs + attn_decode_batch_kernel) + lm_head GEMM + argmax, one CUDA graph")
+    out = {"metric": "realtime_factor", "value": audio_total * steps / (dev_ms / 1e3), "unit": "x realtime (audio s / wall s)", "n_gpus": world,
+           "steps": steps, "warmup": 1, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+           "dtype": "bf16", "data": "synthetic",
+           "config": {"workload": desc, "audio_seconds": audio_total, "units": units, "parallelism": f"dp{world} (independent units, no collective)",
+                      "l2": "inputs larger than L2: every decode step streams >= 1.19 GB of weights", "weights": "random-init synthetic checkpoint (seed 1234)", **extra},
+           "clocks": clocks,
+           "e2e": {"value": audio_total * steps / (wall_ms / 1e3), "unit": "x realtime (audio s / wall s)", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": wall_ms / steps},
+           "gpu_launches": launches, "decoder_tok_s": tok_s, "sequences_per_decode_step": group, "groups_per_rank": groups,
+           "rank_ms": {"slowest": dev_ms / steps, "fastest": fastest_ms / steps, "mean": mean_ms / steps, "imbalance": dev_ms / max(mean_ms, 1e-9)},
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "traffic_source": None, "peak_source": peak_src, "kernel": kernel, "bytes_per_launch": step_bytes,
+                        "bytes_model": f"weights {w_bytes} + {group} sequences x {int(kv_bytes)} (f32 KV rows, ~{int(kv_avg)} cached positions)", "ms_per_launch": dec_ms_per_step}}
+    if workload == "cfg4":
+        l = sorted(lat)
+        out["chunk_latency_ms"] = {"p50": l[len(l) // 2], "p95": l[min(len(l) - 1, int(0.95 * len(l)))], "max": l[-1], "chunks": len(l)}
+        out["tokens_per_chunk"] = float(np.mean([len(r["ids"]) for r in res]))
+        out["reused_rows_mean"] = float(np.mean([r["reused"] for r in res]))
+    return out
+
+
+def strong_block(pkg, eng17, rank, local_rank, world, dist, utterances, recording_sec):
+    """`extra.strong`: the two sharded jobs BASELINE.json names, on the ranks of this run (SCALE record at 1/2/4/8 GPUs).
+    The driver computes scaling efficiency from the per-N values; `rank_ms.imbalance` and `sequences_per_decode_step` name
+    the causes (shard sizes differ by one unit; a smaller shard means fewer sequences per pass over the weights)."""
+    keep = ("value", "ms_per_step", "scaling", "e2e", "decoder_tok_s", "sequences_per_decode_step", "groups_per_rank", "rank_ms", "roofline", "gpu_launches")
+    out = {}
+    r = measure_multi(pkg, eng17, "cfg5", rank, local_rank, world, dist, utterances=utterances)
+    if r is not None:
+        out["configs[4]"] = {"workload": f"{utterances} x 30 s utterances, Qwen3-ASR-1.7B, 128 new tokens each, sharded over {world} GPU(s)", **{k: r[k] for k in keep}}
+    if local_rank == 0:
+        pkg.ensure_model_dir("0.6b")
     if dist is not None:
         dist.barrier()
-        dist.destroy_process_group()
-    return 0
+    eng06 = pkg.QasrCuda(local_rank).load(pkg.ensure_model_dir("0.6b"))
+    try:
+        r = measure_multi(pkg, eng06, "cfg3", rank, local_rank, world, dist, recording_sec=recording_sec)
+        if r is not None:
+            out["configs[2]"] = {"workload": f"{recording_sec:.0f} s recording, -S 20 -W 3 ({r['config']['segments']} segments), Qwen3-ASR-0.6B, sharded over {world} GPU(s)",
+                                 **{k: r[k] for k in keep}}
+        if rank == 0:  # north-star target model: decode roofline of the persistent kernel on configs[0] (11 s, 48 tokens)
+            out["roofline_0p6b"] = single_decode_roofline(pkg, eng06, "cfg1")
+    finally:
+        eng06.close()
+    return out
+
+
+def single_decode_roofline(pkg, eng, workload, steps=8):
+    """Decode roofline of decode_stream_kernel on one staged utterance of `workload` (device time per greedy step)."""
+    variant, n_samples, max_new, desc = WORKLOADS[workload]
+    audio = pkg.synth_audio(n_samples / 16000.0, seed=100)[:n_samples]
+    eng.stage_audio(audio)
+    ids_buf = np.zeros(max_new, np.int32)
+    for _ in range(3):
+        eng.transcribe_staged(max_new, ids_buf)
+    eng.decode_stats(reset=True)
+    for _ in range(steps):
+        _, info = eng.transcribe_staged(max_new, ids_buf)
+    dec_steps, dec_ms = eng.decode_stats(reset=True)
+    peak, peak_src = peaks()
+    ms = dec_ms / max(dec_steps, 1)
+    step_bytes = decode_bytes_per_step(eng.cfg, info["enc_tokens"] + 15 + max_new / 2.0)
+    ach = step_bytes / (ms * 1e-3) / 1e9
+    return {"workload": desc, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "frac_of_8000_nominal": ach / 8000.0,
+            "peak_source": peak_src, "kernel": "one greedy step of decode_stream_kernel", "bytes_per_launch": step_bytes, "ms_per_launch": ms,
+            "decoder_tok_s": 1000.0 / ms, "traffic": None, "traffic_source": None}
 
 
 def main():
@@ -353,6 +437,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--recording-sec", type=float, default=3600.0, help="cfg3: length of the synthetic recording")
     ap.add_argument("--utterances", type=int, default=256, help="cfg5: number of 30 s utterances (whole job)")
+    ap.add_argument("--no-strong", action="store_true", help="default workload: skip the extra.strong block (configs[2] / configs[4] sharded over the ranks) and roofline_0p6b")
     ap.add_argument("--no-batch", action="store_true", help="cfg3/cfg5: one sequence per decode step instead of qasr_cuda_transcribe_batch; cfg4: host-driven session instead of qasr_cuda_stream_feed")
     args = ap.parse_args()
     rank, local_rank, world = dist_env()
@@ -456,6 +541,14 @@ def main():
     else:
         e2e_ms, dec_ms_per_step = e2e_s * 1000.0, dec_ms / max(dec_steps, 1)
 
+    strong = None
+    if not args.no_strong:
+        try:
+            strong = strong_block(pkg, eng, rank, local_rank, world, dist, args.utterances, args.recording_sec)
+        except Exception as ex:  # never lose the headline line to the extra block
+            strong = {"error": str(ex)[:300]}
+            if dist is not None:
+                raise
     if rank == 0:
         ms_per_step = dev_ms / args.steps
         value = world * audio_s / (ms_per_step / 1000.0)
@@ -464,6 +557,7 @@ def main():
         kv_avg = info["enc_tokens"] + 15 + max_new / 2.0  # mean cached positions over the greedy steps
         step_bytes = decode_bytes_per_step(eng.cfg, kv_avg)
         achieved = step_bytes / (dec_ms_per_step * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic_per_step(variant)
         out = {"metric": "realtime_factor", "value": value, "unit": "x realtime (audio s / wall s)", "n_gpus": world,
                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
@@ -475,10 +569,14 @@ def main():
                "stage_ms": {k: v / args.steps for k, v in stage_acc.items()},
                "ids_head": ids[:8],
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": ncu_traffic_per_step(variant), "peak_source": peak_src,
+                            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                             "kernel": "one greedy step of decode_stream_kernel (persistent cooperative kernel, qasr_stream.cu; a launch runs up to 16 steps)",
                             "bytes_per_launch": step_bytes, "ms_per_launch": dec_ms_per_step,
                             "frac_of_8000_nominal": achieved / 8000.0}}
+        if strong is not None:
+            if "roofline_0p6b" in strong:
+                out["roofline_0p6b"] = strong.pop("roofline_0p6b")
+            out["extra"] = {"strong": strong}
         try:
             out["gemm_rooflines"] = gemm_rooflines(eng)
         except Exception as ex:  # debug hook missing: the headline does not depend on it

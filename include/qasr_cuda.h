@@ -145,12 +145,17 @@ int qasr_cuda_transcribe_ids(qasr_ctx_t *ctx, const float *samples, int n_sample
  * 151704) (+ past-text tokens + 151704).  n_suf >= 1. */
 int qasr_cuda_set_prompt(qasr_ctx_t *ctx, const int *pre_ids, int n_pre, const int *suf_ids, int n_suf);
 
-/* Independent units (the segments of -S mode, reference qwen_asr.c:941-1103, or separate utterances) decoded
- * together: up to qasr_cuda_max_batch() sequences share every decode step (one pass over the weights serves all
- * of them); front end, encoder and prefill run per unit.  samples[i] / n_samples[i] / max_new[i] describe unit i;
- * unit i's ids go to out_ids + i*ids_stride (max_new[i] <= ids_stride), its count to out_n[i].  Ids are identical
- * to qasr_cuda_transcribe_ids on the same unit.  timings_ms (nullable) = {mel, encoder, prefill, decode} totals. */
+/* Independent units (the segments of -S mode, reference qwen_asr.c:941-1103 with --past-text no, or separate utterances)
+ * transcribed together.  Up to qasr_cuda_max_batch() units (4 for 0.6B, 2 for 1.7B) share the persistent decode kernel
+ * (one pass over the weights per step serves all of them; front end, encoder and prefill per unit).  More units take the
+ * batched throughput path: encoder, prefill and every decode step run as GEMMs over the rows of a whole group (up to 128
+ * units, QASR_BATCH_MAX), attention per unit over a pooled KV cache.  samples[i] / n_samples[i] / max_new[i] describe unit
+ * i; its ids go to out_ids + i*ids_stride (max_new[i] <= ids_stride), its count to out_n[i].  Ids are those of
+ * qasr_cuda_transcribe_ids on the same unit.  timings_ms (nullable) = {mel, encoder, prefill, decode} totals. */
 int qasr_cuda_max_batch(const qasr_ctx_t *ctx);
+/* How a call with `count` units would be split: *out_groups groups, the first (largest) of *out_group_size units = the
+ * sequences that share one pass over the weights in every decode step (benchmark reporting). */
+int qasr_cuda_batch_plan(const qasr_ctx_t *ctx, int count, int *out_groups, int *out_group_size);
 int qasr_cuda_transcribe_batch(qasr_ctx_t *ctx, const float *const *samples, const int *n_samples, int count,
                                const int *max_new, int ids_stride, int *out_ids, int *out_n, double *timings_ms);
 

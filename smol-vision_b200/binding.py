@@ -49,6 +49,7 @@ SIGNATURES = {
     "qasr_cuda_transcribe_ids": (ci, [vp, f32p, ci, ci, i32p, ip, vp, ip]),
     "qasr_cuda_set_prompt": (ci, [vp, i32p, ci, i32p, ci]),
     "qasr_cuda_max_batch": (ci, [vp]),
+    "qasr_cuda_batch_plan": (ci, [vp, ci, ip, ip]),
     "qasr_cuda_transcribe_batch": (ci, [vp, vp, i32p, ci, i32p, ci, i32p, i32p, vp]),
     "qasr_cuda_stream_begin": (ci, [vp, cf, ci]),
     "qasr_cuda_stream_feed": (ci, [vp, f32p, ci, ci, i32p, ip, ip, ip]),
@@ -263,6 +264,12 @@ class QasrCuda:
     @property
     def max_batch(self):
         return int(self.lib.qasr_cuda_max_batch(self.ctx))
+
+    def batch_plan(self, count):
+        """(number of groups, size of the largest group) a transcribe_batch call with `count` units would use."""
+        g, b = ci(0), ci(0)
+        self._ck(self.lib.qasr_cuda_batch_plan(self.ctx, int(count), C.byref(g), C.byref(b)))
+        return g.value, b.value
 
     def transcribe_batch(self, units, max_new):
         """Independent segments / utterances decoded together (up to `max_batch` per decode step).

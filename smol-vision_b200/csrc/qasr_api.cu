@@ -1204,6 +1204,20 @@ int qasr_cuda_max_batch(const qasr_ctx_t *c) {
     return c->use_stream ? stream_max_seqs(c->H, c->I) : 1;
 }
 
+// How qasr_cuda_transcribe_batch would split `count` units: number of groups and the size of the first (largest) one
+// = sequences that share one pass over the weights in every decode step.
+int qasr_cuda_batch_plan(const qasr_ctx_t *c, int count, int *out_groups, int *out_group_size) {
+    if (!c || !c->loaded || count < 0) return set_err(QASR_ERR_ARG, "bad argument");
+    const int maxb = qasr_cuda_max_batch(c);
+    const char *e = getenv("QASR_BATCH");
+    const bool gemm_path = e && !strcmp(e, "gemm") ? count > 1 : (e && !strcmp(e, "stream") ? false : count > maxb);
+    if (gemm_path) return batch_plan(count, out_groups, out_group_size);
+    const int B = count >= 4 && maxb >= 4 ? 4 : (count >= 2 && maxb >= 2 ? 2 : (count > 0 ? 1 : 0));
+    if (out_group_size) *out_group_size = B;
+    if (out_groups) { int g = 0; for (int i = 0; i < count; g++) i += count - i >= 4 && maxb >= 4 ? 4 : (count - i >= 2 && maxb >= 2 ? 2 : 1); *out_groups = g; }
+    return 0;
+}
+
 static int transcribe_group(qasr_ctx_t *c, const float *const *samples, const int *n_samples, int B, const int *max_new, int ids_stride,
                             int *out_ids, int *out_n, double *tm) {
     const int *PRE = c ? c->pre_ids.data() : nullptr, *SUF = c ? c->suf_ids.data() : nullptr; // qwen_asr.c:388-396 (+ prompt / language tokens)

@@ -66,11 +66,24 @@ static int batch_state(qasr_ctx_t *c, BatchState **out) {
 
 // Largest group the batched path takes at once.  The per-step weight traffic is shared by the whole group while the KV
 // read grows with it (229 376 B per cached position per sequence, f32 like the reference), so past a few dozen sequences
-// the step time is dominated by attention; 64 keeps the skinny GEMMs in their 64-column variant.
+// the step time is dominated by attention: measured on one B200 (1.7B, 30 s units) 12.2k / 17.5k / 24.2k tokens/s at 32 / 64 / 128
+// sequences per step (0.6B, 20 s units: 25.5k at 60, 35.8k at 120).
 static int batch_group_max() {
     static int v = 0;
-    if (!v) { const char *e = getenv("QASR_BATCH_MAX"); v = e && atoi(e) >= 1 ? atoi(e) : 64; if (v > BatchState::MAX_UNITS) v = BatchState::MAX_UNITS; }
+    if (!v) { const char *e = getenv("QASR_BATCH_MAX"); v = e && atoi(e) >= 1 ? atoi(e) : 128; if (v > BatchState::MAX_UNITS) v = BatchState::MAX_UNITS; }
     return v;
+}
+// equal-sized groups: 140 units with a group limit of 128 run as 70 + 70, not 128 + 12
+static int batch_group_size(int remaining) {
+    const int gmax = batch_group_max(), groups = (remaining + gmax - 1) / gmax;
+    return (remaining + groups - 1) / groups;
+}
+int batch_plan(int count, int *out_groups, int *out_group_size) {
+    int groups = 0, first = 0;
+    for (int i = 0; i < count;) { const int B = batch_group_size(count - i); if (!groups) first = B; groups++; i += B; }
+    if (out_groups) *out_groups = groups;
+    if (out_group_size) *out_group_size = first;
+    return 0;
 }
 
 struct GroupPlan {
@@ -291,11 +304,8 @@ int batch_transcribe(qasr_ctx_t *c, const float *const *samples, const int *n_sa
                      int *out_ids, int *out_n, double *timings_ms) {
     BatchState *b = nullptr;
     CKR(batch_state(c, &b));
-    const int gmax = batch_group_max();
     for (int i = 0; i < count;) {
-        // equal-sized groups: 70 units with a group limit of 64 run as 35 + 35, not 64 + 6
-        const int groups = (count - i + gmax - 1) / gmax;
-        const int B = (count - i + groups - 1) / groups;
+        const int B = batch_group_size(count - i);
         CKR(run_group(c, b, samples + i, n_samples + i, B, max_new + i, ids_stride, out_ids + (size_t)i * ids_stride, out_n + i, timings_ms));
         i += B;
     }

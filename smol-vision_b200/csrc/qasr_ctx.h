@@ -174,3 +174,4 @@ int gemm(qasr_ctx_t *c, const bf16_t *a_hi, const bf16_t *a_lo, int M, int K, co
 int batch_transcribe(qasr_ctx_t *c, const float *const *samples, const int *n_samples, int count, const int *max_new, int ids_stride,
                      int *out_ids, int *out_n, double *timings_ms);
 void batch_release(qasr_ctx_t *c);
+int batch_plan(int count, int *out_groups, int *out_group_size);

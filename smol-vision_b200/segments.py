@@ -19,18 +19,17 @@ def find_split_point(samples, target_sample, search_sec):
     lo = max(0, target_sample - half)
     hi = min(n, target_sample + half)
     win = (ENERGY_WINDOW_MS * SAMPLE_RATE) // 1000  # 1600
-    best_energy = np.float32(1e30)
-    best_center = target_sample
-    sq = samples.astype(np.float32) ** 2
-    pos = lo
-    while pos + win <= hi:
-        end = min(pos + win, n)
-        energy = np.float32(sq[pos:end].sum(dtype=np.float32) / np.float32(end - pos))
-        if energy < best_energy:
-            best_energy = energy
-            best_center = pos + (end - pos) // 2
-        pos += win // 2
-    return best_center
+    if hi - lo < win:
+        return target_sample
+    # windows start at lo, lo + win/2, ... while pos + win <= hi; the first window with the strictly lowest mean energy wins
+    sq = samples[lo:hi].astype(np.float32) ** 2
+    starts = np.arange(0, hi - lo - win + 1, win // 2)
+    view = np.lib.stride_tricks.sliding_window_view(sq, win)[starts]
+    energy = view.sum(axis=1, dtype=np.float32) / np.float32(win)
+    best = int(np.argmin(energy))
+    if not energy[best] < np.float32(1e30):
+        return target_sample
+    return lo + int(starts[best]) + win // 2
 
 
 def split_segments(samples, segment_sec, search_sec=3.0, max_splits=REFERENCE_MAX_SPLITS):
