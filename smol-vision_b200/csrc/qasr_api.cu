@@ -684,8 +684,10 @@ int encode_units_device(qasr_ctx_t *c, const float *d_mel, int mel_stride, const
     // workspace carve (all offsets 256-byte aligned)
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-    const size_t o_act1 = carve((size_t)tot1 * 480 * 2 * 2), o_col2 = carve((size_t)tot2 * 4320 * 2 * 2),
-                 o_act2 = carve((size_t)tot2 * 480 * 2 * 2), o_col3 = carve((size_t)tot3 * 4320 * 2 * 2),
+    static int conv_im2col = -1; // QASR_CONV_IM2COL=1: round 1's materialised patch matrices (A/B runs)
+    if (conv_im2col < 0) { const char *e = getenv("QASR_CONV_IM2COL"); conv_im2col = e && e[0] == '1'; }
+    const size_t o_act1 = carve((size_t)tot1 * 480 * 2 * 2), o_col2 = carve(conv_im2col ? (size_t)tot2 * 4320 * 2 * 2 : 0),
+                 o_act2 = carve((size_t)tot2 * 480 * 2 * 2), o_col3 = carve(conv_im2col ? (size_t)tot3 * 4320 * 2 * 2 : 0),
                  o_act3 = carve((size_t)tot3 * 480 * 2 * 2), o_x = carve((size_t)T * d * 4),
                  o_xn = carve((size_t)T * d * 2 * 2), o_qkv = carve((size_t)T * 3 * d * 4),
                  o_att = carve((size_t)T * d * 2 * 2), o_mid = carve((size_t)T * F * 2 * 2);
@@ -700,9 +702,18 @@ int encode_units_device(qasr_ctx_t *c, const float *d_mel, int mel_stride, const
     const bool two = c->nsplit == 2;
     // conv stem, reference qwen_asr_encoder.c:221-276
     launch_conv1(s, d_mel, mel_stride > 0 ? mel_stride : frames, c->c1w, c->c1b, g, HI(o_act1), two ? LO(o_act1, (size_t)tot1 * 480) : nullptr);
+    if (!conv_im2col) { // implicit GEMM: the kernel gathers the 3 x 3 patches itself
+        GemmEpilogue e2;
+        e2.mode = QASR_GEMM_GELU_SPLIT; e2.out_f32 = nullptr; e2.out_hi = HI(o_act2); e2.out_lo = two ? LO(o_act2, (size_t)tot2 * 480) : nullptr; e2.bias = c->c2b; e2.ldo = 480;
+        if (launch_conv_gemm_tc(s, HI(o_act1), two ? LO(o_act1, (size_t)tot1 * 480) : nullptr, g, 2, c->c2w, e2) != 0) return set_err(QASR_ERR_CUDA, "%s", gemm_tc_error());
+        GemmEpilogue e3 = e2;
+        e3.out_hi = HI(o_act3); e3.out_lo = two ? LO(o_act3, (size_t)tot3 * 480) : nullptr; e3.bias = c->c3b;
+        if (launch_conv_gemm_tc(s, HI(o_act2), two ? LO(o_act2, (size_t)tot2 * 480) : nullptr, g, 3, c->c3w, e3) != 0) return set_err(QASR_ERR_CUDA, "%s", gemm_tc_error());
+        c->launches += 2;
+    } else {
     launch_im2col_stage(s, HI(o_act1), HI(o_col2), g, 2);
     if (two) launch_im2col_stage(s, LO(o_act1, (size_t)tot1 * 480), LO(o_col2, (size_t)tot2 * 4320), g, 2);
-    c->launches += two ? 3 : 2;
+    c->launches += two ? 2 : 1;
     CKR(gemm(c, HI(o_col2), LO(o_col2, (size_t)tot2 * 4320), tot2, 4320, c->c2w, 480, QASR_GEMM_GELU_SPLIT, nullptr,
              HI(o_act2), LO(o_act2, (size_t)tot2 * 480), c->c2b, 480));
     launch_im2col_stage(s, HI(o_act2), HI(o_col3), g, 3);
@@ -710,6 +721,7 @@ int encode_units_device(qasr_ctx_t *c, const float *d_mel, int mel_stride, const
     c->launches += two ? 2 : 1;
     CKR(gemm(c, HI(o_col3), LO(o_col3, (size_t)tot3 * 4320), tot3, 4320, c->c3w, 480, QASR_GEMM_GELU_SPLIT, nullptr,
              HI(o_act3), LO(o_act3, (size_t)tot3 * 480), c->c3b, 480));
+    }
     float *x = reinterpret_cast<float *>(B + o_x);
     CKR(gemm(c, HI(o_act3), LO(o_act3, (size_t)tot3 * 480), T, 7680, c->conv_out, d, QASR_GEMM_F32, x, nullptr, nullptr, nullptr, d));
     launch_add_rows(s, x, c->pe, d_rowpos, T, d);

@@ -176,11 +176,11 @@ static int run_group(qasr_ctx_t *c, BatchState *b, const float *const *samples, 
         c->launches += 3 * B;
     }
     CK(cudaEventRecord(ev[2], s));
-    // ---- encoder, in sub-groups bounded by the im2col workspace (~8 x 30 s of audio per pass)
+    // ---- encoder, in sub-groups of ~16 x 30 s of audio per pass (bounds the activation workspace: the stage-1 conv output is 184 MB per 30 s)
     if (b->enc.reserve((size_t)g.T_total * H * 4)) return set_err(QASR_ERR_NOMEM, "batch encoder output");
     {
         static int enc_frames_max = 0;
-        if (!enc_frames_max) { const char *e = getenv("QASR_BATCH_ENC_FRAMES"); enc_frames_max = e && atoi(e) >= 100 ? atoi(e) : 24000; }
+        if (!enc_frames_max) { const char *e = getenv("QASR_BATCH_ENC_FRAMES"); enc_frames_max = e && atoi(e) >= 100 ? atoi(e) : 48000; }
         // the units of a pass must be contiguous along the mel frame axis: conv1 reads mel[ih * F_total + frame]
         int u0 = 0, f0 = 0;
         while (u0 < B) {

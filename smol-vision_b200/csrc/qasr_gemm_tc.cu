@@ -216,10 +216,26 @@ __device__ __forceinline__ void tc_epilogue_block(const GemmEpilogue &e, const f
 // Persistent kernel: one CTA per SM walks the tile list; the accumulator is double-buffered in TMEM (2 x BN columns), so
 // the epilogue of tile i (warps 2-5) overlaps the mainloop of tile i+1 (warps 0-1) and the operand ring never drains
 // between tiles.
-template <int BN, int STAGES = (BN > 128 ? 3 : TC_STAGES)>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+//
+// GATHER = true is the implicit-GEMM form of the conv stem (stages 2 and 3, reference qwen_conv2d + im2col,
+// qwen_asr_kernels.c:566-590,643-685): the A operand is not a matrix in memory.  Row `pos` of the GEMM is an output
+// position (chunk, ow, oh), its K = 9 x 480 columns are the 3 x 3 input patch (tap-major, channel-minor) of the
+// position-major activation act_in[(off_in[c] + iw * Hin + ih)][480]; four extra warps (thread = A row) gather every
+// 64-column k-block straight into the 128B-swizzled operand stage with 16-byte cp.async (zero-fill for the padding at
+// chunk edges and past K), wait for their own copies, fence them towards the async proxy and arrive on the stage's
+// full barrier; the weights still arrive by TMA.  Nothing is materialised (round 1 wrote and re-read the 9 x expanded
+// patch matrix: 2.5 GB per launch at 8 x 30 s).
+struct ConvGather {
+    const bf16_t *src_hi, *src_lo;   // activation planes of the previous stage, [positions][480]
+    const int *w0s, *off_in, *off_out;
+    int n_chunks, Hin;               // Hin = 64 (stage 2) or 32 (stage 3); Hout = Hin / 2
+};
+#define TC_GATHER_THREADS 128
+
+template <int BN, bool GATHER = false, int STAGES = (BN > 128 ? 3 : TC_STAGES)>
+__global__ void __launch_bounds__(TC_THREADS + (GATHER ? TC_GATHER_THREADS : 0), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-               const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmB, const TcParams p, const ConvGather cg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stage][A_hi 16K | A_lo 16K | B BN*128] then barriers
     constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;
@@ -241,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         if (p.nsplit == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], GATHER ? 1 + TC_GATHER_THREADS : 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < 2; s++) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -259,7 +275,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const uint32_t tx = (p.nsplit == 2 ? 2 * A_BYTES : A_BYTES) + B_BYTES;
+            const uint32_t tx = GATHER ? B_BYTES : (p.nsplit == 2 ? 2 * A_BYTES : A_BYTES) + B_BYTES;
             uint32_t it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int m0 = (t / p.tiles_n) * TC_BM, n0 = (t % p.tiles_n) * BN;
@@ -268,8 +284,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                     mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
                     uint8_t *st = smem + s * STAGE_BYTES;
                     mbar_expect_tx(&full_bar[s], tx);
-                    tma_load_2d(st, &tmA_hi, &full_bar[s], kb * TC_BK, m0);
-                    if (p.nsplit == 2) tma_load_2d(st + A_BYTES, &tmA_lo, &full_bar[s], kb * TC_BK, m0);
+                    if (!GATHER) {
+                        tma_load_2d(st, &tmA_hi, &full_bar[s], kb * TC_BK, m0);
+                        if (p.nsplit == 2) tma_load_2d(st + A_BYTES, &tmA_lo, &full_bar[s], kb * TC_BK, m0);
+                    }
                     tma_load_2d(st + 2 * A_BYTES, &tmB, &full_bar[s], kb * TC_BK, n0);
                 }
             }
@@ -308,6 +326,63 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 tc_commit(&tmem_full_bar[as]); // accumulator of this tile complete
             }
         }
+    } else if (GATHER && warp >= 6) {
+        // ===== A-operand gather warps 6..9 (conv stem): thread = row r of the tile =====
+        const int r = threadIdx.x - TC_THREADS;
+        const int Hin = cg.Hin, Hout = Hin >> 1;
+        const uint32_t row_sm = (uint32_t)r * 128u, sw = (uint32_t)(r & 7);
+        // A gather thread publishes k-block i as soon as its copies have landed and never blocks on a ring slot with more than
+        // DEPTH k-blocks unpublished: with S stages the MMA warp consumes block i while i+1 is ready and i+2 .. i+S-1 are in flight.
+        constexpr int DEPTH = STAGES - 2;
+        uint32_t it = 0, arrived = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int pos = (t / p.tiles_n) * TC_BM + r;
+            int oh = 0, ow = 0, in0 = 0, Win = 0; // Win = 0 (row past M): every tap is padding
+            if (pos < p.M) {
+                int lo = 0, hi = cg.n_chunks - 1; // chunk containing pos
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (cg.off_out[mid] <= pos) lo = mid; else hi = mid - 1;
+                }
+                const int w0 = cg.w0s[lo], w1 = (w0 - 1) / 2 + 1, w2 = (w1 - 1) / 2 + 1;
+                Win = Hin == 64 ? w1 : w2;
+                const int local = pos - cg.off_out[lo];
+                ow = local / Hout; oh = local - ow * Hout; in0 = cg.off_in[lo];
+            }
+            // element offset of the 480-channel vector of a tap, -1 = zero padding (chunk edge, frequency edge, tap >= 9)
+            auto tap_base = [&](int tap) {
+                const int ki = tap / 3, ih = 2 * oh - 1 + ki, iw = 2 * ow - 1 + (tap - 3 * ki);
+                return (tap < 9 && ih >= 0 && ih < Hin && iw >= 0 && iw < Win) ? (in0 + iw * Hin + ih) * 480 : -1;
+            };
+            for (int kb = 0; kb < num_kb; kb++, it++) {
+                const int s = it % STAGES;
+                mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                const uint32_t st = smem_u32(smem + s * STAGE_BYTES) + row_sm;
+                const int k0 = kb * TC_BK, tapA = k0 / 480, cA = k0 - tapA * 480; // a k-block spans at most two taps (480 = 7.5 x 64)
+                const int bA = tap_base(tapA), bB = tap_base(tapA + 1);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int ch = cA + 8 * j;                      // channel inside tap A, or 480 + channel inside tap B
+                    const int b = ch < 480 ? bA : bB, c = ch < 480 ? ch : ch - 480;
+                    const bool ok = b >= 0 && k0 + 8 * j < p.K;
+                    const size_t off = ok ? (size_t)b + c : 0;
+                    const uint32_t dst = st + ((uint32_t)(j ^ sw) << 4);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(cg.src_hi + off), "r"(ok ? 16 : 0) : "memory");
+                    if (p.nsplit == 2)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + A_BYTES), "l"(cg.src_lo + off), "r"(ok ? 16 : 0) : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                if (it >= DEPTH) { // the copies of k-block it - DEPTH have landed: publish them to the async proxy (tcgen05 reads)
+                    asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH) : "memory");
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&full_bar[arrived % STAGES]);
+                    arrived++;
+                }
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (; arrived < it; arrived++) mbar_arrive(&full_bar[arrived % STAGES]);
     } else {
         // ===== epilogue warps 2..5: TMEM lane quarter q = rows m0 + 32 q .. + 31, thread = row =====
         const int q = warp & 3;
@@ -663,6 +738,8 @@ int gemm_tc_init(void) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_skinny_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk_smem_bytes<64, 6>());
     if (e == cudaSuccess)
@@ -840,13 +917,51 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
     { static int sm_count[32] = {}; if (!sm_count[dev & 31]) cudaDeviceGetAttribute(&sm_count[dev & 31], cudaDevAttrMultiProcessorCount, dev); sms = sm_count[dev & 31] > 0 ? sm_count[dev & 31] : 148; }
     const long long total = (long long)p.tiles_m * p.tiles_n;
     dim3 grid((unsigned)(total < sms ? total : sms)); // persistent: one CTA per SM walks the tile list
-    if (bn256) launch_pdl(gemm_tc_kernel<256>, grid, TC_THREADS, tc_smem_bytes<256>(), s, ma, ml, mb, p);
-    else if (bn64) launch_pdl(gemm_tc_kernel<64>, grid, TC_THREADS, tc_smem_bytes<64>(), s, ma, ml, mb, p);
-    else launch_pdl(gemm_tc_kernel<128>, grid, TC_THREADS, tc_smem_bytes<128>(), s, ma, ml, mb, p);
+    const ConvGather none = {};
+    if (bn256) launch_pdl(gemm_tc_kernel<256>, grid, TC_THREADS, tc_smem_bytes<256>(), s, ma, ml, mb, p, none);
+    else if (bn64) launch_pdl(gemm_tc_kernel<64>, grid, TC_THREADS, tc_smem_bytes<64>(), s, ma, ml, mb, p, none);
+    else launch_pdl(gemm_tc_kernel<128>, grid, TC_THREADS, tc_smem_bytes<128>(), s, ma, ml, mb, p, none);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc launch: %s", cudaGetErrorString(e));
         return -1;
     }
+    return 0;
+}
+
+// Conv stem stage 2 / 3 as an implicit GEMM (see ConvGather): out[pos][oc] = epilogue(sum_k patch(pos)[k] * W[oc][k]),
+// M = output positions of all chunks, K = 9 * 480, N = 480.
+int launch_conv_gemm_tc(cudaStream_t s, const bf16_t *src_hi, const bf16_t *src_lo, const ConvGeom &g, int stage, const bf16_t *W,
+                        const GemmEpilogue &epi) {
+    const int M = stage == 2 ? g.total2 : g.total3, K = 4320, N = 480;
+    if (M <= 0) return 0;
+    if (gemm_tc_init() != 0) return -1;
+    if (((uintptr_t)src_hi & 15) || (src_lo && ((uintptr_t)src_lo & 15)) || ((uintptr_t)W & 15)) {
+        snprintf(g_tc_err, sizeof g_tc_err, "conv gemm: operands must be 16-byte aligned");
+        return -1;
+    }
+    TcParams p;
+    p.M = M; p.N = N; p.K = K;
+    p.nsplit = src_lo ? 2 : 1;
+    p.epi = epi;
+    p.tiles_m = (M + TC_BM - 1) / TC_BM;
+    const bool bn256 = (long long)p.tiles_m * 2 >= 296; // two 256-wide tiles cover N = 480; narrower tiles while they would leave SMs idle
+    const int bn = bn256 ? 256 : 128;
+    p.tiles_n = (N + bn - 1) / bn;
+    ConvGather cg;
+    cg.src_hi = src_hi; cg.src_lo = src_lo ? src_lo : src_hi;
+    cg.w0s = g.d_w0; cg.off_in = stage == 2 ? g.d_off1 : g.d_off2; cg.off_out = stage == 2 ? g.d_off2 : g.d_off3;
+    cg.n_chunks = g.n_chunks; cg.Hin = stage == 2 ? 64 : 32;
+    CUtensorMap mb;
+    if (make_map(&mb, W, N, K, bn) != 0) return -1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long total = (long long)p.tiles_m * p.tiles_n;
+    dim3 grid((unsigned)(total < sms ? total : sms));
+    if (bn256) launch_pdl(gemm_tc_kernel<256, true>, grid, TC_THREADS + TC_GATHER_THREADS, tc_smem_bytes<256>(), s, mb, mb, mb, p, cg);
+    else launch_pdl(gemm_tc_kernel<128, true>, grid, TC_THREADS + TC_GATHER_THREADS, tc_smem_bytes<128>(), s, mb, mb, mb, p, cg);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "conv gemm launch: %s", cudaGetErrorString(e)); return -1; }
     return 0;
 }

@@ -194,5 +194,8 @@ int gemm_tc_prepare(void); // per-device split-K scratch (call once per device, 
 int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M, int K, const bf16_t *W, int N,
                    const GemmEpilogue &epi);
 const char *gemm_tc_error(void);
+// conv stem stage 2 / 3 as an implicit GEMM: the 3 x 3 patches are gathered into the operand stage by the kernel itself
+int launch_conv_gemm_tc(cudaStream_t s, const bf16_t *src_hi, const bf16_t *src_lo, const ConvGeom &g, int stage, const bf16_t *W,
+                        const GemmEpilogue &epi);
 // encode a 2-D bf16 [rows, K] row-major tensor map with the given box and 128B swizzle into *out (sizeof(CUtensorMap) = 128 bytes, host)
 int tc_encode_map(void *out_map64, const bf16_t *ptr, int rows, int K, int box_cols, int box_rows);
