@@ -1249,9 +1249,9 @@ static int transcribe_group(qasr_ctx_t *c, const float *const *samples, const in
         CKR(prefill_prompt_device(c, PRE, n_pre, T, SUF, n_suf, 0));
         CK(cudaMemcpyAsync(c->x + (size_t)q * c->H, c->pending, (size_t)c->H * 4, cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaEventRecord(c->ev[4], c->stream));
-        CK(cudaEventSynchronize(c->ev[4]));
         c->has_pending = false;
-        if (tm) {
+        if (tm) { // per-stage times were asked for: the only reason to wait here (everything is stream-ordered, the workspaces are reused in order)
+            CK(cudaEventSynchronize(c->ev[4]));
             float a = 0, b = 0, d = 0;
             cudaEventElapsedTime(&a, c->ev[0], c->ev[2]); cudaEventElapsedTime(&b, c->ev[2], c->ev[3]); cudaEventElapsedTime(&d, c->ev[3], c->ev[4]);
             tm[0] += a; tm[1] += b; tm[2] += d;

@@ -14,7 +14,8 @@
 //               embedding gather.  A step is one CUDA graph (positions / step counter live in device memory) replayed
 //               from the host, ids are read back every few steps to stop at EOS / the caps.
 //
-// KV pool: f32 [unit][layer][cap][1024] for K and for V (same row format as the reference, qwen_asr.h:205-206).
+// KV pool: f32 [unit][layer][kv head][cap][128] for K and for V: the reference's f32 values (qwen_asr.h:205-206), head-major
+// so that the decode attention of one (unit, kv head) streams one contiguous range.
 // Groups of at most qasr_cuda_max_batch() units fall through to the persistent single-launch decode kernel instead
 // (qasr_stream.cu, 2 / 4 sequences per weight pass): its per-step latency is lower than a chain of GEMM launches.
 #include "qasr_ctx.h"
@@ -94,6 +95,7 @@ struct GroupPlan {
 
 // ---- one decode step for B sequences (enqueued on the stream; captured into a graph by the caller)
 static int enqueue_batch_step(qasr_ctx_t *c, BatchState *b, int B, float *xb, uint8_t *W, size_t unit_stride, size_t layer_stride) {
+    const size_t head_stride = layer_stride / 8; // [kv head][cap][128] inside a layer block
     const int H = c->H, I = c->I;
     cudaStream_t s = c->stream;
     const bool two = c->nsplit == 2;
@@ -110,7 +112,7 @@ static int enqueue_batch_step(qasr_ctx_t *c, BatchState *b, int B, float *xb, ui
         float *kl = b->kv_k.as<float>() + (size_t)l * layer_stride, *vl = b->kv_v.as<float>() + (size_t)l * layer_stride;
         launch_rmsnorm(s, xb, L.in_norm, 1e-6f, B, H, nullptr, xn_hi, two ? xn_lo : nullptr);
         CKR(gemm(c, xn_hi, xn_lo, B, H, L.wqkv, 4096, QASR_GEMM_F32, qkv, nullptr, nullptr, nullptr, 4096));
-        launch_attn_decode_batch(s, qkv, L.qn, L.kn, c->rope_cos, c->rope_sin, kl, vl, unit_stride, b->d_pos, B, 1e-6f, scale, at_hi, two ? at_lo : nullptr);
+        launch_attn_decode_batch(s, qkv, L.qn, L.kn, c->rope_cos, c->rope_sin, kl, vl, unit_stride, head_stride, b->d_pos, B, 1e-6f, scale, at_hi, two ? at_lo : nullptr);
         CKR(gemm(c, at_hi, at_lo, B, 2048, L.wo, H, QASR_GEMM_RESIDUAL, xb, nullptr, nullptr, nullptr, H));
         launch_rmsnorm(s, xb, L.post_norm, 1e-6f, B, H, nullptr, xn_hi, two ? xn_lo : nullptr);
         CKR(gemm(c, xn_hi, xn_lo, B, H, L.wgu, 2 * I, QASR_GEMM_SWIGLU_SPLIT, nullptr, ac_hi, ac_lo, nullptr, I));
@@ -249,8 +251,8 @@ static int run_group(qasr_ctx_t *c, BatchState *b, const float *const *samples, 
             float *kl = b->kv_k.as<float>() + (size_t)l * layer_stride, *vl = b->kv_v.as<float>() + (size_t)l * layer_stride;
             launch_rmsnorm(s, x, Lw.in_norm, 1e-6f, g.R, H, nullptr, xn_hi, two ? xn_lo : nullptr);
             CKR(gemm(c, xn_hi, xn_lo, g.R, H, Lw.wqkv, 4096, QASR_GEMM_F32, qkv, nullptr, nullptr, nullptr, 4096));
-            launch_qk_norm_rope_store_rows(s, qkv, Lw.qn, Lw.kn, c->rope_cos, c->rope_sin, d_runit, d_rpos, g.R, 1e-6f, q, kl, vl, unit_stride);
-            launch_attn_prefill_batch(s, q, kl, vl, unit_stride, d_row0, d_P, B, g.max_P, c->heads, c->kv_heads, scale, at_hi, two ? at_lo : nullptr);
+            launch_qk_norm_rope_store_rows(s, qkv, Lw.qn, Lw.kn, c->rope_cos, c->rope_sin, d_runit, d_rpos, g.R, 1e-6f, q, kl, vl, unit_stride, layer_stride / 8);
+            launch_attn_prefill_batch(s, q, kl, vl, unit_stride, layer_stride / 8, d_row0, d_P, B, g.max_P, c->heads, c->kv_heads, scale, at_hi, two ? at_lo : nullptr);
             CKR(gemm(c, at_hi, at_lo, g.R, 2048, Lw.wo, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H));
             launch_rmsnorm(s, x, Lw.post_norm, 1e-6f, g.R, H, nullptr, xn_hi, two ? xn_lo : nullptr);
             CKR(gemm(c, xn_hi, xn_lo, g.R, H, Lw.wgu, 2 * I, QASR_GEMM_SWIGLU_SPLIT, nullptr, ac_hi, ac_lo, nullptr, I));

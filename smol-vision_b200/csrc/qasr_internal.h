@@ -142,14 +142,16 @@ void launch_attn_prefill(cudaStream_t s, const float *q, const float *kc, const 
 void launch_attn_windowed(cudaStream_t s, const float *q, const float *k, const float *v, int ld, int n_heads,
                           const int *d_window_starts, int n_windows, int max_window, float scale, int out_ld,
                           float *out_f32, bf16_t *out_hi, bf16_t *out_lo);
-// batched path (qasr_batch.cu): per-unit KV caches inside one pool, unit u's block of a layer at pool + u * unit_stride
+// batched path (qasr_batch.cu): per-unit KV caches inside one pool, unit u's block of a layer at pool + u * unit_stride,
+// head-major inside ([kv head][cap][128], head_stride = cap * 128)
 void launch_qk_norm_rope_store_rows(cudaStream_t s, const float *qkv, const float *qn, const float *kn, const float *rope_cos,
                                     const float *rope_sin, const int *d_row_unit, const int *d_row_pos, int R, float eps, float *q_out,
-                                    float *kpool, float *vpool, size_t unit_stride);
-void launch_attn_prefill_batch(cudaStream_t s, const float *q, const float *kpool, const float *vpool, size_t unit_stride, const int *d_row0,
-                               const int *d_P, int n_units, int max_P, int n_heads, int n_kv_heads, float scale, bf16_t *out_hi, bf16_t *out_lo);
+                                    float *kpool, float *vpool, size_t unit_stride, size_t head_stride);
+void launch_attn_prefill_batch(cudaStream_t s, const float *q, const float *kpool, const float *vpool, size_t unit_stride, size_t head_stride,
+                               const int *d_row0, const int *d_P, int n_units, int max_P, int n_heads, int n_kv_heads, float scale, bf16_t *out_hi, bf16_t *out_lo);
 void launch_attn_decode_batch(cudaStream_t s, const float *qkv, const float *qn, const float *kn, const float *rope_cos, const float *rope_sin,
-                              float *kpool, float *vpool, size_t unit_stride, const int *d_pos, int B, float eps, float scale, bf16_t *ohi, bf16_t *olo);
+                              float *kpool, float *vpool, size_t unit_stride, size_t head_stride, const int *d_pos, int B, float eps, float scale, bf16_t *ohi,
+                              bf16_t *olo);
 void launch_argmax_next(cudaStream_t s, const float *logits, int V, const bf16_t *E, int H, float *x_next, int *d_pos, int *d_step,
                         int *d_tokens, volatile int *h_tokens, int B, int max_steps);
 void launch_assemble_prompts(cudaStream_t s, const bf16_t *E, int H, const int *d_pre, int n_pre, const int *d_suf, int n_suf, const float *enc,

@@ -151,12 +151,13 @@ void launch_qk_norm_rope_store(cudaStream_t s, const float *qkv, const float *qn
 }
 
 // Batched variant (qasr_batch.cu): row r belongs to unit row_unit[r] at position row_pos[r]; K/V rows go to that unit's
-// cache kpool + unit * unit_stride (this layer's [cap][1024] block).
+// cache kpool + unit * unit_stride (this layer's head-major [kv head][cap][128] block): a head's keys are contiguous, so the
+// decode attention streams them as one sequential range instead of 512-byte pieces 4 KB apart.
 __global__ void __launch_bounds__(128)
 qk_norm_rope_store_rows_kernel(const float *__restrict__ qkv, const float *__restrict__ qn, const float *__restrict__ kn,
                                const float *__restrict__ rope_cos, const float *__restrict__ rope_sin, const int *__restrict__ row_unit,
                                const int *__restrict__ row_pos, float eps, float *__restrict__ q_out, float *__restrict__ kpool,
-                               float *__restrict__ vpool, size_t unit_stride) {
+                               float *__restrict__ vpool, size_t unit_stride, size_t head_stride) {
     __shared__ float tmp[128];
     __shared__ float red[4];
     const int p = blockIdx.x, slot = blockIdx.y, t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -164,7 +165,7 @@ qk_norm_rope_store_rows_kernel(const float *__restrict__ qkv, const float *__res
     const size_t ub = (size_t)row_unit[p] * unit_stride;
     const float v = qkv[(size_t)p * 4096 + slot * 128 + t];
     if (slot >= 24) {
-        vpool[ub + (size_t)pos * 1024 + (slot - 24) * 128 + t] = v;
+        vpool[ub + (size_t)(slot - 24) * head_stride + (size_t)pos * 128 + t] = v;
         return;
     }
     float ss = warp_sum(v * v);
@@ -178,12 +179,12 @@ qk_norm_rope_store_rows_kernel(const float *__restrict__ qkv, const float *__res
     const float c = rope_cos[(size_t)pos * 64 + d], sn = rope_sin[(size_t)pos * 64 + d];
     const float r = t < 64 ? tmp[t] * c - tmp[t + 64] * sn : tmp[t] * c + tmp[t - 64] * sn;
     if (slot < 16) q_out[(size_t)p * 2048 + slot * 128 + t] = r;
-    else kpool[ub + (size_t)pos * 1024 + (slot - 16) * 128 + t] = r;
+    else kpool[ub + (size_t)(slot - 16) * head_stride + (size_t)pos * 128 + t] = r;
 }
 void launch_qk_norm_rope_store_rows(cudaStream_t s, const float *qkv, const float *qn, const float *kn, const float *rope_cos,
                                     const float *rope_sin, const int *d_row_unit, const int *d_row_pos, int R, float eps, float *q_out,
-                                    float *kpool, float *vpool, size_t unit_stride) {
-    if (R > 0) qk_norm_rope_store_rows_kernel<<<dim3(R, 32), 128, 0, s>>>(qkv, qn, kn, rope_cos, rope_sin, d_row_unit, d_row_pos, eps, q_out, kpool, vpool, unit_stride);
+                                    float *kpool, float *vpool, size_t unit_stride, size_t head_stride) {
+    if (R > 0) qk_norm_rope_store_rows_kernel<<<dim3(R, 32), 128, 0, s>>>(qkv, qn, kn, rope_cos, rope_sin, d_row_unit, d_row_pos, eps, q_out, kpool, vpool, unit_stride, head_stride);
 }
 
 // ------------------------------------------------------------------ online-softmax helpers
@@ -311,15 +312,18 @@ __device__ __forceinline__ void att_store_tile(AttSmem<HD> &sm, const AttRegs<HD
 // Query position i attends keys [0, q_offset + i].
 __device__ __forceinline__ void attn_prefill_body(const float *__restrict__ q, const float *__restrict__ kc, const float *__restrict__ vc,
                                                   int q_offset, int P, int seq_k, int n_heads, int n_kv_heads, float scale, float *of, bf16_t *ohi,
-                                                  bf16_t *olo, size_t out_row0, int kvh, int ib) {
+                                                  bf16_t *olo, size_t out_row0, int kvh, int ib, int kld_override = 0, int kcol_override = -1) {
     extern __shared__ __align__(16) uint8_t att_raw[];
     AttSmem<128> &sm = *reinterpret_cast<AttSmem<128> *>(att_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = n_heads / n_kv_heads; // 2
-    const size_t qld = (size_t)n_heads * 128, kld = (size_t)n_kv_heads * 128;
+    // K/V rows: [key][n_kv_heads * 128] with this head at column kvh * 128 (the reference's cache rows), or - batched pool -
+    // a head-major block [key][128] the caller already points at
+    const size_t qld = (size_t)n_heads * 128, kld = kld_override ? (size_t)kld_override : (size_t)n_kv_heads * 128;
+    const int kcol = kcol_override >= 0 ? kcol_override : kvh * 128;
     const int kmax_cta = min(q_offset + min(ib + 16, P), seq_k); // keys needed by the last position of the CTA
     AttRegs<128> regs;
-    att_fetch_tile<128>(regs, kc, vc, kld, kvh * 128, 0, min(ATT_KT, kmax_cta));
+    att_fetch_tile<128>(regs, kc, vc, kld, kcol, 0, min(ATT_KT, kmax_cta));
     for (int e = threadIdx.x; e < 32 * 32; e += 256) { // 32 queries x 32 float4
         const int qi = e >> 5, c4 = e & 31, pos = ib + (qi >> 1), hh = kvh * per + (qi & 1);
         reinterpret_cast<float4 *>(sm.qs[qi])[c4] = pos < P ? *reinterpret_cast<const float4 *>(q + (size_t)pos * qld + hh * 128 + c4 * 4)
@@ -339,7 +343,7 @@ __device__ __forceinline__ void attn_prefill_body(const float *__restrict__ q, c
         __syncthreads(); // the previous tile has been consumed
         att_store_tile<128>(sm, regs, nk);
         __syncthreads();
-        if (t0 + ATT_KT < kmax_cta) att_fetch_tile<128>(regs, kc, vc, kld, kvh * 128, t0 + ATT_KT, min(ATT_KT, kmax_cta - t0 - ATT_KT));
+        if (t0 + ATT_KT < kmax_cta) att_fetch_tile<128>(regs, kc, vc, kld, kcol, t0 + ATT_KT, min(ATT_KT, kmax_cta - t0 - ATT_KT));
         if (t0 < max(max(hi[0], hi[1]), max(hi[2], hi[3]))) att_tile<128>(sm, warp, lane, t0, nk, hi, scale, m, l, acc);
     }
 #pragma unroll
@@ -363,17 +367,17 @@ attn_prefill_kernel(const float *__restrict__ q, const float *__restrict__ kc, c
 }
 
 // Batched variant (qasr_batch.cu): blockIdx.z = unit.  Unit u owns rows [row0[u], row0[u] + P[u]) of the concatenated
-// q / output matrices and its own KV cache kpool + u * unit_stride (this layer's [cap][1024] block); every unit starts at
-// position 0 (a fresh segment / utterance, reference qwen_asr.c:763).
+// q / output matrices and its own KV cache kpool + u * unit_stride (this layer's head-major [kv head][cap][128] block, head_stride = cap * 128);
+// every unit starts at position 0 (a fresh segment / utterance, reference qwen_asr.c:763).
 __global__ void __launch_bounds__(256)
 attn_prefill_batch_kernel(const float *__restrict__ q, const float *__restrict__ kpool, const float *__restrict__ vpool, size_t unit_stride,
-                          const int *__restrict__ row0, const int *__restrict__ Ps, int n_heads, int n_kv_heads, float scale,
+                          size_t head_stride, const int *__restrict__ row0, const int *__restrict__ Ps, int n_heads, int n_kv_heads, float scale,
                           bf16_t *ohi, bf16_t *olo) {
     const int u = blockIdx.z, P = Ps[u], ib = blockIdx.y * 16;
     if (ib >= P) return;
     const size_t r0 = (size_t)row0[u];
-    attn_prefill_body(q + r0 * n_heads * 128, kpool + u * unit_stride, vpool + u * unit_stride, 0, P, P, n_heads, n_kv_heads, scale,
-                      nullptr, ohi, olo, r0, blockIdx.x, ib);
+    attn_prefill_body(q + r0 * n_heads * 128, kpool + u * unit_stride + blockIdx.x * head_stride, vpool + u * unit_stride + blockIdx.x * head_stride, 0, P, P,
+                      n_heads, n_kv_heads, scale, nullptr, ohi, olo, r0, blockIdx.x, ib, 128, 0);
 }
 static void attn_prefill_opt_in() { // per-device bit: the attribute belongs to the (function, device) pair
     static unsigned attr_set = 0;
@@ -392,12 +396,12 @@ void launch_attn_prefill(cudaStream_t s, const float *q, const float *kc, const 
     dim3 grid(n_kv_heads, (P + 15) / 16);
     launch_pdl(attn_prefill_kernel, grid, 256, sizeof(AttSmem<128>), s, q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, out_f32, out_hi, out_lo);
 }
-void launch_attn_prefill_batch(cudaStream_t s, const float *q, const float *kpool, const float *vpool, size_t unit_stride, const int *d_row0,
-                               const int *d_P, int n_units, int max_P, int n_heads, int n_kv_heads, float scale, bf16_t *out_hi, bf16_t *out_lo) {
+void launch_attn_prefill_batch(cudaStream_t s, const float *q, const float *kpool, const float *vpool, size_t unit_stride, size_t head_stride,
+                               const int *d_row0, const int *d_P, int n_units, int max_P, int n_heads, int n_kv_heads, float scale, bf16_t *out_hi, bf16_t *out_lo) {
     if (n_units <= 0 || max_P <= 0) return;
     attn_prefill_opt_in();
     dim3 grid(n_kv_heads, (max_P + 15) / 16, n_units);
-    attn_prefill_batch_kernel<<<grid, 256, sizeof(AttSmem<128>), s>>>(q, kpool, vpool, unit_stride, d_row0, d_P, n_heads, n_kv_heads, scale, out_hi, out_lo);
+    attn_prefill_batch_kernel<<<grid, 256, sizeof(AttSmem<128>), s>>>(q, kpool, vpool, unit_stride, head_stride, d_row0, d_P, n_heads, n_kv_heads, scale, out_hi, out_lo);
 }
 
 // ------------------------------------------------------------------ windowed bidirectional attention (encoder)
@@ -656,7 +660,7 @@ void launch_transpose_bias(cudaStream_t s, const float *in, const float *bias, f
 __global__ void __launch_bounds__(256)
 attn_decode_batch_kernel(const float *__restrict__ qkv /*[B][4096]*/, const float *__restrict__ qn, const float *__restrict__ kn,
                          const float *__restrict__ rope_cos, const float *__restrict__ rope_sin, float *__restrict__ kpool,
-                         float *__restrict__ vpool, size_t unit_stride, const int *__restrict__ d_pos, float eps, float scale,
+                         float *__restrict__ vpool, size_t unit_stride, size_t head_stride, const int *__restrict__ d_pos, float eps, float scale,
                          bf16_t *__restrict__ ohi, bf16_t *__restrict__ olo /*[B][2048] planes*/) {
     __shared__ float4 s_new[3][32];        // roped q0, q1, k_new (4 dims per lane)
     __shared__ float4 s_vnew[32];
@@ -667,8 +671,8 @@ attn_decode_batch_kernel(const float *__restrict__ qkv /*[B][4096]*/, const floa
     const int kvh = blockIdx.x, u = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pos = d_pos[u];
     const float *row = qkv + (size_t)u * 4096;
-    float *kc = kpool + (size_t)u * unit_stride, *vc = vpool + (size_t)u * unit_stride;
-    const size_t hoff = (size_t)kvh * 128 + lane * 4;
+    float *kc = kpool + (size_t)u * unit_stride + (size_t)kvh * head_stride, *vc = vpool + (size_t)u * unit_stride + (size_t)kvh * head_stride; // [key][128]
+    const size_t hoff = (size_t)lane * 4;
     if (warp < 3) { // warps 0, 1: the two query heads of this kv head; warp 2: the new key
         const float *src = warp < 2 ? row + (2 * kvh + warp) * 128 : row + 2048 + kvh * 128;
         float4 v = *reinterpret_cast<const float4 *>(src + lane * 4);
@@ -684,11 +688,11 @@ attn_decode_batch_kernel(const float *__restrict__ qkv /*[B][4096]*/, const floa
         const float sgn = lane < 16 ? -1.0f : 1.0f;
         const float4 r = make_float4(v.x * rc.x + sgn * o.x * rs.x, v.y * rc.y + sgn * o.y * rs.y, v.z * rc.z + sgn * o.z * rs.z, v.w * rc.w + sgn * o.w * rs.w);
         s_new[warp][lane] = r;
-        if (warp == 2) *reinterpret_cast<float4 *>(kc + (size_t)pos * 1024 + hoff) = r;
+        if (warp == 2) *reinterpret_cast<float4 *>(kc + (size_t)pos * 128 + hoff) = r;
     } else if (warp == 3) {
         const float4 v = *reinterpret_cast<const float4 *>(row + 3072 + kvh * 128 + lane * 4);
         s_vnew[lane] = v;
-        *reinterpret_cast<float4 *>(vc + (size_t)pos * 1024 + hoff) = v;
+        *reinterpret_cast<float4 *>(vc + (size_t)pos * 128 + hoff) = v;
     }
     __syncthreads();
     const float4 q0 = s_new[0][lane], q1 = s_new[1][lane];
@@ -701,8 +705,8 @@ attn_decode_batch_kernel(const float *__restrict__ qkv /*[B][4096]*/, const floa
         for (int i = 0; i < ATTD_KEYS; i++) {
             const int j = base + 8 * i;
             if (j < pos) {
-                kr[i] = __ldcg(reinterpret_cast<const float4 *>(kc + (size_t)j * 1024 + hoff));
-                vr[i] = __ldcg(reinterpret_cast<const float4 *>(vc + (size_t)j * 1024 + hoff));
+                kr[i] = __ldcg(reinterpret_cast<const float4 *>(kc + (size_t)j * 128 + hoff));
+                vr[i] = __ldcg(reinterpret_cast<const float4 *>(vc + (size_t)j * 128 + hoff));
             } else if (j == pos) { kr[i] = s_new[2][lane]; vr[i] = s_vnew[lane]; } // never read the row being appended from the cache
         }
         float d0[ATTD_KEYS], d1[ATTD_KEYS];
@@ -750,8 +754,9 @@ attn_decode_batch_kernel(const float *__restrict__ qkv /*[B][4096]*/, const floa
     }
 }
 void launch_attn_decode_batch(cudaStream_t s, const float *qkv, const float *qn, const float *kn, const float *rope_cos, const float *rope_sin,
-                              float *kpool, float *vpool, size_t unit_stride, const int *d_pos, int B, float eps, float scale, bf16_t *ohi, bf16_t *olo) {
-    if (B > 0) launch_pdl(attn_decode_batch_kernel, dim3(8, B), 256, 0, s, qkv, qn, kn, rope_cos, rope_sin, kpool, vpool, unit_stride, d_pos, eps, scale, ohi, olo);
+                              float *kpool, float *vpool, size_t unit_stride, size_t head_stride, const int *d_pos, int B, float eps, float scale, bf16_t *ohi,
+                              bf16_t *olo) {
+    if (B > 0) launch_pdl(attn_decode_batch_kernel, dim3(8, B), 256, 0, s, qkv, qn, kn, rope_cos, rope_sin, kpool, vpool, unit_stride, head_stride, d_pos, eps, scale, ohi, olo);
 }
 
 // Greedy head of the batched step: argmax over the f32 logits row of sequence u (strict >, ties -> lowest index,

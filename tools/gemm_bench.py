@@ -30,6 +30,9 @@ def pipeline_mode(name):   # the epilogue each shape has in the pipeline: 0 f32 
     if "fc1" in name or name.startswith("conv2") or name.startswith("conv3"): return 2
     if ".wo" in name or ".down" in name or "fc2" in name: return 1
     return 0
+if len(sys.argv) > 1 and sys.argv[1] == "decode":   # one decode step of the batched path at 128 sequences (1.7B and 0.6B)
+    shapes = [("dec.qkv", 128, 2048, 4096), ("dec.wo", 128, 2048, 2048), ("dec.gu", 128, 2048, 12288), ("dec.down", 128, 6144, 2048), ("dec.head", 128, 2048, 151936),
+              ("dec06.qkv", 128, 1024, 4096), ("dec06.wo", 128, 2048, 1024), ("dec06.gu", 128, 1024, 6144), ("dec06.down", 128, 3072, 1024), ("dec06.head", 128, 1024, 151936)]
 for name, M, K, N in shapes:
     us = C.c_double(0)
     rc = f(eng.ctx, M, K, N, 64, pipeline_mode(name), C.byref(us))
