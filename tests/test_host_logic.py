@@ -191,3 +191,69 @@ def test_skinny_gemm_split_plan_invariants(pkg):
     assert plan(0, 8, 8, out) != 0 and plan(8, 8, 8, None) != 0
     # bench workload, Qwen3-ASR-1.7B: prefill QKV / WO / gate-up / down and encoder fc2 (tools/gemm_bench.py)
     assert [get(61, 2048, 4096)[4], get(61, 2048, 2048)[4], get(61, 2048, 12288)[4], get(61, 6144, 2048)[4], get(47, 4096, 1024)[4]] == [3, 5, 1, 5, 8]
+
+
+def test_find_split_point_equals_scalar_restatement(pkg):
+    """The vectorised split search must pick exactly the window the reference's scalar loop picks (qwen_asr.c:617-643:
+    100 ms windows every 50 ms inside +-search_sec, strict '<' so the first minimum wins, centre of the window)."""
+    seg = pkg.segments
+
+    def scalar(samples, target, search_sec):
+        n = len(samples)
+        half = int(search_sec * 16000)
+        lo, hi = max(0, target - half), min(n, target + half)
+        win = 1600
+        best_e, best_c = np.float32(1e30), target
+        pos = lo
+        while pos + win <= hi:
+            e = np.float32((samples[pos:pos + win].astype(np.float32) ** 2).sum(dtype=np.float32) / np.float32(win))
+            if e < best_e:
+                best_e, best_c = e, pos + win // 2
+            pos += win // 2
+        return best_c
+    audio = pkg.synth_audio(70.0, seed=9)
+    for target, search in ((16000 * 20, 3.0), (16000 * 33 + 123, 1.5), (16000 * 2, 3.0), (len(audio) - 8000, 3.0), (16000 * 50, 0.04)):
+        assert seg.find_split_point(audio, target, search) == scalar(audio, target, search)
+    flat = np.zeros(16000 * 8, np.float32)          # all windows tie: the first one wins
+    assert seg.find_split_point(flat, 16000 * 4, 1.0) == scalar(flat, 16000 * 4, 1.0)
+
+
+def test_checkpoint_variant_helpers(tmp_path):
+    """tests/variants.py: the vocab in which every id decodes to a distinct string, and the embedding-row patcher."""
+    import json
+    import struct
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import variants
+    b2u = variants.bytes_to_unicode()
+    assert len(b2u) == 256 and len(set(b2u.values())) == 256 and b2u[ord("A")] == "A" and b2u[ord(" ")] == "Ġ"
+    vp = tmp_path / "vocab.json"
+    variants.write_full_vocab(str(vp), vocab_size=1000)
+    vocab = json.load(open(vp, encoding="utf-8"))
+    assert len(vocab) == 1000 and sorted(vocab.values()) == list(range(1000)) and vocab["t999."] == 999
+    # a two-tensor safetensors file: the patcher rewrites rows of the embedding only
+    base = tmp_path / "m"
+    base.mkdir()
+    emb = np.arange(8 * 4, dtype=np.uint16).reshape(8, 4)
+    other = np.full(6, 7, np.uint16)
+    header = {"x": {"dtype": "BF16", "shape": [6], "data_offsets": [0, 12]},
+              variants.EMBED: {"dtype": "BF16", "shape": [8, 4], "data_offsets": [12, 12 + 64]}}
+    hj = json.dumps(header).encode()
+    with open(base / "model.safetensors", "wb") as f:
+        f.write(struct.pack("<Q", len(hj)) + hj + other.tobytes() + emb.tobytes())
+    (base / "vocab.json").write_text("{}")
+    out = variants.patched_model_dir(str(base), "dup", lambda E: E.__setitem__(5, E[1]), full_vocab=False)
+    off, nbytes, shape, dtype = variants.tensor_span(os.path.join(out, "model.safetensors"), variants.EMBED)
+    raw = open(os.path.join(out, "model.safetensors"), "rb").read()
+    got = np.frombuffer(raw[off:off + nbytes], np.uint16).reshape(shape)
+    want = emb.copy()
+    want[5] = want[1]
+    assert np.array_equal(got, want) and raw[off - 12:off] == other.tobytes()
+    assert np.array_equal(variants.f32_to_bf16(variants.bf16_to_f32(emb[2])), emb[2])
+
+
+def test_batch_plan_is_host_only(pkg):
+    """qasr_cuda_batch_plan needs a loaded context; without a GPU it must fail cleanly (no CPU fallback, no crash)."""
+    import ctypes as C
+    lib = pkg.load_library()
+    g, b = C.c_int(0), C.c_int(0)
+    assert lib.qasr_cuda_batch_plan(None, 10, C.byref(g), C.byref(b)) != 0
