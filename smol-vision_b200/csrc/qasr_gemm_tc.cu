@@ -423,6 +423,178 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 }
 
 
+// ------------------------------------------------------------------ 2-CTA variant of the persistent kernel (cta_group::2)
+// A CTA pair (cluster (2,1,1) = the two SMs of a TPC) owns a 256 x 256 output tile: CTA r loads ITS 128 rows of A (hi and lo
+// planes) and ITS half of the 256 W rows (128 x 64 per k-block), and the leader issues ONE tcgen05.mma.cta_group::2 (M = 256,
+// N = 256, K = 16) per k-step and plane; each SM's tensor core reads its own A rows and both halves of W.  Per CTA and
+// k-block that is 48 KB through L2 -> shared memory instead of 64 KB (W is fetched once per pair) and half the W operand
+// reads from shared memory, so the ring holds 4 stages instead of 3.  Barriers: TMA completions of BOTH CTAs land on the
+// leader's full barrier (the follower passes the leader's barrier address); tcgen05.commit multicasts "slot free" /
+// "accumulator complete" to the same barrier in both CTAs; the follower's epilogue warps signal "accumulator drained" on
+// the leader's barrier through its cluster address.
+#define TC2_STAGES 4
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t *bar) { // arrives on `bar` (same offset) in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int BN = 256;                        // pair tile: 256 (M) x 256 (N)
+    constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2; // this CTA's 128 rows of one A plane
+    constexpr uint32_t B_BYTES = 128 * TC_BK * 2;   // this CTA's half of the W rows
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + B_BYTES;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + TC2_STAGES * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + TC2_STAGES;
+    uint64_t *tmem_full_bar = empty_bar + TC2_STAGES;
+    uint64_t *tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + 2);
+
+    pdl_trigger();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int num_kb = (p.K + TC_BK - 1) / TC_BK;
+    const int total_tiles = p.tiles_m * p.tiles_n; // tiles_m counts 256-row pair tiles
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        if (p.nsplit == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
+        for (int s = 0; s < TC2_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); } // 4 epilogue warps x 2 CTAs
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) { // both CTAs of the pair take part in the allocation (same columns in both tensor memories)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all(); // barriers of both CTAs are initialised before anything can signal them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own A rows, own half of the W rows; completions go to the leader's full barrier =====
+        if (lane == 0) {
+            const uint32_t tx = 2u * ((p.nsplit == 2 ? 2 * A_BYTES : A_BYTES) + B_BYTES); // bytes of BOTH CTAs per stage
+            uint32_t it = 0;
+            for (int t = pair; t < total_tiles; t += n_pairs) {
+                const int m0 = (t / p.tiles_n) * 256 + (int)rank * 128, n0 = (t % p.tiles_n) * BN + (int)rank * 128;
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int s = it % TC2_STAGES;
+                    mbar_wait(&empty_bar[s], ((it / TC2_STAGES) & 1) ^ 1);
+                    uint8_t *st = smem + s * STAGE_BYTES;
+                    if (leader) mbar_expect_tx(&full_bar[s], tx);
+                    const uint32_t lbar = mapa_u32(smem_u32(&full_bar[s]), 0);
+                    tma_load_2d_2sm(st, &tmA_hi, lbar, kb * TC_BK, m0);
+                    if (p.nsplit == 2) tma_load_2d_2sm(st + A_BYTES, &tmA_lo, lbar, kb * TC_BK, m0);
+                    tma_load_2d_2sm(st + 2 * A_BYTES, &tmB, lbar, kb * TC_BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one elected lane of the LEADER CTA drives both tensor cores =====
+        if (leader && lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            uint32_t it = 0, lt = 0;
+            for (int t = pair; t < total_tiles; t += n_pairs, lt++) {
+                const uint32_t as = lt & 1;
+                mbar_wait(&tmem_empty_bar[as], ((lt >> 1) & 1) ^ 1); // both CTAs' epilogues have drained this accumulator stage
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; kb++, it++) {
+                    const int s = it % TC2_STAGES;
+                    mbar_wait(&full_bar[s], (it / TC2_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t dah = make_sw128_desc(a_hi);
+                    const uint64_t dal = make_sw128_desc(a_hi + A_BYTES);
+                    const uint64_t db = make_sw128_desc(a_hi + 2 * A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; k++)
+                        tc_mma_bf16_2sm(tacc, dah + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    if (p.nsplit == 2) {
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; k++)
+                            tc_mma_bf16_2sm(tacc, dal + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+                    }
+                    tc_commit_2sm(&empty_bar[s]); // the slot is free in both CTAs once these MMAs have read it
+                }
+                tc_commit_2sm(&tmem_full_bar[as]);
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5 of both CTAs: this CTA's 128 rows of the pair tile =====
+        const int q = warp & 3;
+        const GemmEpilogue &e = p.epi;
+        const int width = e.mode == QASR_GEMM_SWIGLU_SPLIT ? 2 : 1;
+        const bool aligned = (e.ldo % 8 == 0) && ((e.mode == QASR_GEMM_F32 || e.mode == QASR_GEMM_RESIDUAL)
+                                 ? (reinterpret_cast<uintptr_t>(e.out_f32) & 15) == 0 && (!e.bias || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0)
+                                 : (reinterpret_cast<uintptr_t>(e.out_hi) & 15) == 0 && (!e.out_lo || (reinterpret_cast<uintptr_t>(e.out_lo) & 15) == 0));
+        uint32_t lt = 0;
+        for (int t = pair; t < total_tiles; t += n_pairs, lt++) {
+            const int m0 = (t / p.tiles_n) * 256 + (int)rank * 128, n0 = (t % p.tiles_n) * BN;
+            const uint32_t as = lt & 1;
+            mbar_wait(&tmem_full_bar[as], (lt >> 1) & 1);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int n = n0 + c0;
+                if (n >= p.N) break;
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + (uint32_t)c0, r);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+                tc_epilogue_block(e, v, row, n, p.N, row_ok, aligned && n + 32 <= p.N && (width == 1 || (p.N & 1) == 0));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { // "drained" goes to the leader's barrier (the MMA issuer waits there for all 8 epilogue warps)
+                const uint32_t lbar = mapa_u32(smem_u32(&tmem_empty_bar[as]), 0);
+                asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lbar) : "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all(); // nobody leaves (or frees tensor memory) while the peer may still signal its barriers or read its operands
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------ skinny-M variant (M <= 256)
 // At the single-utterance shapes of the encoder / prefill (M = 26...157 rows) a GEMM is a weight
 // stream: bytes = 2*N*K, flops are irrelevant.  Roles are swapped so that the 128-row MMA operand is
@@ -709,6 +881,8 @@ static constexpr size_t tc_smem_bytes() {
     return (size_t)(BN > 128 ? 3 : TC_STAGES) * (2 * TC_BM * TC_BK * 2 + BN * TC_BK * 2) + 256 + 1024;
 }
 
+static constexpr size_t tc2_smem_bytes() { return (size_t)TC2_STAGES * (2 * TC_BM * TC_BK * 2 + 128 * TC_BK * 2) + 256 + 1024; }
+
 template <int MP, int STAGES>
 static constexpr size_t sk_smem_bytes() {
     return (size_t)STAGES * (128 * TC_BK * 2 + 2 * MP * TC_BK * 2) + 256 + 1024;
@@ -738,6 +912,7 @@ int gemm_tc_init(void) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<64>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_smem_bytes());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256>());
     if (e == cudaSuccess)
@@ -905,6 +1080,25 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
     p.M = M; p.N = N; p.K = K;
     p.nsplit = A_lo ? 2 : 1;
     p.epi = epi;
+    static int use_2cta = -1; // QASR_GEMM_2CTA=0: keep the one-CTA 128 x 256 tiles (A/B runs)
+    if (use_2cta < 0) { const char *ev = getenv("QASR_GEMM_2CTA"); use_2cta = !(ev && ev[0] == '0'); }
+    if (bn256 && use_2cta && M > 128) { // CTA pairs, 256 x 256 tiles
+        p.tiles_m = (M + 255) / 256;
+        p.tiles_n = (N + 255) / 256;
+        CUtensorMap ma, ml, mb;
+        if (make_map(&ma, A_hi, M, K, TC_BM) != 0) return -1;
+        if (make_map(&ml, A_lo ? A_lo : A_hi, M, K, TC_BM) != 0) return -1;
+        if (make_map(&mb, W, N, K, 128) != 0) return -1;
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long total = (long long)p.tiles_m * p.tiles_n;
+        const long long pairs = total < sms / 2 ? total : sms / 2;
+        launch_pdl(gemm_tc2_kernel, dim3((unsigned)(2 * pairs)), TC_THREADS, tc2_smem_bytes(), s, ma, ml, mb, p);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc 2-CTA launch: %s", cudaGetErrorString(e2)); return -1; }
+        return 0;
+    }
     const int bn = bn64 ? 64 : (bn256 ? 256 : 128);
     p.tiles_m = (M + TC_BM - 1) / TC_BM;
     p.tiles_n = (N + bn - 1) / bn;

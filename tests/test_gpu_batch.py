@@ -100,3 +100,21 @@ def test_batched_custom_prompt(gpu06, ref_lib, oracle_lib, model06, pkg):
         assert [g.tolist() for g in got] == want
     finally:
         gpu06.set_prompt(PRE, SUF)
+
+
+def test_batched_config5_shape_vs_reference(pkg, model17, ref_lib, oracle_lib):
+    """BASELINE configs[4] through the batched path at its real shape: three 30 s utterances (T = 390, prompt 405 rows each,
+    4 encoder windows), Qwen3-ASR-1.7B, 64 greedy tokens - one group of 3 > qasr_cuda_max_batch() = 2."""
+    units = [pkg.synth_audio(30.0, seed=i)[:480000] for i in range(3)]
+    cpu = checker(ref_lib, oracle_lib, model17)
+    try:
+        want = [cpu.transcribe_ids(u, 64)[0].tolist() for u in units]
+    finally:
+        cpu.close()
+    eng = pkg.QasrCuda(0).load(model17)
+    try:
+        assert eng.batch_plan(3) == (1, 3)
+        got, _ = eng.transcribe_batch(units, 64)
+        assert [g.tolist() for g in got] == want
+    finally:
+        eng.close()
