@@ -1022,7 +1022,9 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
         snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: K must be a multiple of 8 and operands 16-byte aligned (K=%d)", K);
         return -1;
     }
-    if (M <= 256) { // weight-streaming regime: skinny-M kernel with split-K over ~148 CTAs
+    static int skinny_max_m = -1; // QASR_GEMM_SKINNY_MAX_M: largest M that takes the skinny kernel (experiments; default 256)
+    if (skinny_max_m < 0) { const char *ev = getenv("QASR_GEMM_SKINNY_MAX_M"); skinny_max_m = ev ? atoi(ev) : 256; if (skinny_max_m > 256) skinny_max_m = 256; }
+    if (M <= skinny_max_m) { // weight-streaming regime: skinny-M kernel with split-K over ~148 CTAs
         int dev = 0;
         cudaGetDevice(&dev);
         SkScratch &sc = g_sk[dev & 15];
