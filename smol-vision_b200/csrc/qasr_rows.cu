@@ -379,6 +379,208 @@ attn_prefill_batch_kernel(const float *__restrict__ q, const float *__restrict__
     attn_prefill_body(q + r0 * n_heads * 128, kpool + u * unit_stride + blockIdx.x * head_stride, vpool + u * unit_stride + blockIdx.x * head_stride, 0, P, P,
                       n_heads, n_kv_heads, scale, nullptr, ohi, olo, r0, blockIdx.x, ib, 128, 0);
 }
+// ------------------------------------------------------------------ causal GQA attention on tensor cores (prefill)
+// The same attention as attn_prefill_body (reference qwen_asr_kernels.c:1101-1148), with Q.K^T and P.V on mma.sync
+// (m16n8k16, bf16 in / f32 out).  The reference works in f32, so every operand is split a = hi + lo (two bf16) and each
+// product is the three-term sum hi.hi + hi.lo + lo.hi (the dropped lo.lo term is ~2^-18 relative): scores and outputs carry
+// ~16 mantissa bits, like the GEMMs.  CTA = (kv head, 32 query positions) = 64 query rows (both query heads of the
+// kv head share every K/V tile); warp w owns 16 rows (head w >> 1, positions 16 (w & 1) ...).  K/V tiles of 64 keys are read
+// from the f32 cache, split and stored as bf16 hi / lo planes in shared memory (16-byte chunks XOR-swizzled by the key, so
+// ldmatrix is conflict free); B fragments come from ldmatrix (.trans for V).  Online softmax per row in f32 (initial max
+// -1e30 like the reference).  kld / kcol: row pitch and first column of this kv head inside a K/V row.
+#define ATC_KT 64
+struct AttTcSmem {
+    uint16_t k[2][ATC_KT * 128]; // [plane hi/lo][key][dim], 256 B per key, chunk c stored at c ^ (key & 7)
+    uint16_t v[2][ATC_KT * 128];
+};
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t &hi, uint32_t &lo) { // (a, b) -> bf16x2 hi and bf16x2 lo (a in the low half)
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+    hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+}
+
+__device__ __forceinline__ void attn_prefill_tc_body(const float *__restrict__ q, const float *__restrict__ kc, const float *__restrict__ vc,
+                                                     int q_offset, int P, int seq_k, int n_heads, float scale, float *of, bf16_t *ohi, bf16_t *olo,
+                                                     size_t out_row0, int kvh, int ib, size_t kld, int kcol) {
+    extern __shared__ __align__(16) uint8_t att_raw[];
+    AttTcSmem &sm = *reinterpret_cast<AttTcSmem *>(att_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+    const size_t qld = (size_t)n_heads * 128;
+    const int head = kvh * 2 + (warp >> 1), p0 = ib + (warp & 1) * 16; // this warp: 16 positions of one query head
+    const int r0 = p0 + g, r1 = p0 + g + 8;                            // the two rows (positions) this thread holds
+    // Q fragments (A operand), hi / lo: k-step kk covers dims 16 kk .. 16 kk + 15
+    uint32_t qh[8][4], ql[8][4];
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) {
+        const int d0 = 16 * kk + 2 * t;
+        const float2 z = make_float2(0.f, 0.f);
+        const float2 a0 = r0 < P ? *reinterpret_cast<const float2 *>(q + (size_t)r0 * qld + head * 128 + d0) : z;
+        const float2 a1 = r1 < P ? *reinterpret_cast<const float2 *>(q + (size_t)r1 * qld + head * 128 + d0) : z;
+        const float2 a2 = r0 < P ? *reinterpret_cast<const float2 *>(q + (size_t)r0 * qld + head * 128 + d0 + 8) : z;
+        const float2 a3 = r1 < P ? *reinterpret_cast<const float2 *>(q + (size_t)r1 * qld + head * 128 + d0 + 8) : z;
+        split_pair(a0.x, a0.y, qh[kk][0], ql[kk][0]);
+        split_pair(a1.x, a1.y, qh[kk][1], ql[kk][1]);
+        split_pair(a2.x, a2.y, qh[kk][2], ql[kk][2]);
+        split_pair(a3.x, a3.y, qh[kk][3], ql[kk][3]);
+    }
+    const int hi0 = r0 < P ? min(q_offset + r0 + 1, seq_k) : 0, hi1 = r1 < P ? min(q_offset + r1 + 1, seq_k) : 0; // keys [0, hi) are attended
+    const int warp_hi = min(q_offset + min(p0 + 16, P), seq_k);         // keys any row of this warp attends
+    const int kmax_cta = min(q_offset + min(ib + 32, P), seq_k);
+    float m0 = -1e30f, m1 = -1e30f, l0 = 0.0f, l1 = 0.0f;
+    float o[16][4];
+#pragma unroll
+    for (int j = 0; j < 16; j++) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.0f;
+    const uint32_t sk_hi = (uint32_t)__cvta_generic_to_shared(sm.k[0]), sk_lo = (uint32_t)__cvta_generic_to_shared(sm.k[1]);
+    const uint32_t sv_hi = (uint32_t)__cvta_generic_to_shared(sm.v[0]), sv_lo = (uint32_t)__cvta_generic_to_shared(sm.v[1]);
+    const int lm = lane >> 3, lr = lane & 7; // ldmatrix: this lane addresses row lr of matrix lm
+
+    for (int t0 = 0; t0 < kmax_cta; t0 += ATC_KT) {
+        __syncthreads(); // the previous tile has been consumed
+        // K / V tile: 64 keys x 128 dims, f32 -> bf16 hi / lo planes (rows past the last needed key are zero)
+        for (int e = tid; e < ATC_KT * 32; e += 128) {
+            const int key = e >> 5, c4 = e & 31;
+            float4 kv4 = make_float4(0.f, 0.f, 0.f, 0.f), vv4 = kv4;
+            if (t0 + key < kmax_cta) {
+                kv4 = *reinterpret_cast<const float4 *>(kc + (size_t)(t0 + key) * kld + kcol + c4 * 4);
+                vv4 = *reinterpret_cast<const float4 *>(vc + (size_t)(t0 + key) * kld + kcol + c4 * 4);
+            }
+            const int off = key * 128 + ((((c4 >> 1) ^ (key & 7)) << 3) | ((c4 & 1) << 2)); // element offset of 4 consecutive dims
+            uint32_t h0, h1, l0w, l1w;
+            split_pair(kv4.x, kv4.y, h0, l0w); split_pair(kv4.z, kv4.w, h1, l1w);
+            *reinterpret_cast<uint2 *>(&sm.k[0][off]) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2 *>(&sm.k[1][off]) = make_uint2(l0w, l1w);
+            split_pair(vv4.x, vv4.y, h0, l0w); split_pair(vv4.z, vv4.w, h1, l1w);
+            *reinterpret_cast<uint2 *>(&sm.v[0][off]) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2 *>(&sm.v[1][off]) = make_uint2(l0w, l1w);
+        }
+        __syncthreads();
+        if (t0 >= warp_hi) continue; // causal: nothing in this tile for the rows of this warp (the barriers above stay CTA-uniform)
+        // ---- S = Q K^T over the 64 keys of the tile: 8 n-tiles of 8 keys
+        float sacc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; j++) sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int key = 8 * j + lr;
+#pragma unroll
+            for (int kk2 = 0; kk2 < 4; kk2++) { // dims 32 kk2 .. 32 kk2 + 31: matrices lm = 0..3 are the four 8-dim chunks
+                const uint32_t offb = (uint32_t)(key * 256 + (((4 * kk2 + lm) ^ (key & 7)) << 4));
+                uint32_t bh[4], bl[4];
+                ldsm_x4(bh, sk_hi + offb);
+                ldsm_x4(bl, sk_lo + offb);
+                mma_bf16_16816(sacc[j], qh[2 * kk2], bh[0], bh[1]);
+                mma_bf16_16816(sacc[j], qh[2 * kk2], bl[0], bl[1]);
+                mma_bf16_16816(sacc[j], ql[2 * kk2], bh[0], bh[1]);
+                mma_bf16_16816(sacc[j], qh[2 * kk2 + 1], bh[2], bh[3]);
+                mma_bf16_16816(sacc[j], qh[2 * kk2 + 1], bl[2], bl[3]);
+                mma_bf16_16816(sacc[j], ql[2 * kk2 + 1], bh[2], bh[3]);
+            }
+        }
+        // ---- online softmax: this thread holds keys t0 + 8 j + 2 t, + 1 of rows r0 (c0, c1) and r1 (c2, c3)
+        float mx0 = -1e30f, mx1 = -1e30f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int key = t0 + 8 * j + 2 * t;
+            sacc[j][0] = key < hi0 ? sacc[j][0] * scale : -INFINITY;
+            sacc[j][1] = key + 1 < hi0 ? sacc[j][1] * scale : -INFINITY;
+            sacc[j][2] = key < hi1 ? sacc[j][2] * scale : -INFINITY;
+            sacc[j][3] = key + 1 < hi1 ? sacc[j][3] * scale : -INFINITY;
+            mx0 = fmaxf(mx0, fmaxf(sacc[j][0], sacc[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(sacc[j][2], sacc[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+        const float c0 = expf(m0 - mn0), c1 = expf(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            sacc[j][0] = expf(sacc[j][0] - mn0); sacc[j][1] = expf(sacc[j][1] - mn0);
+            sacc[j][2] = expf(sacc[j][2] - mn1); sacc[j][3] = expf(sacc[j][3] - mn1);
+            s0 += sacc[j][0] + sacc[j][1];
+            s1 += sacc[j][2] + sacc[j][3];
+        }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        l0 = l0 * c0 + s0; l1 = l1 * c1 + s1;
+#pragma unroll
+        for (int j = 0; j < 16; j++) { o[j][0] *= c0; o[j][1] *= c0; o[j][2] *= c1; o[j][3] *= c1; }
+        // ---- O += P V: k-step kk covers keys 16 kk .. 16 kk + 15 = S n-tiles 2 kk and 2 kk + 1
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+            uint32_t ph[4], pl[4];
+            split_pair(sacc[2 * kk][0], sacc[2 * kk][1], ph[0], pl[0]);
+            split_pair(sacc[2 * kk][2], sacc[2 * kk][3], ph[1], pl[1]);
+            split_pair(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1], ph[2], pl[2]);
+            split_pair(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], ph[3], pl[3]);
+            const int key = 16 * kk + (lm & 1) * 8 + lr;
+#pragma unroll
+            for (int j2 = 0; j2 < 8; j2++) { // dim tiles 2 j2 and 2 j2 + 1
+                const uint32_t offb = (uint32_t)(key * 256 + (((2 * j2 + (lm >> 1)) ^ (key & 7)) << 4));
+                uint32_t vh[4], vl[4];
+                ldsm_x4_t(vh, sv_hi + offb);
+                ldsm_x4_t(vl, sv_lo + offb);
+                mma_bf16_16816(o[2 * j2], ph, vh[0], vh[1]);
+                mma_bf16_16816(o[2 * j2], ph, vl[0], vl[1]);
+                mma_bf16_16816(o[2 * j2], pl, vh[0], vh[1]);
+                mma_bf16_16816(o[2 * j2 + 1], ph, vh[2], vh[3]);
+                mma_bf16_16816(o[2 * j2 + 1], ph, vl[2], vl[3]);
+                mma_bf16_16816(o[2 * j2 + 1], pl, vh[2], vh[3]);
+            }
+        }
+    }
+    const float inv0 = l0 > 0.0f ? 1.0f / l0 : 0.0f, inv1 = l1 > 0.0f ? 1.0f / l1 : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const int col = head * 128 + 8 * j + 2 * t;
+        if (r0 < P) {
+            const size_t base = (out_row0 + (size_t)r0) * qld + col;
+            store_out(o[j][0] * inv0, base, of, ohi, olo);
+            store_out(o[j][1] * inv0, base + 1, of, ohi, olo);
+        }
+        if (r1 < P) {
+            const size_t base = (out_row0 + (size_t)r1) * qld + col;
+            store_out(o[j][2] * inv1, base, of, ohi, olo);
+            store_out(o[j][3] * inv1, base + 1, of, ohi, olo);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+attn_prefill_tc_kernel(const float *__restrict__ q, const float *__restrict__ kc, const float *__restrict__ vc, int q_offset, int P, int seq_k,
+                       int n_heads, int n_kv_heads, float scale, float *of, bf16_t *ohi, bf16_t *olo) {
+    pdl_trigger();
+    pdl_wait();
+    attn_prefill_tc_body(q, kc, vc, q_offset, P, seq_k, n_heads, scale, of, ohi, olo, 0, blockIdx.x, blockIdx.y * 32, (size_t)n_kv_heads * 128, blockIdx.x * 128);
+}
+__global__ void __launch_bounds__(128)
+attn_prefill_tc_batch_kernel(const float *__restrict__ q, const float *__restrict__ kpool, const float *__restrict__ vpool, size_t unit_stride,
+                             size_t head_stride, const int *__restrict__ row0, const int *__restrict__ Ps, int n_heads, float scale, bf16_t *ohi,
+                             bf16_t *olo) {
+    const int u = blockIdx.z, P = Ps[u], ib = blockIdx.y * 32;
+    if (ib >= P) return;
+    const size_t r0 = (size_t)row0[u];
+    attn_prefill_tc_body(q + r0 * n_heads * 128, kpool + u * unit_stride + blockIdx.x * head_stride, vpool + u * unit_stride + blockIdx.x * head_stride, 0, P, P,
+                         n_heads, scale, nullptr, ohi, olo, r0, blockIdx.x, ib, 128, 0);
+}
+static bool attn_use_tc() { // QASR_ATTN_FFMA=1: the f32 FFMA kernels of round 1 (A/B runs)
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("QASR_ATTN_FFMA"); v = !(e && e[0] == '1'); }
+    return v != 0;
+}
+
 static void attn_prefill_opt_in() { // per-device bit: the attribute belongs to the (function, device) pair
     static unsigned attr_set = 0;
     int dev = 0;
@@ -386,6 +588,8 @@ static void attn_prefill_opt_in() { // per-device bit: the attribute belongs to 
     if (!(attr_set >> (dev & 31) & 1u)) {
         cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttSmem<128>));
         cudaFuncSetAttribute(attn_prefill_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttSmem<128>));
+        cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttTcSmem));
+        cudaFuncSetAttribute(attn_prefill_tc_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AttTcSmem));
         attr_set |= 1u << (dev & 31);
     }
 }
@@ -393,6 +597,11 @@ void launch_attn_prefill(cudaStream_t s, const float *q, const float *kc, const 
                          int n_heads, int n_kv_heads, float scale, float *out_f32, bf16_t *out_hi, bf16_t *out_lo) {
     if (P <= 0) return;
     attn_prefill_opt_in();
+    // short prompts keep the FFMA kernel: its 16-position CTAs give twice the CTAs, and at P = 61 the kernel is pure latency
+    if (attn_use_tc() && n_heads == 2 * n_kv_heads && P >= 128) {
+        launch_pdl(attn_prefill_tc_kernel, dim3(n_kv_heads, (P + 31) / 32), 128, sizeof(AttTcSmem), s, q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, out_f32, out_hi, out_lo);
+        return;
+    }
     dim3 grid(n_kv_heads, (P + 15) / 16);
     launch_pdl(attn_prefill_kernel, grid, 256, sizeof(AttSmem<128>), s, q, kc, vc, q_offset, P, seq_k, n_heads, n_kv_heads, scale, out_f32, out_hi, out_lo);
 }
@@ -400,6 +609,10 @@ void launch_attn_prefill_batch(cudaStream_t s, const float *q, const float *kpoo
                                const int *d_row0, const int *d_P, int n_units, int max_P, int n_heads, int n_kv_heads, float scale, bf16_t *out_hi, bf16_t *out_lo) {
     if (n_units <= 0 || max_P <= 0) return;
     attn_prefill_opt_in();
+    if (attn_use_tc() && n_heads == 2 * n_kv_heads && max_P >= 128) {
+        attn_prefill_tc_batch_kernel<<<dim3(n_kv_heads, (max_P + 31) / 32, n_units), 128, sizeof(AttTcSmem), s>>>(q, kpool, vpool, unit_stride, head_stride, d_row0, d_P, n_heads, scale, out_hi, out_lo);
+        return;
+    }
     dim3 grid(n_kv_heads, (max_P + 15) / 16, n_units);
     attn_prefill_batch_kernel<<<grid, 256, sizeof(AttSmem<128>), s>>>(q, kpool, vpool, unit_stride, head_stride, d_row0, d_P, n_heads, n_kv_heads, scale, out_hi, out_lo);
 }
