@@ -144,6 +144,20 @@ def test_attention_production_shapes_vs_oracle(gpu06, oracle_lib):
     assert rel_err(gpu06.causal_attention(Qc, Kc, Vc, 16, 8, 128, sc, off), ref) < F32
 
 
+@pytest.mark.parametrize("P,off", [(128, 0), (201, 0), (150, 77), (404, 0)])
+def test_causal_attention_tensor_core_kernel_vs_oracle(gpu06, oracle_lib, P, off):
+    """Prompts of 128+ rows take attn_prefill_tc_kernel (mma.sync, bf16 hi/lo three-product form): ragged query blocks (P not
+    a multiple of 32), ragged key tiles (not a multiple of 64), a non-zero q_offset (delta prefill on top of cached keys) and
+    the configs[4] length.  Same 1e-5 bar as the f32 kernels: the split keeps ~16 mantissa bits."""
+    L = oracle_lib().lib
+    Qc, Kc, Vc = rnd((P, 2048), 50 + P), rnd((off + P, 1024), 51 + P), rnd((off + P, 1024), 52 + P)
+    ref = np.zeros_like(Qc)
+    L.qo_causal_attention.argtypes = [f32p, f32p, f32p, f32p] + [C.c_int] * 5 + [C.c_float, C.c_int]
+    sc = float(1.0 / np.sqrt(128.0))
+    L.qo_causal_attention(ref, Qc, Kc, Vc, P, off + P, 16, 8, 128, sc, off)
+    assert rel_err(gpu06.causal_attention(Qc, Kc, Vc, 16, 8, 128, sc, off), ref) < F32
+
+
 def test_conv2d_stem_shape_vs_oracle(gpu06, oracle_lib):
     L = oracle_lib().lib
     x, w, b = rnd((8, 64, 21), 40), rnd((6, 8, 3, 3), 41, 0.2), rnd((6,), 42, 0.1)
