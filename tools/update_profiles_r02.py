@@ -1,0 +1,95 @@
+"""Rewrites the '# Round 2' section of profiles/README.md from the committed r02_* artefacts (python tools/update_profiles_r02.py)."""
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = os.path.join(ROOT, "profiles")
+d = json.load(open(os.path.join(P, "r02_bench_default.json")))
+d2 = json.load(open(os.path.join(P, "r02_bench_default_2gpu.json")))
+d8 = json.load(open(os.path.join(P, "r02_bench_default_8gpu.json")))
+ref = json.load(open(os.path.join(P, "r02_bench_reference_arm.json")))
+ncu = json.load(open(os.path.join(P, "r02_ncu_summary.json")))
+st, st2, st8 = d["extra"]["strong"], d2["extra"]["strong"], d8["extra"]["strong"]
+
+
+def row(e):
+    return (f"| `{e['kernel'].split('(')[0].replace('void ', '')}` | {int(e.get('grid', 0))} | {e.get('duration_us', 0):.1f} | {e.get('dram_bytes', 0) / 1e6:.1f} | "
+            f"{e.get('dram_pct', 0):.1f} | {e.get('tensor_pipe_pct', 0):.1f} | {e.get('l2_throughput_pct', 0):.1f} | {e.get('warps_active_pct', 0):.1f} | {int(e.get('regs', 0))} |")
+
+
+names = {
+    "r2_ncu_skinny_prefill": "single-utterance prefill chain (1.7B, M = 61): `gemm_tc_skinny_kernel<64,6>` - WO, gate/up, down, QKV of two layers",
+    "r2_ncu_attn_prefill": "`attn_prefill_kernel` (P = 61)", "r2_ncu_attn_windowed": "`attn_windowed_kernel` (T = 47)",
+    "r2_ncu_gemm_batched_prefill": "batched prefill (16 x 30 s, 1.7B, M = 6464), persistent one-CTA `gemm_tc_kernel<256,3>` (before the 2-CTA variant) - gate/up, down, QKV, WO",
+    "r2_ncu_gemm_batched_encoder": "batched encoder (8 x 30 s per pass): `gemm_tc_kernel` - conv3, conv_out, QKV ...",
+    "r2_ncu_batched_misc": "batched conv stem of round 1: `conv1_kernel`, `im2col_stage_kernel` (stage 2 hi / lo, stage 3 hi / lo) - the im2col launches are gone since the implicit-GEMM conv",
+    "r2_ncu_attn_decode_batch": "`attn_decode_batch_kernel` (16 sequences, ~410 cached positions)"}
+tables = []
+for k, t in names.items():
+    tables.append(f"\n{t}:\n\n| kernel | grid | us | DRAM MB | DRAM % | tensor pipe % | L2 % | warps active % | regs |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|")
+    tables += [row(e) for e in ncu[k][:6]]
+
+s = f"""
+
+# Round 2
+
+| file | what | how |
+|---|---|---|
+| `r02_bench_default.json` | **default bench line of round 2**: configs[1] headline + `roofline_0p6b` + `extra.strong` (configs[4] 256 x 30 s and configs[2] 3600 s / 180 segments on the ranks of the run) + `gemm_rooflines` (algorithmic and issued) + cpu_baseline | `python bench.py` (about 50 s on the box) |
+| `r02_bench_default_2gpu.json`, `r02_bench_default_8gpu.json` | the same line on 2 and 8 GPUs | `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps 10 --warmup 3` |
+| `r02_bench_reference_arm.json` | reference arm: the reference's own CPU path (`oracle/_ref`, 16 host cores) | `python bench.py --impl reference --steps 3 --warmup 1` |
+| `r02_ncu_summary.json` | `ncu --set full` captures of the kernels VERDICT r1 asked evidence for: skinny GEMMs of the prefill chain at M = 61, `attn_prefill_kernel`, `attn_windowed_kernel`, the persistent large-tile GEMM in the batched prefill / encoder, conv stem kernels, `attn_decode_batch_kernel` | `bash tools/ncu_round2.sh` (each profiled command first exited 0 without ncu), summarised by `tools/ncu_summary.py` |
+| `r02_launches_batched_64x30s.csv.gz` | ncu launch list of the first version of the batched path: 64 x 30 s utterances, 1.7B, 3 decode steps | `ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/batch_profile.py 1.7b 64 30 3 1` |
+| `r02_batched_path.txt` | stage timings of the batched path vs group size, GEMM microbenchmark at the batched shapes (zero vs hashed operands, f32-store vs pipeline epilogues, one-CTA-per-tile vs persistent vs 2-CTA kernel), dropped variants | `tools/batch_profile.py`, `tools/gemm_bench.py batch|decode` |
+
+Regenerate this section: `python tools/update_profiles_r02.py`.
+
+## Headline and the north-star target model
+
+configs[1] (1.7B, 3.64 s, 32 tokens): {d['value']:.1f} x realtime device-timed, {d['e2e']['value']:.1f} x end to end ({d['ms_per_step']:.2f} ms per utterance: mel
+{d['stage_ms']['mel_ms']:.2f} + encoder {d['stage_ms']['enc_ms']:.2f} + prefill {d['stage_ms']['prefill_ms']:.2f} + decode {d['stage_ms']['decode_ms']:.2f} ms), decode step {d['roofline']['ms_per_launch']:.3f} ms = {d['roofline']['achieved']:.0f} GB/s =
+**{d['roofline']['frac']:.3f}** of the measured HBM peak; ids identical to the compiled reference (`cpu_baseline.ids_match_gpu` = {d['cpu_baseline']['ids_match_gpu']}); the reference's CPU path on the
+box's 16 host cores: {ref['value']:.2f} x realtime ({ref['ms_per_step']:.0f} ms). `roofline_0p6b` (0.6B, 11 s, 48 tokens): {d['roofline_0p6b']['ms_per_launch']:.3f} ms per step = {d['roofline_0p6b']['achieved']:.0f} GB/s =
+**{d['roofline_0p6b']['frac']:.3f}** - exchange-latency bound (DESIGN 8.1). `qasr_cuda_step_logits` runs the same kernel, so the logits-level parity
+tests pin what the bench times. 8 GPUs: {d8['value']:.0f} x (one replica per GPU, weak scaling).
+
+## The splits BASELINE.json names (`extra.strong`)
+
+| job | 1 GPU | 2 GPUs | 8 GPUs | sequences per weight pass (1 / 2 / 8 GPUs) | decode-step roofline, 1 GPU |
+|---|---:|---:|---:|---:|---:|
+| configs[4]: 256 x 30 s utterances, 1.7B, 128 tokens each | **{st['configs[4]']['value']:.0f} x** ({st['configs[4]']['ms_per_step'] / 1e3:.2f} s for 7680 s of audio, {st['configs[4]']['decoder_tok_s']:.0f} tokens/s; round 1: 405 x) | {st2['configs[4]']['value']:.0f} x | {st8['configs[4]']['value']:.0f} x | {st['configs[4]']['sequences_per_decode_step']} / {st2['configs[4]']['sequences_per_decode_step']} / {st8['configs[4]']['sequences_per_decode_step']} | {st['configs[4]']['roofline']['frac']:.2f} of the HBM peak (weights once + f32 KV rows of every sequence) |
+| configs[2]: 3600 s recording, -S 20 -W 3, 180 segments, 0.6B | **{st['configs[2]']['value']:.0f} x** ({st['configs[2]']['ms_per_step'] / 1e3:.2f} s, {st['configs[2]']['decoder_tok_s']:.0f} tokens/s; round 1: 770 x) | {st2['configs[2]']['value']:.0f} x | {st8['configs[2]']['value']:.0f} x | {st['configs[2]']['sequences_per_decode_step']} / {st2['configs[2]']['sequences_per_decode_step']} / {st8['configs[2]']['sequences_per_decode_step']} | {st['configs[2]']['roofline']['frac']:.2f} |
+
+(The 2-GPU line predates the 2-CTA GEMM, the implicit-GEMM conv and the tensor-core attention: 2.00 x of the one-GPU numbers of its day, 3020 / 3986 x.)
+Strong scaling is bounded by the shard size, not by a collective (there is none): at 8 GPUs a rank holds 32 utterances / 22-23 segments, so
+32 / 23 sequences share each pass over the weights instead of 128 / 90 (one GPU, 1.7B: 24.2k / 17.5k / 12.2k tokens/s at 128 / 64 / 32 sequences per
+step) and the encoder / prefill GEMMs run at a quarter of the rows; slowest / mean rank {st8['configs[4]']['rank_ms']['imbalance']:.3f} (configs[4]) and {st8['configs[2]']['rank_ms']['imbalance']:.3f} (configs[2]).
+
+## GEMM rooflines (`gemm_rooflines`: hashed non-zero operands, the epilogue of the pipeline)
+
+| shape | us | 2MNK TFLOP/s | frac_algorithmic | frac_issued (hi + lo MMAs) |
+|---|---:|---:|---:|---:|
+"""
+for g in d["gemm_rooflines"]:
+    if g["bound"] == "tensor":
+        s += f"| {g['shape']} | {g['us']:.1f} | {g['achieved']:.0f} | {g['frac_algorithmic']:.2f} | {g['frac_issued']:.2f} |\n"
+    else:
+        s += f"| {g['shape']} (weight stream) | {g['us']:.1f} | {g['achieved']:.0f} GB/s | {g['frac']:.2f} of the HBM peak | - |\n"
+s += """
+Peak = 1653.5 TFLOP/s (MEASURED_PEAKS.json, cuBLAS burst). The hi/lo split of the f32 activations issues two MMAs per k-block,
+so `frac_algorithmic` = `frac_issued` / 2 by construction; the M = 25856 shapes run as CTA pairs (`tcgen05.mma.cta_group::2`). ncu on the
+one-CTA persistent kernel showed the tensor pipe 74-92 % active on the batched prefill GEMMs. All-zero operands (round 1's
+microbenchmark) read ~25 % higher than hashed ones (power), and the f32-store epilogue hid the cost of the SwiGLU / GELU / residual
+epilogues: see `r02_batched_path.txt`.
+
+## ncu --set full (`r02_ncu_summary.json`)
+""" + "\n".join(tables) + """
+
+Reading: the single-utterance chains are launch / latency bound (DRAM 8-22 %, 80-96 CTAs, 14-28 us per GEMM; attention 10-14 us
+on 32-64 CTAs). The batched GEMMs are tensor-pipe bound (74-92 %). `attn_decode_batch_kernel` streams the f32 KV rows (2.1 TB/s
+at 16 sequences / 128 CTAs, 4.6-5.3 TB/s at 64-128 sequences).
+"""
+readme = open(os.path.join(P, "README.md")).read()
+i = readme.find("\n\n# Round 2")
+open(os.path.join(P, "README.md"), "w").write((readme[:i] if i >= 0 else readme) + s)
+print("profiles/README.md: round-2 section rewritten")
