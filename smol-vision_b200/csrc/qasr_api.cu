@@ -519,8 +519,14 @@ static int load_from(qasr_ctx_t *c, qst_dir_t *st) {
             const DecLayerW &L = c->dec[l];
             mats.push_back(L.wqkv); mats.push_back(L.wo); mats.push_back(L.wgu); mats.push_back(L.wdown);
         }
-        if (stream_build_image(c->stream, c->dec_layers, H, I, c->V, mats.data(), c->emb, c->sk_cta_off, c->sk_image) != 0)
+        if (stream_build_image(c->stream, c->dec_layers, H, I, c->V, mats.data(), c->emb, c->sk_cta_off, c->sk_image, 0) != 0)
             return set_err(QASR_ERR_CUDA, "%s", stream_error());
+        if (stream_use_rounds(H)) { // second copy, round-major, for the single-sequence producer / consumer kernel (qasr_stream_r.cu)
+            c->sk_image_r = (uint8_t *)dev_alloc(c, image_bytes);
+            if (!c->sk_image_r) return set_err(QASR_ERR_NOMEM, "decode weight image, round-major (%zu bytes)", image_bytes);
+            if (stream_build_image(c->stream, c->dec_layers, H, I, c->V, mats.data(), c->emb, c->sk_cta_off, c->sk_image_r, 1) != 0)
+                return set_err(QASR_ERR_CUDA, "%s", stream_error());
+        }
         CK(cudaStreamSynchronize(c->stream));
         const size_t NS = QASR_STREAM_MAX_SEQS;
         c->ll_qkv = (unsigned long long *)dalloc(NS * 4096 * 8); c->ll_att = (unsigned long long *)dalloc(NS * QASR_STREAM_ATT_WORDS * 8);
@@ -930,7 +936,7 @@ static int enqueue_steps(qasr_ctx_t *c, int n, int nseq = 1) {
     if (nseq != 1 && !c->use_stream) return set_err(QASR_ERR_STATE, "batched decode needs the stream kernel (unset QASR_DECODE)");
     if (c->use_stream) { // one persistent cooperative launch runs all n steps (stops itself after an EOS token)
         StreamParams p = {};
-        p.image = c->sk_image; p.cta_off = c->sk_cta_off;
+        p.image = c->sk_image; p.image_r = c->sk_image_r; p.cta_off = c->sk_cta_off;
         p.n_layers = c->dec_layers; p.H = c->H; p.I = c->I; p.V = c->V; p.n_steps = n; p.eps = 1e-6f;
         p.emb = c->emb; p.final_norm = c->final_norm;
         for (int l = 0; l < c->dec_layers; l++) {

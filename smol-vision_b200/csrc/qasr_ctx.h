@@ -96,6 +96,7 @@ struct qasr_ctx {
     bool use_graph = true;
     bool use_stream = true; // persistent cooperative decode kernel of qasr_stream.cu (default); QASR_DECODE=graph selects the per-phase kernels
     uint8_t *sk_image = nullptr;           // decode weight image (pre-tiled, per-warp streams)
+    uint8_t *sk_image_r = nullptr;         // the same units round-major (single-sequence producer / consumer kernel)
     unsigned long long *sk_cta_off = nullptr;
     unsigned long long *ll_qkv = nullptr, *ll_att = nullptr, *ll_xwo = nullptr, *ll_act = nullptr, *ll_xdn = nullptr, *ll_head = nullptr;
     unsigned sk_tag = 1;                   // next free exchange tag

@@ -94,6 +94,7 @@ void launch_embed_gather(cudaStream_t s, const bf16_t *E, const int *d_ids, int 
 // ---- streaming decode kernel (qasr_stream.cu): pre-tiled weight image + flag-in-data exchanges
 struct StreamParams {
     const uint8_t *image;                  // decode weight image (units of 16x64 bf16 in A-fragment order, per-warp streams)
+    const uint8_t *image_r;                // the same units round-major (qasr_stream_r.cu), or NULL
     const unsigned long long *cta_off;     // [grid+1] byte offsets of each CTA's 16 streams
     int n_layers, H, I, V, n_steps;
     float eps;
@@ -115,6 +116,7 @@ struct StreamParams {
     int trace_cta;                         // CTA whose warp 0 writes the per-unit trace (debug bit 6)
     int l2_issue;                          // units prefetched per poll iteration
     int l2_ahead_units;                    // second-level prefetch distance into L2, in 2 KB units per warp (0 = off)
+    int sr_chunk, sr_pace_pct;             // producer of qasr_stream_r.cu: bytes per bulk copy, pacing (percent of the previous step's layer time; 0 = unpaced)
     float *dbg_logits;                     // test hook (NULL in production): [nseq][V] logits of the LAST step of the launch
     float *dbg_hidden;                     // test hook (NULL in production): [nseq][H] post-final-norm hidden state
 };
@@ -123,8 +125,10 @@ int stream_grid(void);
 int stream_max_seqs(int H, int I);
 size_t stream_image_layout(int L, int H, int I, int V, unsigned long long *cta_off_host /* [grid+1] */);
 int stream_build_image(cudaStream_t s, int L, int H, int I, int V, const bf16_t *const *layer_mats /* [L*4] */, const bf16_t *emb,
-                       const unsigned long long *d_cta_off, uint8_t *image);
+                       const unsigned long long *d_cta_off, uint8_t *image, int round_major);
 int launch_decode_stream(cudaStream_t s, const StreamParams &p);
+bool stream_use_rounds(int H);
+int launch_decode_rounds(cudaStream_t s, const StreamParams &p, int grid, char *err, size_t errlen); // qasr_stream_r.cu
 const char *stream_error(void);
 #define QASR_STREAM_MAX_SEQS 4
 #define QASR_STREAM_ATT_WORDS (16 * 4 * 130) /* per sequence: 16 heads x SK_ATT_MAXS splits x (128 acc + m + l) */

@@ -37,56 +37,16 @@
 // Phases per layer:  QKV | ATTN | WO(+residual) | GU(+SwiGLU) | DOWN(+residual); then HEAD (per-CTA argmax,
 // exchange of the 148 winners, lowest index wins ties, reference qwen_asr_kernels.c:536-541) and the embedding
 // gather of the next input row by every CTA.
-#include "qasr_common.cuh"
-#include "qasr_internal.h"
-
-#include <stdio.h>
-#include <stdlib.h>
-#include <type_traits>
-
-#define SK_WARPS 16
-#define SK_THREADS (SK_WARPS * 32)
-#define SK_UNIT 2048          /* 16 rows x 64 cols bf16, A-fragment order: [kb 0..3][lane][a0..a3] */
-#define SK_CHUNK_GROUPS 8     /* 16-row groups reduced together (128 rows) */
-#define SK_PSTRIDE 17
-#define SK_MAX_K 6144
-#define SK_MAX_H 2048
-#ifndef SK_ATT_MAXS
-#define SK_ATT_MAXS 4         /* key splits per (sequence, head); measured: 4 > 8 (the merge at the WO stage grows with it) */
-#endif
-#ifndef SK_ATT_BATCH
-#define SK_ATT_BATCH 2        /* cached keys per warp whose K/V rows are loaded ahead of the q words; a split holds 32 keys per batch */
-#endif
-#define SK_ATT_STRIDE 130     /* 128 acc + m + l */
-// p.debug bits: 4 = stall-driven L2 prefetch without the evict_last hint, 64 = per-unit trace of warp 0 of CTA p.trace_cta
-
-typedef unsigned long long u64;
-
-// ---- static schedule, shared by the re-tiling kernel and the decode kernel ---------------------
-struct SkDims { int L, H, I, V, G; };
-__host__ __device__ __forceinline__ void sk_phase_shape(const SkDims &d, int wp, int &N, int &K) {
-    if (wp < 4 * d.L) {
-        switch (wp & 3) {
-            case 0: N = 4096; K = d.H; break;
-            case 1: N = d.H; K = 2048; break;
-            case 2: N = 2 * d.I; K = d.H; break;
-            default: N = d.H; K = d.I; break;
-        }
-    } else { N = d.V; K = d.H; }
-}
-__host__ __device__ __forceinline__ int sk_g0(int NG, int b, int G) { return (int)((unsigned)NG * (unsigned)b / (unsigned)G); }
-// units per warp of CTA b in phase wp
-__host__ __device__ __forceinline__ int sk_phase_units(const SkDims &d, int wp, int b) {
-    int N, K;
-    sk_phase_shape(d, wp, N, K);
-    return (sk_g0(N >> 4, b + 1, d.G) - sk_g0(N >> 4, b, d.G)) * (K >> 10);
-}
+#include "qasr_stream_common.cuh"
+#include <string.h>
 
 // ---- re-tiling: row-major [N, K] bf16 -> the image (one CTA per (cta b, phase wp)) -------------
 struct RetileArgs {
     const bf16_t *src[28 * 4 + 1];
 };
-__global__ void __launch_bounds__(SK_THREADS) sk_retile_kernel(const RetileArgs a, SkDims d, const u64 *cta_off, uint8_t *image) {
+// round_major: the 16 units of a (group, j) round contiguous, in the order the 8 consumer warps of qasr_stream_r.cu read
+// them (warp w: old streams w, w + 8); otherwise one contiguous stream per warp.
+__global__ void __launch_bounds__(SK_THREADS) sk_retile_kernel(const RetileArgs a, SkDims d, const u64 *cta_off, uint8_t *image, int round_major) {
     const int b = blockIdx.x, wp = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
     __shared__ int s_off;
@@ -100,13 +60,15 @@ __global__ void __launch_bounds__(SK_THREADS) sk_retile_kernel(const RetileArgs 
     sk_phase_shape(d, wp, N, K);
     const int g0 = sk_g0(N >> 4, b, d.G), g1 = sk_g0(N >> 4, b + 1, d.G), nj = K >> 10;
     const u64 slen = (cta_off[b + 1] - cta_off[b]) / SK_WARPS;
-    uint8_t *dst = image + cta_off[b] + (u64)warp * slen + (u64)s_off * SK_UNIT;
+    uint8_t *dst = round_major ? image + cta_off[b] + (u64)s_off * (SK_WARPS * SK_UNIT) + (u64)((warp & 7) * 2 + (warp >> 3)) * SK_UNIT
+                               : image + cta_off[b] + (u64)warp * slen + (u64)s_off * SK_UNIT;
+    const size_t ustride = round_major ? (size_t)SK_WARPS * SK_UNIT : (size_t)SK_UNIT;
     const uint32_t *W = reinterpret_cast<const uint32_t *>(a.src[wp]); // pairs of bf16
     const size_t ldw = (size_t)K >> 1;
     for (int g = g0; g < g1; g++)
         for (int j = 0; j < nj; j++) {
             const int slice = warp + 16 * j;
-            uint4 *u = reinterpret_cast<uint4 *>(dst + (size_t)((g - g0) * nj + j) * SK_UNIT);
+            uint4 *u = reinterpret_cast<uint4 *>(dst + (size_t)((g - g0) * nj + j) * ustride);
 #pragma unroll
             for (int kb = 0; kb < 4; kb++) {
                 const size_t c = (size_t)(slice * 64 + kb * 16 + 2 * tig) >> 1;
@@ -117,68 +79,6 @@ __global__ void __launch_bounds__(SK_THREADS) sk_retile_kernel(const RetileArgs 
             }
         }
 }
-
-// ---- device helpers ----------------------------------------------------------------------------
-__device__ __forceinline__ void sk_csync() { asm volatile("bar.sync 1, %0;" ::"n"(SK_THREADS) : "memory"); }
-__device__ __forceinline__ uint32_t sk_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ll_store(u64 *p, float v, unsigned tag) {
-    const u64 w = ((u64)tag << 32) | (u64)__float_as_uint(v);
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ void ll_store_u32(u64 *p, unsigned v, unsigned tag) {
-    const u64 w = ((u64)tag << 32) | (u64)v;
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
-}
-__device__ __forceinline__ void ll_load2(const u64 *p, u64 &a, u64 &b) {
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
-}
-__device__ __forceinline__ u64 ll_load1(const u64 *p) {
-    u64 a;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
-    return a;
-}
-// All poll loops are warp-uniform (the whole warp stays in the loop until every lane has its words), so the
-// service functor - the weight-stream top-up, whose cursor state must stay identical across lanes - runs converged.
-template <class Svc>
-__device__ __forceinline__ float ll_wait1(const u64 *p, unsigned tag, bool active, Svc &&svc) {
-    u64 w = active ? ll_load1(p) : (u64)tag << 32;
-    for (;;) {
-        const bool ok = (unsigned)(w >> 32) == tag;
-        if (__all_sync(QASR_FULL, ok)) break;
-        svc();
-        if (!ok) w = ll_load1(p);
-    }
-    return __uint_as_float((unsigned)w);
-}
-// Poll NP pairs of consecutive words per thread (pair p = tid + i*512, valid while p < npairs).
-template <int NP, class Svc>
-__device__ __forceinline__ void ll_gather_pairs(const u64 *buf, int npairs, unsigned tag, int tid, float (&v)[NP][2], Svc &&svc) {
-    u64 w[NP][2];
-#pragma unroll
-    for (int i = 0; i < NP; i++) {
-        const int p = tid + i * SK_THREADS;
-        if (p < npairs) ll_load2(buf + 2 * p, w[i][0], w[i][1]);
-        else w[i][0] = w[i][1] = (u64)tag << 32;
-    }
-    for (;;) {
-        bool ok = true;
-#pragma unroll
-        for (int i = 0; i < NP; i++) ok = ok && (unsigned)(w[i][0] >> 32) == tag && (unsigned)(w[i][1] >> 32) == tag;
-        if (__all_sync(QASR_FULL, ok)) break;
-        svc();
-#pragma unroll
-        for (int i = 0; i < NP; i++)
-            if ((unsigned)(w[i][0] >> 32) != tag || (unsigned)(w[i][1] >> 32) != tag) ll_load2(buf + 2 * (tid + i * SK_THREADS), w[i][0], w[i][1]);
-    }
-#pragma unroll
-    for (int i = 0; i < NP; i++) { v[i][0] = __uint_as_float((unsigned)w[i][0]); v[i][1] = __uint_as_float((unsigned)w[i][1]); }
-}
-
-__device__ __forceinline__ uint32_t sk_pack_bf16(float a, float b) {
-    const __nv_bfloat162 v = __floats2bfloat162_rn(a, b); // .x = a (low half)
-    return *reinterpret_cast<const uint32_t *>(&v);
-}
-__device__ __forceinline__ bool sk_better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
 
 __device__ __forceinline__ float sk_block_sum(float v, float *red, int tid) {
     v = warp_sum(v);
@@ -205,16 +105,6 @@ struct SkLayout {
     static constexpr size_t small_bytes = (64 + NSEQ * SK_WARPS + SK_WARPS + NSEQ * 16 * SK_ATT_MAXS) * 4;
     static __host__ __device__ size_t total(int kmax, int H) { return ring_bytes + xf_bytes(kmax) + x_bytes(H) + partial_bytes + small_bytes + 1024; }
 };
-
-// elements (2p, 2p+1) of sequence s -> hi / lo words of the B-fragment image ([kb][lane = column*4 + tig][2 regs])
-template <int NSEQ>
-__device__ __forceinline__ void sk_put_pair(uint32_t *xf, int s, int p, float v0, float v1) {
-    const float h0 = __bfloat162float(__float2bfloat16_rn(v0)), h1 = __bfloat162float(__float2bfloat16_rn(v1));
-    const int kb = p >> 3, jj = p & 7, tig = jj & 3, reg = jj >> 2;
-    uint32_t *q = xf + kb * (16 * NSEQ) + 16 * s + tig * 2 + reg;
-    q[0] = sk_pack_bf16(v0, v1);            // column 2s   : x_hi
-    q[8] = sk_pack_bf16(v0 - h0, v1 - h1);  // column 2s+1 : x_lo
-}
 
 template <int NSEQ, int SLOTS>
 __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const StreamParams p) {
@@ -960,17 +850,26 @@ size_t stream_image_layout(int L, int H, int I, int V, unsigned long long *cta_o
 }
 
 int stream_build_image(cudaStream_t s, int L, int H, int I, int V, const bf16_t *const *layer_mats /* [L*4] */, const bf16_t *emb,
-                       const unsigned long long *d_cta_off, uint8_t *image) {
+                       const unsigned long long *d_cta_off, uint8_t *image, int round_major) {
     if (stream_init() != 0) return -1;
     if (!sk_dims_ok(L, H, I, V)) { snprintf(g_sk_err, sizeof g_sk_err, "decode stream kernel: unsupported dims L=%d H=%d I=%d V=%d", L, H, I, V); return -1; }
     RetileArgs a;
     for (int i = 0; i < 4 * L; i++) a.src[i] = layer_mats[i];
     a.src[4 * L] = emb;
     SkDims d{L, H, I, V, stream_grid()};
-    sk_retile_kernel<<<dim3(d.G, 4 * L + 1), SK_THREADS, 0, s>>>(a, d, d_cta_off, image);
+    sk_retile_kernel<<<dim3(d.G, 4 * L + 1), SK_THREADS, 0, s>>>(a, d, d_cta_off, image, round_major);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_sk_err, sizeof g_sk_err, "re-tile launch: %s", cudaGetErrorString(e)); return -1; }
     return 0;
+}
+
+// Which single-sequence kernel: the producer / consumer kernel over round-major weights (qasr_stream_r.cu) or the per-lane
+// cp.async ring kernel.  QASR_DECODE_KERNEL=ring | rounds overrides the default.
+bool stream_use_rounds(int H) {
+    static int mode = -1; // 0 = default, 1 = ring, 2 = rounds
+    if (mode < 0) { const char *e = getenv("QASR_DECODE_KERNEL"); mode = e && !strcmp(e, "ring") ? 1 : (e && !strcmp(e, "rounds") ? 2 : 0); }
+    (void)H;
+    return mode != 1;
 }
 
 // Largest number of sequences one launch can carry for these dims (shared memory: the DOWN input image is K x 4 B per sequence)
@@ -986,6 +885,7 @@ int launch_decode_stream(cudaStream_t s, const StreamParams &p) {
     void *args[] = {(void *)&p};
     const int grid = stream_grid();
     const int kmax = p.I > 2048 ? p.I : 2048;
+    if (p.nseq == 1 && p.image_r && stream_use_rounds(p.H)) return launch_decode_rounds(s, p, grid, g_sk_err, sizeof g_sk_err);
     cudaError_t e;
     if (p.nseq == 1)
         e = cudaLaunchCooperativeKernel((const void *)decode_stream_kernel<1, 5>, dim3(grid), dim3(SK_THREADS), args, SkLayout<1, 5>::total(kmax, p.H), s);
