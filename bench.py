@@ -104,6 +104,15 @@ def gemm_rooflines(eng):
     return out
 
 
+def decode_kernel_name(cfg):
+    """The single-sequence decode kernel the library picks for these dims (qasr_stream.cu: stream_use_rounds)."""
+    mode = os.environ.get("QASR_DECODE_KERNEL", "")
+    rounds = mode == "rounds" or (mode != "ring" and cfg["dec_hidden"] <= 1024)
+    return ("decode_rounds_kernel (persistent cooperative kernel, qasr_stream_r.cu: TMA producer warp + 8 consumer warps over a round-major weight image; a launch runs up to 16 steps)"
+            if rounds else
+            "decode_stream_kernel (persistent cooperative kernel, qasr_stream.cu: per-lane cp.async weight ring; a launch runs up to 16 steps)")
+
+
 def decode_bytes_per_step(cfg, kv_positions):
     """Algorithmic bytes of one decode step: bf16 decoder-layer weights + tied lm_head
     + f32 KV rows read (229 376 B per cached position)."""
@@ -357,7 +366,7 @@ def measure_multi(pkg, eng, workload, rank, local_rank, world, dist, recording_s
     kv_bytes = decode_bytes_per_step(eng.cfg, kv_avg) - w_bytes
     step_bytes = w_bytes + group * kv_bytes          # one pass over the weights + the KV rows of every sequence of the group
     achieved = step_bytes / (dec_ms_per_step * 1e-3) / 1e9
-    kernel = ("one greedy step of decode_stream_kernel" if group <= eng.max_batch else
+    kernel = ("one greedy step of decode_stream_kernel<NSEQ> (qasr_stream.cu)" if group <= eng.max_batch else
               "one decode step of the batched path: 28 x (4 skinny tcgen05 GEMMs + attn_decode_batch_kernel) + lm_head GEMM + argmax, one CUDA graph")
     out = {"metric": "realtime_factor", "value": audio_total * steps / (dev_ms / 1e3), "unit": "x realtime (audio s / wall s)", "n_gpus": world,
            "steps": steps, "warmup": 1, "ms_per_step": dev_ms / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
@@ -423,7 +432,7 @@ def single_decode_roofline(pkg, eng, workload, steps=8):
     step_bytes = decode_bytes_per_step(eng.cfg, info["enc_tokens"] + 15 + max_new / 2.0)
     ach = step_bytes / (ms * 1e-3) / 1e9
     return {"workload": desc, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "frac_of_8000_nominal": ach / 8000.0,
-            "peak_source": peak_src, "kernel": "one greedy step of decode_stream_kernel", "bytes_per_launch": step_bytes, "ms_per_launch": ms,
+            "peak_source": peak_src, "kernel": "one greedy step of " + decode_kernel_name(eng.cfg), "bytes_per_launch": step_bytes, "ms_per_launch": ms,
             "decoder_tok_s": 1000.0 / ms, "traffic": None, "traffic_source": None}
 
 
@@ -570,7 +579,7 @@ def main():
                "ids_head": ids[:8],
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                            "kernel": "one greedy step of decode_stream_kernel (persistent cooperative kernel, qasr_stream.cu; a launch runs up to 16 steps)",
+                            "kernel": "one greedy step of " + decode_kernel_name(eng.cfg),
                             "bytes_per_launch": step_bytes, "ms_per_launch": dec_ms_per_step,
                             "frac_of_8000_nominal": achieved / 8000.0}}
         if strong is not None:

@@ -131,7 +131,7 @@ bool stream_use_rounds(int H);
 int launch_decode_rounds(cudaStream_t s, const StreamParams &p, int grid, char *err, size_t errlen); // qasr_stream_r.cu
 const char *stream_error(void);
 #define QASR_STREAM_MAX_SEQS 4
-#define QASR_STREAM_ATT_WORDS (16 * 4 * 130) /* per sequence: 16 heads x SK_ATT_MAXS splits x (128 acc + m + l) */
+#define QASR_STREAM_ATT_WORDS (16 * 4 * 132) /* per sequence: 16 heads x SK_ATT_MAXS splits x (128 acc + m + l + 2 pad) */
 
 // ---- row-wise / prefill / encoder kernels (qasr_rows.cu)
 void launch_rmsnorm(cudaStream_t s, const float *x, const float *gamma, float eps, int M, int H, float *out_f32,

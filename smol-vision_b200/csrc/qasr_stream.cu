@@ -718,8 +718,8 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
 #pragma unroll
             for (int w = 1; w < WPS; w++)
                 if (sk_better(sm_red[tid * WPS + w], sm_redi[tid * WPS + w], v, ix)) { v = sm_red[tid * WPS + w]; ix = sm_redi[tid * WPS + w]; }
-            ll_store(p.ll_head + (size_t)tid * 2048 + 2 * b, v, htag);
-            ll_store_u32(p.ll_head + (size_t)tid * 2048 + 2 * b + 1, (unsigned)ix, htag);
+            ll_store(p.ll_head + (size_t)tid * 2048 + 4 * b, v, htag);
+            ll_store_u32(p.ll_head + (size_t)tid * 2048 + 4 * b + 1, (unsigned)ix, htag);
         }
         int toks[NSEQ];
 #pragma unroll 1
@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(SK_THREADS, 1) decode_stream_kernel(const Stre
             int wi = 0x7fffffff;
             {
                 const bool active = tid < G;
-                const u64 *hp2 = p.ll_head + (size_t)s * 2048 + 2 * tid;
+                const u64 *hp2 = p.ll_head + (size_t)s * 2048 + 4 * tid; // one 32-byte sector per CTA: two writers never share a sector
                 u64 w0 = (u64)htag << 32, w1 = (u64)htag << 32;
                 if (active) ll_load2(hp2, w0, w1);
                 for (;;) {
@@ -868,8 +868,7 @@ int stream_build_image(cudaStream_t s, int L, int H, int I, int V, const bf16_t 
 bool stream_use_rounds(int H) {
     static int mode = -1; // 0 = default, 1 = ring, 2 = rounds
     if (mode < 0) { const char *e = getenv("QASR_DECODE_KERNEL"); mode = e && !strcmp(e, "ring") ? 1 : (e && !strcmp(e, "rounds") ? 2 : 0); }
-    (void)H;
-    return mode != 1;
+    return mode == 2 || (mode == 0 && H <= 1024); // measured: 0.6B 455 -> 400 us/token, 1.7B 709 -> 757 (HBM-bound phases want the deeper ring)
 }
 
 // Largest number of sequences one launch can carry for these dims (shared memory: the DOWN input image is K x 4 B per sequence)

@@ -22,7 +22,7 @@
 #ifndef SK_ATT_BATCH
 #define SK_ATT_BATCH 2        /* cached keys per warp whose K/V rows are loaded ahead of the q words; a split holds 32 keys per batch */
 #endif
-#define SK_ATT_STRIDE 130     /* 128 acc + m + l */
+#define SK_ATT_STRIDE 132     /* 128 acc + m + l, padded to whole 32-byte sectors: writers of neighbouring blocks never share a sector (2.4 x slower exchange when they do, tools/microbench/ll_exchange2.cu) */
 // p.debug bits: 4 = stall-driven L2 prefetch without the evict_last hint, 64 = per-unit trace of warp 0 of CTA p.trace_cta
 
 typedef unsigned long long u64;

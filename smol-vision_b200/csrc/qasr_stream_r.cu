@@ -14,7 +14,7 @@
 //  * the producer warp (one elected lane) keeps up to 6 rounds in flight: mbarrier expect_tx + ONE cp.async.bulk of
 //    32 KB per round, and a cp.async.bulk.prefetch.L2 a fixed number of rounds further ahead;
 //  * consumer warp w reads its 4 KB of a round (column slices w + 16 j and w + 8 + 16 j of the same 16 rows) with eight
-//    conflict-free LDS.128 after an mbarrier wait that has normally long completed, runs 8 MMAs on four independent
+//    conflict-free LDS.128 after an mbarrier wait that has normally long completed, runs 8 MMAs on two independent
 //    accumulator chains and releases the slot with one arrive per warp.
 // 8 consumer warps x <= 224 registers leave room for every exchange word of a thread to be in flight at once.
 #include "qasr_stream_common.cuh"
@@ -26,8 +26,22 @@
 #define SR_MAX_SLOTS 6
 #define SR_PSTRIDE 9
 #define SR_ATT_BATCH 4        /* cached keys per warp and batch: 8 warps x 4 = 32 keys per split, as in the ring kernel */
-#define SR_ATT_STRIDE 132     /* 128 acc + m + l, padded to whole 32-byte sectors: two writers never share a sector */
+#define SR_ATT_STRIDE SK_ATT_STRIDE
 #define SR_HEAD_STRIDE 4
+#ifndef SR_CHAINS
+#define SR_CHAINS 2           /* independent MMA accumulator chains per round (2 or 4) */
+#endif
+#ifndef SR_ROUND_INFLIGHT
+#define SR_ROUND_INFLIGHT 0   /* 1: all 16 operand loads of a round in flight before the first MMA (48 operand registers instead of 24) */
+#endif
+#ifndef SR_FAST_EXP
+#define SR_FAST_EXP 0
+#endif
+#if SR_FAST_EXP
+#define sr_exp __expf
+#else
+#define sr_exp expf
+#endif
 #ifndef SR_MERGE_PG
 #define SR_MERGE_PG 2         /* pairs per thread whose S x 4 exchange words are in flight together when the keys are split */
 #endif      /* words per CTA in the head exchange (one sector) */
@@ -62,6 +76,7 @@ struct SrLayout { // dynamic shared memory: ring | xf | x | partial | small | ba
     static __host__ __device__ size_t total(int nslot, int kmax, int H) { return ring_bytes(nslot) + rest(kmax, H); }
 };
 
+template <int NPX> // pairs of the hidden vector per consumer thread: H = 512 NPX
 __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const StreamParams p, const int nslot) {
     extern __shared__ __align__(128) uint8_t sr_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -136,16 +151,22 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
         return;
     }
     uint32_t cslot = 0, cpar = 0, consumed = 0; // consumer cursor: ring slot, parity of its full barrier, rounds consumed
-    auto no_svc = []() {};
+    auto no_svc = []() {}; // stall-driven L2 prefetch from the polling warps (the ring kernel's hook) was measured here too: no gain, dropped
 
     long long *prof = (p.prof && (b == 0 || b == G - 1) && tid == 0) ? p.prof + (b == 0 ? 0 : p.prof_cap) : nullptr;
     int prof_n = 0;
     auto mark = [&]() { if (prof && prof_n < p.prof_cap) prof[prof_n++] = clock64(); };
-    const bool fine = (p.debug & 128) != 0; // extra stamps inside every layer phase: B fragments read | MMAs done | after bar.sync | after the epilogue
-    bool finer = (p.debug & 256) != 0; // + per unit: B fragments requested | MMAs issued | refill issued
-    // one round for this warp: 16 rows x (64 + 64) columns against the phase input, four independent accumulator chains
-    auto do_round = [&](int j, float(&c)[4][4]) {
+#ifdef SR_FINE_PROF // -DSR_FINE_PROF: finer stamps for tools/mega_prof_fine.py (costs registers: not in the product build)
+    const bool fine = (p.debug & 128) != 0; // extra stamps inside every layer phase: MMAs done | after bar.sync | after the epilogue
+    bool finer = (p.debug & 256) != 0;      // + per round: A fragments requested | MMAs issued
+#else
+    constexpr bool fine = false;
+    bool finer = false;
+#endif
+    // one round for this warp: 16 rows x (64 + 64) columns against the phase input, two independent accumulator chains
+    auto do_round = [&](int j, float(&c)[SR_CHAINS][4]) {
         const uint2 *xb = reinterpret_cast<const uint2 *>(sm_xf) + (size_t)(warp + 16 * j) * 32 + (lane & 7);
+#if SR_ROUND_INFLIGHT
         uint2 b0[4], b1[4];
 #pragma unroll
         for (int kb = 0; kb < 4; kb++) { b0[kb] = xb[kb * 8]; b1[kb] = xb[SR_WARPS * 32 + kb * 8]; } // lanes >= 8 feed D columns nobody reads
@@ -156,9 +177,32 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
         for (int kb = 0; kb < 4; kb++) { a0[kb] = ring[kb * 32]; a1[kb] = ring[128 + kb * 32]; }
         if (finer) mark();
 #pragma unroll
-        for (int kb = 0; kb < 4; kb++) sr_mma(c[kb], a0[kb], b0[kb]);
+        for (int kb = 0; kb < 4; kb++) sr_mma(c[kb & (SR_CHAINS - 1)], a0[kb], b0[kb]);
 #pragma unroll
-        for (int kb = 0; kb < 4; kb++) sr_mma(c[kb], a1[kb], b1[kb]);
+        for (int kb = 0; kb < 4; kb++) sr_mma(c[kb & (SR_CHAINS - 1)], a1[kb], b1[kb]);
+#else
+        uint2 b0[4];
+#pragma unroll
+        for (int kb = 0; kb < 4; kb++) b0[kb] = xb[kb * 8]; // lanes >= 8 feed D columns nobody reads
+        while (!sr_mbar_try(bar_full + 8 * cslot, cpar)) {}
+        const uint4 *ring = reinterpret_cast<const uint4 *>(sm_ring + (size_t)cslot * SR_ROUND + (size_t)warp * (2 * SK_UNIT)) + lane;
+        {
+            uint4 a0[4];
+#pragma unroll
+            for (int kb = 0; kb < 4; kb++) a0[kb] = ring[kb * 32];
+            if (finer) mark();
+#pragma unroll
+            for (int kb = 0; kb < 4; kb++) sr_mma(c[kb & (SR_CHAINS - 1)], a0[kb], b0[kb]);
+        }
+        { // second half (column slice warp + 8 + 16 j): the operand registers of the first half are free again
+            uint4 a1[4];
+            uint2 b1[4];
+#pragma unroll
+            for (int kb = 0; kb < 4; kb++) { b1[kb] = xb[SR_WARPS * 32 + kb * 8]; a1[kb] = ring[128 + kb * 32]; }
+#pragma unroll
+            for (int kb = 0; kb < 4; kb++) sr_mma(c[kb & (SR_CHAINS - 1)], a1[kb], b1[kb]);
+        }
+#endif
         __syncwarp();
         if (lane == 0) sr_mbar_arrive(bar_empty + 8 * cslot); // operands were read at issue: the slot may be refilled
         if (finer) mark();
@@ -183,15 +227,20 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
             const int cg1 = min(cg0 + SK_CHUNK_GROUPS, g1);
             float(*part)[SR_PSTRIDE] = sm_partial[pbuf];
             for (int grp = cg0; grp < cg1; grp++) {
-                float c[4][4];
+                float c[SR_CHAINS][4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.0f;
+                for (int i = 0; i < SR_CHAINS; i++) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0.0f;
                 for (int j = 0; j < nj; j++) do_round(j, c);
                 if (grp + 1 == cg1) flush_ss(); // shuffles overlap the latency of the last MMAs
                 if (tig == 0) { // D columns 0 / 1 = x_hi / x_lo sums; rows gid and gid + 8
                     const int r = (grp - cg0) * 16 + gid;
+#if SR_CHAINS == 4
                     part[r][warp] = ((c[0][0] + c[1][0]) + (c[2][0] + c[3][0])) + ((c[0][1] + c[1][1]) + (c[2][1] + c[3][1]));
                     part[r + 8][warp] = ((c[0][2] + c[1][2]) + (c[2][2] + c[3][2])) + ((c[0][3] + c[1][3]) + (c[2][3] + c[3][3]));
+#else
+                    part[r][warp] = (c[0][0] + c[1][0]) + (c[0][1] + c[1][1]);
+                    part[r + 8][warp] = (c[0][2] + c[1][2]) + (c[0][3] + c[1][3]);
+#endif
                 }
             }
             if (fine && layer_phase) mark();
@@ -211,7 +260,6 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
 
     // x (shared, or gathered from an exchange buffer first) -> x * gamma -> B-fragment image; the RMSNorm scalar is
     // applied to the phase output (norm_scale()), so the reduction of squares leaves the critical path
-    constexpr int NPX = 4; // 256 threads x 4 pairs cover H / 2 <= 1024
     auto stage_norm = [&](const u64 *src, unsigned tag, const float2(&gm2)[NPX]) {
         float v[NPX][2];
         const int hp = H >> 1;
@@ -393,12 +441,12 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
                         if (j < k1) {
                             const float s = sc8[i];
                             if (s > m) {
-                                const float cc = expf(m - s);
+                                const float cc = sr_exp(m - s);
                                 lsum = lsum * cc + 1.0f;
                                 acc.x = acc.x * cc + vr[i].x; acc.y = acc.y * cc + vr[i].y; acc.z = acc.z * cc + vr[i].z; acc.w = acc.w * cc + vr[i].w;
                                 m = s;
                             } else {
-                                const float w = expf(s - m);
+                                const float w = sr_exp(s - m);
                                 lsum += w;
                                 acc.x += w * vr[i].x; acc.y += w * vr[i].y; acc.z += w * vr[i].z; acc.w += w * vr[i].w;
                             }
@@ -416,7 +464,7 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
                     float Ls = 0.0f, Aa = 0.0f;
 #pragma unroll
                     for (int w = 0; w < SR_WARPS; w++) {
-                        const float e = expf(wml[w * 2] - M);
+                        const float e = sr_exp(wml[w * 2] - M);
                         Ls += wml[w * 2 + 1] * e;
                         Aa += wacc[w * 128 + tid] * e;
                     }
@@ -629,8 +677,9 @@ int launch_decode_rounds(cudaStream_t s, const StreamParams &p, int grid, char *
     if (!g_sr_slots_dev[dev & 31]) {
         int optin = 0, per_sm = 0;
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        cudaError_t e = cudaFuncSetAttribute(decode_rounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_rounds_kernel, SR_ALL_THREADS, (size_t)optin);
+        cudaError_t e = cudaFuncSetAttribute(decode_rounds_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_rounds_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_rounds_kernel<4>, SR_ALL_THREADS, (size_t)optin);
         if (e != cudaSuccess || per_sm < 1 || optin < (int)SrLayout::total(3, SK_MAX_K, SK_MAX_H)) {
             snprintf(err, errlen, "decode rounds kernel unavailable: %s (blocks/SM=%d, shared memory opt-in %d)", cudaGetErrorString(e), per_sm, optin);
             cudaGetLastError();
@@ -644,13 +693,16 @@ int launch_decode_rounds(cudaStream_t s, const StreamParams &p, int grid, char *
     // measured (profiles/r02_decode_latency.txt): a SHORT ring wins - 3 rounds in flight and 3 more prefetched into L2; deeper rings and
     // longer prefetch distances make the exchanges slower than the earlier weights are worth
     { static int cap = -1; if (cap < 0) { const char *e = getenv("QASR_SR_SLOTS"); cap = e ? atoi(e) : 3; } if (cap >= 2 && cap < nslot) nslot = cap; }
-    const size_t smem = SrLayout::total(nslot, kmax, p.H);
+    size_t smem = SrLayout::total(nslot, kmax, p.H);
+    { static int pad = -1; if (pad < 0) { const char *e = getenv("QASR_SR_PAD_KB"); pad = e ? atoi(e) : 0; } // experiment: unused shared memory (shrinks L1)
+      if (pad > 0 && smem + (size_t)pad * 1024 <= (size_t)g_sr_slots_dev[dev & 31]) smem += (size_t)pad * 1024; }
     StreamParams q = p;
     { static int v = -1; if (v < 0) { const char *e = getenv("QASR_SR_CHUNK"); v = e ? atoi(e) : SR_ROUND; if (v < 512 || SR_ROUND % v) v = SR_ROUND; } q.sr_chunk = v; }
     { static int v = -1; if (v < 0) { const char *e = getenv("QASR_SR_L2AHEAD"); v = e ? atoi(e) : 3; } q.l2_ahead_units = v; }
     { static int v = -1; if (v < 0) { const char *e = getenv("QASR_SR_PACE"); v = e ? atoi(e) : 0; } q.sr_pace_pct = v; }
     void *args[] = {(void *)&q, (void *)&nslot};
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)decode_rounds_kernel, dim3(grid), dim3(SR_ALL_THREADS), args, smem, s);
+    const void *kern = p.H <= 1024 ? (const void *)decode_rounds_kernel<2> : (const void *)decode_rounds_kernel<4>;
+    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(SR_ALL_THREADS), args, smem, s);
     if (e != cudaSuccess) {
         snprintf(err, errlen, "decode rounds kernel launch: %s", cudaGetErrorString(e));
         return -1;

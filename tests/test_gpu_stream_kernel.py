@@ -190,3 +190,59 @@ def test_config4_stream_real_parameters_vs_reference(pkg, model06, gpu06, ref_li
     assert max(w["rows"] for w in want) <= 9 + 4 * 104 + 78 + 6          # never more than 4 cached windows + a partial one
     n_pre = len(pkg.streaming.PROMPT_PRE)
     assert any(want[i]["reused"] == n_pre and want[i - 1]["reused"] > n_pre for i in range(1, 22))   # the eviction chunk reuses the prompt prefix only
+
+
+def test_single_sequence_eos_stop_matches_reference(pkg, model06, ref_lib, oracle_lib):
+    """Early stop of the persistent single-sequence kernel (reference qwen_asr.c:788-793): on the EOS-capable checkpoint the launch
+    ends before its step budget, the producer warp of decode_rounds_kernel drains what it has in flight, and the next
+    utterances on the same context decode normally.  ids equal the reference's, terminating EOS included."""
+    vdir = variants.eos_model_dir(model06, 2.5)
+    units = [pkg.synth_audio(1.0 + 0.37 * i, seed=500 + i) for i in range(4)]
+    cpu = checker(ref_lib, oracle_lib, vdir)
+    try:
+        want = [cpu.transcribe_ids(u, 40)[0].tolist() for u in units]
+    finally:
+        cpu.close()
+    assert min(len(w) for w in want) < 40
+    eng = pkg.QasrCuda(0).load(vdir)
+    try:
+        for rep in range(2):
+            for u, w in zip(units, want):
+                assert eng.transcribe_ids(u, 40)[0].tolist() == w
+    finally:
+        eng.close()
+
+
+_OTHER_KERNEL = r"""
+import sys, json
+sys.path.insert(0, {root!r})
+import __graft_entry__ as ge
+pkg = ge.load_package()
+out = {{}}
+for variant in ("0.6b", "1.7b"):
+    eng = pkg.QasrCuda(0).load(pkg.ensure_model_dir(variant))
+    out[variant] = [eng.transcribe_ids(pkg.synth_audio(s, seed=900 + i), 10)[0].tolist() for i, s in enumerate((1.3, 3.64, 7.0))]
+    eng.close()
+print("IDS " + json.dumps(out))
+"""
+
+
+def test_ring_and_rounds_kernels_decode_the_same_ids(pkg, ref_lib, oracle_lib):
+    """Both single-sequence decode kernels are kept (qasr_stream.cu: per-lane cp.async ring, default for the 1.7B dims;
+    qasr_stream_r.cu: TMA producer warp + round-major image, default for the 0.6B dims).  Each is forced for BOTH models in
+    a child process (the choice is read once per process) and must reproduce the reference's greedy ids."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    want = {}
+    for variant in ("0.6b", "1.7b"):
+        cpu = checker(ref_lib, oracle_lib, pkg.ensure_model_dir(variant))
+        try:
+            want[variant] = [cpu.transcribe_ids(pkg.synth_audio(s, seed=900 + i), 10)[0].tolist() for i, s in enumerate((1.3, 3.64, 7.0))]
+        finally:
+            cpu.close()
+    for kernel in ("ring", "rounds"):
+        env = dict(os.environ, QASR_DECODE_KERNEL=kernel)
+        r = subprocess.run([sys.executable, "-c", _OTHER_KERNEL.format(root=root)], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        got = json.loads([l for l in r.stdout.splitlines() if l.startswith("IDS ")][-1][4:])
+        assert got == want, kernel

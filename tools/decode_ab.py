@@ -5,6 +5,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as ge
 pkg = ge.load_package()
+if os.environ.get("QASR_LIB"):  # A/B of library variants built next to the default one
+    sys.modules[pkg.__name__ + ".binding"].LIB_PATH = os.path.abspath(os.environ["QASR_LIB"])
 variant = sys.argv[1] if len(sys.argv) > 1 else "1.7b"
 variants = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 2, 4, 6, 16, 1]
 eng = pkg.QasrCuda(0).load(pkg.ensure_model_dir(variant))
