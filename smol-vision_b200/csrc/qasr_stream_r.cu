@@ -59,8 +59,8 @@ __device__ __forceinline__ bool sr_mbar_try(uint32_t bar, uint32_t parity) {
     asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0;
 }
-__device__ __forceinline__ void sr_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+__device__ __forceinline__ void sr_bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar, u64 pol) { // weights are read once per token: L2 evict-first
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void sr_bulk_prefetch_l2(const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
         if (lane == 0) {
             const uint8_t *src = p.image_r + coff;
             const uint32_t total = rounds_per_step * (uint32_t)p.n_steps;
+            u64 pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
             const uint32_t ahead = (uint32_t)min(p.l2_ahead_units, 64);
             for (uint32_t r = 0; r < ahead && r < rounds_per_step; r++) sr_bulk_prefetch_l2(src + (size_t)r * SR_ROUND, SR_ROUND);
             uint32_t slot = 0, pass = 0, rr = 0, pr = ahead % rounds_per_step; // ring slot, ring pass, round within the step, prefetch cursor
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
                 const bool paced = pace != 0 && rr < layer_rounds;
                 for (uint32_t c = 0; c < chunks_per_round; c++) {
                     if (paced) { while ((uint32_t)(clock64() - t_last) < pace) {} t_last = clock64(); }
-                    sr_bulk_load(dst + c * chunk, g + (size_t)c * chunk, chunk, bar_full + 8 * slot);
+                    sr_bulk_load(dst + c * chunk, g + (size_t)c * chunk, chunk, bar_full + 8 * slot, pol);
                 }
                 if (ahead) { sr_bulk_prefetch_l2(src + (size_t)pr * SR_ROUND, SR_ROUND); if (++pr == rounds_per_step) pr = 0; }
                 if (++rr == rounds_per_step) rr = 0;

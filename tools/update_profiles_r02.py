@@ -40,6 +40,8 @@ s = f"""
 | `r02_bench_reference_arm.json` | reference arm: the reference's own CPU path (`oracle/_ref`, 16 host cores) | `python bench.py --impl reference --steps 3 --warmup 1` |
 | `r02_ncu_summary.json` | `ncu --set full` captures of the kernels VERDICT r1 asked evidence for: skinny GEMMs of the prefill chain at M = 61, `attn_prefill_kernel`, `attn_windowed_kernel`, the persistent large-tile GEMM in the batched prefill / encoder, conv stem kernels, `attn_decode_batch_kernel` | `bash tools/ncu_round2.sh` (each profiled command first exited 0 without ncu), summarised by `tools/ncu_summary.py` |
 | `r02_launches_batched_64x30s.csv.gz` | ncu launch list of the first version of the batched path: 64 x 30 s utterances, 1.7B, 3 decode steps | `ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/batch_profile.py 1.7b 64 30 3 1` |
+| `r02_decode_latency.txt` | the 0.6B decode latency study: exchange microbenchmarks (aligned vs shared sectors, strides, 4-byte phase words, clusters / DSMEM, L2-atomic all-reduce), phase stamps of the ring kernel, the register-window experiment, the TMA producer / consumer kernel and its sweeps (ring depth, L2 prefetch distance, pacing, padding) | `tools/microbench/ll_exchange2.cu`, `cluster_exchange.cu`, `tools/decode_ab.py`, `tools/mega_prof_fine.py` |
+| `r02_ncu_rounds_0p6b.json` | `ncu --set full` of `decode_rounds_kernel<2>` (0.6B, 11 s, one launch = 16 greedy steps): 1234.2 MB of DRAM traffic per step = 1.0004 x algorithmic | `ncu --set full --clock-control none -k regex:decode_rounds_kernel -s 1 -c 2 python tools/profile_utt.py 0.6b 3 11.0 48`, `tools/ncu_summary.py` |
 | `r02_batched_path.txt` | stage timings of the batched path vs group size, GEMM microbenchmark at the batched shapes (zero vs hashed operands, f32-store vs pipeline epilogues, one-CTA-per-tile vs persistent vs 2-CTA kernel), dropped variants | `tools/batch_profile.py`, `tools/gemm_bench.py batch|decode` |
 
 Regenerate this section: `python tools/update_profiles_r02.py`.
@@ -50,7 +52,8 @@ configs[1] (1.7B, 3.64 s, 32 tokens): {d['value']:.1f} x realtime device-timed, 
 {d['stage_ms']['mel_ms']:.2f} + encoder {d['stage_ms']['enc_ms']:.2f} + prefill {d['stage_ms']['prefill_ms']:.2f} + decode {d['stage_ms']['decode_ms']:.2f} ms), decode step {d['roofline']['ms_per_launch']:.3f} ms = {d['roofline']['achieved']:.0f} GB/s =
 **{d['roofline']['frac']:.3f}** of the measured HBM peak; ids identical to the compiled reference (`cpu_baseline.ids_match_gpu` = {d['cpu_baseline']['ids_match_gpu']}); the reference's CPU path on the
 box's 16 host cores: {ref['value']:.2f} x realtime ({ref['ms_per_step']:.0f} ms). `roofline_0p6b` (0.6B, 11 s, 48 tokens): {d['roofline_0p6b']['ms_per_launch']:.3f} ms per step = {d['roofline_0p6b']['achieved']:.0f} GB/s =
-**{d['roofline_0p6b']['frac']:.3f}** - exchange-latency bound (DESIGN 8.1). `qasr_cuda_step_logits` runs the same kernel, so the logits-level parity
+**{d['roofline_0p6b']['frac']:.3f}** on `decode_rounds_kernel` (TMA producer warp + 8 consumer warps; 0.390 / 0.483 ms on the ring kernel; `r02_decode_latency.txt`) - bound by the five dependent
+exchanges per layer (DESIGN 8.1). `qasr_cuda_step_logits` runs the same kernels, so the logits-level parity
 tests pin what the bench times. 8 GPUs: {d8['value']:.0f} x (one replica per GPU, weak scaling).
 
 ## The splits BASELINE.json names (`extra.strong`)
