@@ -107,7 +107,7 @@ def gemm_rooflines(eng):
 def decode_kernel_name(cfg):
     """The single-sequence decode kernel the library picks for these dims (qasr_stream.cu: stream_use_rounds)."""
     mode = os.environ.get("QASR_DECODE_KERNEL", "")
-    rounds = mode == "rounds" or (mode != "ring" and cfg["dec_hidden"] <= 1024)
+    rounds = mode != "ring"
     return ("decode_rounds_kernel (persistent cooperative kernel, qasr_stream_r.cu: TMA producer warp + 8 consumer warps over a round-major weight image; a launch runs up to 16 steps)"
             if rounds else
             "decode_stream_kernel (persistent cooperative kernel, qasr_stream.cu: per-lane cp.async weight ring; a launch runs up to 16 steps)")

@@ -116,7 +116,7 @@ struct StreamParams {
     int trace_cta;                         // CTA whose warp 0 writes the per-unit trace (debug bit 6)
     int l2_issue;                          // units prefetched per poll iteration
     int l2_ahead_units;                    // second-level prefetch distance into L2, in 2 KB units per warp (0 = off)
-    int sr_chunk, sr_pace_pct;             // producer of qasr_stream_r.cu: bytes per bulk copy, pacing (percent of the previous step's layer time; 0 = unpaced)
+    int sr_chunk;                          // producer of qasr_stream_r.cu: bytes per bulk copy
     float *dbg_logits;                     // test hook (NULL in production): [nseq][V] logits of the LAST step of the launch
     float *dbg_hidden;                     // test hook (NULL in production): [nseq][H] post-final-norm hidden state
 };

@@ -864,11 +864,12 @@ int stream_build_image(cudaStream_t s, int L, int H, int I, int V, const bf16_t 
 }
 
 // Which single-sequence kernel: the producer / consumer kernel over round-major weights (qasr_stream_r.cu) or the per-lane
-// cp.async ring kernel.  QASR_DECODE_KERNEL=ring | rounds overrides the default.
+// cp.async ring kernel (which still serves 2 and 4 sequences per launch).  QASR_DECODE_KERNEL=ring | rounds; default rounds.
 bool stream_use_rounds(int H) {
     static int mode = -1; // 0 = default, 1 = ring, 2 = rounds
     if (mode < 0) { const char *e = getenv("QASR_DECODE_KERNEL"); mode = e && !strcmp(e, "ring") ? 1 : (e && !strcmp(e, "rounds") ? 2 : 0); }
-    return mode == 2 || (mode == 0 && H <= 1024); // measured: 0.6B 455 -> 400 us/token, 1.7B 709 -> 757 (HBM-bound phases want the deeper ring)
+    (void)H;
+    return mode != 1; // measured: 0.6B 455 -> 387 us per token, 1.7B 709 -> 641 (profiles/r02_decode_latency.txt)
 }
 
 // Largest number of sequences one launch can carry for these dims (shared memory: the DOWN input image is K x 4 B per sequence)

@@ -21,7 +21,11 @@
 
 #define SR_WARPS 8            /* consumer warps */
 #define SR_THREADS (SR_WARPS * 32)
-#define SR_ALL_THREADS (SR_THREADS + 32) /* + the producer warp */
+#define SR_MAX_PRODUCERS 4
+#ifndef SR_DEFAULT_PRODUCERS
+#define SR_DEFAULT_PRODUCERS 1
+#endif
+#define SR_ALL_THREADS (SR_THREADS + 32 * SR_MAX_PRODUCERS) /* launch bound: consumers + up to 4 producer warps (12 warps = 3 per scheduler => 168 registers) */
 #define SR_ROUND (16 * SK_UNIT) /* 32 KB: 16 rows x 1024 columns */
 #define SR_MAX_SLOTS 6
 #define SR_PSTRIDE 9
@@ -100,55 +104,55 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
         sm_ctl[0] = 0; sm_ctl[1] = 0; sm_ctl[2] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int e = tid; e < H; e += SR_ALL_THREADS) sm_x[e] = p.x_io[e];
+    for (int e = tid; e < H; e += blockDim.x) sm_x[e] = p.x_io[e];
     __syncthreads();
 
-    // ---- producer warp: rounds of this CTA in consumption order, cyclic over the steps of the launch
+    // ---- producer warps: rounds of this CTA in consumption order, cyclic over the steps of the launch.  A round is issued as
+    // SR_ROUND / chunk bulk copies (measured: 8 KB chunks for the 1.7B dims, 4 KB for 0.6B - one 32 KB copy per round is slower,
+    // 2 KB copies are issue-bound); with n_prod producer warps, producer q issues chunks q, q + n_prod, ... of every round, so the
+    // ~0.1 us of issue time per copy is shared.  Producer 0 arms the round's `full` barrier (expect_tx of the whole round; the
+    // transaction count may go negative until it does) and runs the L2 prefetch cursor.
     const u64 coff = p.cta_off[b];
     const uint32_t rounds_per_step = (uint32_t)((p.cta_off[b + 1] - coff) / SR_ROUND);
-    if (warp == SR_WARPS) {
+    if (warp >= SR_WARPS) {
         if (lane == 0) {
+            const uint32_t q = (uint32_t)(warp - SR_WARPS), n_prod = (uint32_t)(blockDim.x >> 5) - SR_WARPS;
             const uint8_t *src = p.image_r + coff;
-            const uint32_t total = rounds_per_step * (uint32_t)p.n_steps;
+            uint32_t total = rounds_per_step * (uint32_t)p.n_steps;
             u64 pol;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-            const uint32_t ahead = (uint32_t)min(p.l2_ahead_units, 64);
+            const uint32_t ahead = q == 0 ? (uint32_t)min(p.l2_ahead_units, 64) : 0u;
             for (uint32_t r = 0; r < ahead && r < rounds_per_step; r++) sr_bulk_prefetch_l2(src + (size_t)r * SR_ROUND, SR_ROUND);
             uint32_t slot = 0, pass = 0, rr = 0, pr = ahead % rounds_per_step; // ring slot, ring pass, round within the step, prefetch cursor
-            uint32_t issued = 0;
-            bool stopped = false;
-            // Pacing: a burst of bulk data shares the SM's return path with the exchange polls (a poll response queues behind
-            // whatever was requested before it), and 148 CTAs refilling at the same instant make an HBM burst.  The layer rounds
-            // are therefore issued in chunks, no faster than `pace` cycles apart = a fraction of the time the layers of the
-            // previous step took, divided by this CTA's chunk count; the lm_head rounds (bandwidth-bound) are never paced.
             const uint32_t chunk = (uint32_t)p.sr_chunk, chunks_per_round = SR_ROUND / chunk;
-            const uint32_t layer_rounds = rounds_per_step - (uint32_t)(sk_g0(p.V >> 4, b + 1, G) - sk_g0(p.V >> 4, b, G)) * (uint32_t)(H >> 10);
-            long long t_last = clock64();
-            uint32_t pace = 0;
-            for (; issued < total; issued++) {
-                if (rr == 0) pace = (uint32_t)((unsigned long long)sm_ctl[2] * (unsigned)p.sr_pace_pct / 100u / (layer_rounds * chunks_per_round + 1));
-                if (pass > 0) { // the slot must have been drained by all consumer warps
-                    while (!sr_mbar_try(bar_empty + 8 * slot, (pass - 1) & 1))
-                        if (sm_ctl[0]) { stopped = true; break; }
-                    if (stopped) break;
-                }
-                sr_mbar_expect_tx(bar_full + 8 * slot, SR_ROUND);
+            bool stopping = false;
+            uint32_t drain_from = 0;
+            for (uint32_t issued = 0; issued < total; issued++) {
+                if (pass > 0) // the slot must have been drained by all consumer warps
+                    while (!sr_mbar_try(bar_empty + 8 * slot, (pass - 1) & 1)) {
+                        if (!stopping && sm_ctl[0]) {
+                            // Early stop (EOS): the consumers drained `sm_ctl[1]` rounds and take no more.  EVERY producer still issues
+                            // its share of the rounds whose slots are free (< drained + nslot: their `empty` phases are complete, so
+                            // nobody blocks), which keeps the barriers of those rounds consistent among the producers; then it waits
+                            // for them to land - no bulk copy may be in flight when the CTA's shared memory goes away.
+                            stopping = true;
+                            drain_from = sm_ctl[1];
+                            total = min(total, drain_from + (uint32_t)nslot);
+                        }
+                        if (issued >= total) break;
+                    }
+                if (issued >= total) break;
+                if (q == 0) sr_mbar_expect_tx(bar_full + 8 * slot, SR_ROUND);
                 const uint32_t dst = sk_smem_u32(sm_ring + (size_t)slot * SR_ROUND);
                 const uint8_t *g = src + (size_t)rr * SR_ROUND;
-                const bool paced = pace != 0 && rr < layer_rounds;
-                for (uint32_t c = 0; c < chunks_per_round; c++) {
-                    if (paced) { while ((uint32_t)(clock64() - t_last) < pace) {} t_last = clock64(); }
-                    sr_bulk_load(dst + c * chunk, g + (size_t)c * chunk, chunk, bar_full + 8 * slot, pol);
-                }
+                for (uint32_t c = q; c < chunks_per_round; c += n_prod) sr_bulk_load(dst + c * chunk, g + (size_t)c * chunk, chunk, bar_full + 8 * slot, pol);
                 if (ahead) { sr_bulk_prefetch_l2(src + (size_t)pr * SR_ROUND, SR_ROUND); if (++pr == rounds_per_step) pr = 0; }
                 if (++rr == rounds_per_step) rr = 0;
                 if (++slot == (uint32_t)nslot) { slot = 0; pass++; }
             }
-            if (stopped) { // early stop (EOS): copies already issued must land before the CTA's shared memory goes away
-                const uint32_t consumed = sm_ctl[1];
-                for (uint32_t k = consumed; k < issued; k++)
+            if (stopping)
+                for (uint32_t k = drain_from; k < total; k++)
                     while (!sr_mbar_try(bar_full + 8 * (k % (uint32_t)nslot), (k / (uint32_t)nslot) & 1)) {}
-            }
         }
         return;
     }
@@ -317,7 +321,6 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
     bool stop = false;
 
     for (; step < p.n_steps && !stop; step++) {
-        const long long t_step = clock64();
         // attention role of this CTA for the whole step: (q head hq, key split sp of S)
         int S = (pos + 1 + SR_ATT_BATCH * SR_WARPS - 1) / (SR_ATT_BATCH * SR_WARPS);
         S = min(S, min(SK_ATT_MAXS, G / 16));
@@ -577,7 +580,6 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
             }
             mark();
         }
-        if (tid == 0) sm_ctl[2] = (unsigned)(clock64() - t_step); // duration of the layer section: paces the producer in the next step
         // ---------------- HEAD: greedy argmax over this CTA's vocab rows of the tied embedding
         const unsigned htag = p.tag_base + (unsigned)(step * (L + 1) + L + 1);
         float2 g_fin[NPX];
@@ -689,22 +691,32 @@ int launch_decode_rounds(cudaStream_t s, const StreamParams &p, int grid, char *
         }
         g_sr_slots_dev[dev & 31] = optin;
     }
+    // Measured defaults (profiles/r02_decode_latency.txt): 0.6B dims - 3 slots, 3 rounds of L2 prefetch, 4 KB copies; 1.7B dims - all the
+    // slots that fit (5), 6 rounds, 8 KB copies.
+    const bool small = p.H <= 1024;
     const int kmax = p.I > 2048 ? p.I : 2048;
     int nslot = (int)((g_sr_slots_dev[dev & 31] - SrLayout::rest(kmax, p.H)) / SR_ROUND);
     if (nslot > SR_MAX_SLOTS) nslot = SR_MAX_SLOTS;
-    // measured (profiles/r02_decode_latency.txt): a SHORT ring wins - 3 rounds in flight and 3 more prefetched into L2; deeper rings and
-    // longer prefetch distances make the exchanges slower than the earlier weights are worth
-    { static int cap = -1; if (cap < 0) { const char *e = getenv("QASR_SR_SLOTS"); cap = e ? atoi(e) : 3; } if (cap >= 2 && cap < nslot) nslot = cap; }
+    static int e_slots = -2, e_chunk = -2, e_ahead = -2, e_prod = -2, e_pad = -2;
+    if (e_slots == -2) {
+        const char *e;
+        e = getenv("QASR_SR_SLOTS"); e_slots = e ? atoi(e) : -1;
+        e = getenv("QASR_SR_CHUNK"); e_chunk = e ? atoi(e) : -1;
+        e = getenv("QASR_SR_L2AHEAD"); e_ahead = e ? atoi(e) : -1;
+        e = getenv("QASR_SR_PRODUCERS"); e_prod = e ? atoi(e) : -1;
+        e = getenv("QASR_SR_PAD_KB"); e_pad = e ? atoi(e) : 0;
+    }
+    const int want_slots = e_slots >= 2 ? e_slots : (small ? 3 : SR_MAX_SLOTS);
+    if (want_slots < nslot) nslot = want_slots;
     size_t smem = SrLayout::total(nslot, kmax, p.H);
-    { static int pad = -1; if (pad < 0) { const char *e = getenv("QASR_SR_PAD_KB"); pad = e ? atoi(e) : 0; } // experiment: unused shared memory (shrinks L1)
-      if (pad > 0 && smem + (size_t)pad * 1024 <= (size_t)g_sr_slots_dev[dev & 31]) smem += (size_t)pad * 1024; }
+    if (e_pad > 0 && smem + (size_t)e_pad * 1024 <= (size_t)g_sr_slots_dev[dev & 31]) smem += (size_t)e_pad * 1024; // experiment: unused shared memory (shrinks L1)
     StreamParams q = p;
-    { static int v = -1; if (v < 0) { const char *e = getenv("QASR_SR_CHUNK"); v = e ? atoi(e) : SR_ROUND; if (v < 512 || SR_ROUND % v) v = SR_ROUND; } q.sr_chunk = v; }
-    { static int v = -1; if (v < 0) { const char *e = getenv("QASR_SR_L2AHEAD"); v = e ? atoi(e) : 3; } q.l2_ahead_units = v; }
-    { static int v = -1; if (v < 0) { const char *e = getenv("QASR_SR_PACE"); v = e ? atoi(e) : 0; } q.sr_pace_pct = v; }
+    q.sr_chunk = (e_chunk >= 1024 && SR_ROUND % e_chunk == 0) ? e_chunk : (small ? 4096 : 8192);
+    q.l2_ahead_units = e_ahead >= 0 ? e_ahead : (small ? 3 : 6);
+    const int n_prod = (e_prod >= 1 && e_prod <= SR_MAX_PRODUCERS) ? e_prod : SR_DEFAULT_PRODUCERS;
     void *args[] = {(void *)&q, (void *)&nslot};
     const void *kern = p.H <= 1024 ? (const void *)decode_rounds_kernel<2> : (const void *)decode_rounds_kernel<4>;
-    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(SR_ALL_THREADS), args, smem, s);
+    cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(SR_THREADS + 32 * n_prod), args, smem, s);
     if (e != cudaSuccess) {
         snprintf(err, errlen, "decode rounds kernel launch: %s", cudaGetErrorString(e));
         return -1;

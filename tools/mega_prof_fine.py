@@ -8,6 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as ge
 pkg = ge.load_package()
+if os.environ.get("QASR_LIB"):  # a -DSR_FINE_PROF build next to the default library
+    sys.modules[pkg.__name__ + ".binding"].LIB_PATH = os.path.abspath(os.environ["QASR_LIB"])
 variant = sys.argv[1] if len(sys.argv) > 1 else "0.6b"
 eng = pkg.QasrCuda(0).load(pkg.ensure_model_dir(variant))
 audio = pkg.synth_audio(3.64, 100)
