@@ -64,12 +64,21 @@ def peaks():
 
 def ncu_traffic_per_step(variant):
     """(dram__bytes_read.sum + dram__bytes_write.sum of the decode kernel per greedy step, where that number comes from).
-    It is NOT measured in this run: it is read from the committed `ncu --set full` capture of the same kernel on the 1.7B
-    workload (profiles/r01_stream_ncu_summary.json); None for other models."""
+    It is NOT measured in this run: it is read from the committed `ncu --set full` capture of the same kernel on the same
+    model (profiles/r02_rounds_ncu_summary.json for decode_rounds_kernel, profiles/r01_stream_ncu_summary.json for the ring
+    kernel on 1.7B); None when no capture of that kernel / model is committed."""
+    note = " (committed ncu --set full capture, not re-measured in this run)"
+    if os.environ.get("QASR_DECODE_KERNEL", "") != "ring":
+        p = os.path.join(ROOT, "profiles", "r02_rounds_ncu_summary.json")
+        if os.path.exists(p):
+            e = json.load(open(p))["models"].get(variant)
+            if e:
+                return float(e["dram_bytes_per_step"]), "profiles/r02_rounds_ncu_summary.json" + note
+        return None, None
     p = os.path.join(ROOT, "profiles", "r01_stream_ncu_summary.json")
     if variant != "1.7b" or not os.path.exists(p):
         return None, None
-    return float(json.load(open(p))["dram_bytes_per_step"]), "profiles/r01_stream_ncu_summary.json (committed ncu --set full capture, not re-measured in this run)"
+    return float(json.load(open(p))["dram_bytes_per_step"]), "profiles/r01_stream_ncu_summary.json" + note
 
 
 def gemm_rooflines(eng):
@@ -433,7 +442,7 @@ def single_decode_roofline(pkg, eng, workload, steps=8):
     ach = step_bytes / (ms * 1e-3) / 1e9
     return {"workload": desc, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "frac_of_8000_nominal": ach / 8000.0,
             "peak_source": peak_src, "kernel": "one greedy step of " + decode_kernel_name(eng.cfg), "bytes_per_launch": step_bytes, "ms_per_launch": ms,
-            "decoder_tok_s": 1000.0 / ms, "traffic": None, "traffic_source": None}
+            "decoder_tok_s": 1000.0 / ms, "traffic": ncu_traffic_per_step(variant)[0], "traffic_source": ncu_traffic_per_step(variant)[1]}
 
 
 def main():

@@ -50,10 +50,11 @@ def test_sass_is_blackwell_native(pkg):
         assert mnemonic in r.stdout, f"{mnemonic} missing from SASS"
     # the single-sequence decode kernel streams its weights with 1-D bulk copies (TMA) signalled through mbarriers
     rounds = [f for f in re.split(r"\n\s*Function : ", r.stdout) if f.startswith("_Z20decode_rounds_kernel")]
-    assert len(rounds) == 1
-    for mnemonic in ("UBLKCP", "UBLKPF", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK", "HMMA.16816.F32.BF16"):
-        assert mnemonic in rounds[0], f"{mnemonic} missing from decode_rounds_kernel"
-    assert "LDGSTS" not in rounds[0]                     # no consumer-issued weight loads
+    assert len(rounds) == 2                              # H = 1024 and H = 2048 instantiations
+    for f in rounds:
+        for mnemonic in ("UBLKCP", "UBLKPF", "SYNCS.ARRIVE.TRANS64", "SYNCS.PHASECHK", "HMMA.16816.F32.BF16"):
+            assert mnemonic in f, f"{mnemonic} missing from decode_rounds_kernel"
+        assert "LDGSTS" not in f                         # no consumer-issued weight loads
     assert "HGMMA" not in r.stdout
 
 
@@ -123,11 +124,11 @@ def test_hot_kernel_resource_budget(pkg):
     assert len(decode) == 3 and len(gemm) == 8, sorted(usage)   # 3 + 2 (implicit-GEMM conv) large-tile, 3 skinny
     for k, (reg, stack) in decode.items():
         assert reg <= 128 and stack <= 16, (k, reg, stack)
-    # producer / consumer decode kernel: 9 warps per CTA, i.e. three warps on one scheduler => at most 168 registers
+    # producer / consumer decode kernel: 9-12 warps per CTA, i.e. three warps on one scheduler => at most 168 registers
     rounds = {k: v for k, v in usage.items() if "decode_rounds_kernel" in k}
-    assert len(rounds) == 1
+    assert len(rounds) == 2
     for k, (reg, stack) in rounds.items():
-        assert reg <= 168 and stack <= 64, (k, reg, stack)
+        assert reg <= 168 and stack == 0, (k, reg, stack)
     for k, (reg, stack) in gemm.items():
         assert reg <= 128 and stack == 0, (k, reg, stack)
 
