@@ -59,3 +59,5 @@ __device__ __forceinline__ float gelu_tanh(float v) {
 }
 // SiLU, reference qwen_asr_kernels.c:930-935
 __device__ __forceinline__ float silu(float g) { return g / (1.0f + expf(-g)); }
+// MUFU-based form for epilogues that sit on a latency path (a few ulp from silu(); the consumers round the result to bf16 hi / lo planes or add it into f32 sums)
+__device__ __forceinline__ float silu_fast(float g) { return __fdividef(g, 1.0f + __expf(-g)); }

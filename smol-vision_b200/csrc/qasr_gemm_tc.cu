@@ -613,6 +613,10 @@ struct SkParams {
     unsigned *tickets;              // [n_tiles], zero between launches
     int fuse_planes;                // 1 (MP <= 128, nsplit == 2): ONE N = 2*MP MMA per k-step over the [hi | lo] planes, two accumulators
     int cluster;                    // 1: the S splits of a tile form one thread-block cluster (1, S, 1) and reduce through DSMEM
+    const uint8_t *w_tiled;         // tile-major copy of W ([n tile][k block][16 KB in the swizzled operand layout]) or NULL: the weight producer
+                                    // then issues ONE contiguous bulk copy per k-block instead of a 2-D box of 128 rows x 128 bytes
+    int total_kb;
+    int rotate_k;                   // 1: CTA `tile` walks its k-blocks starting at tile % num_kb (spreads the activation reads over the L2 slices)
     GemmEpilogue epi;
 };
 
@@ -622,7 +626,7 @@ __device__ __forceinline__ void sk_epilogue_store(const SkParams &p, int n, int 
     if (e.mode == QASR_GEMM_SWIGLU_SPLIT) { // rows (2j, 2j+1) of W = (gate_j, up_j): neighbouring lanes
         const float up = __shfl_down_sync(0xffffffffu, v, 1);
         if (!(lane & 1) && n + 1 < p.N && m < p.M) {
-            const float r = silu(v) * up;
+            const float r = silu_fast(v) * up;
             __nv_bfloat16 hi, lo;
             split_bf16(r, hi, lo);
             e.out_hi[(size_t)m * e.ldo + (n >> 1)] = __bfloat16_as_ushort(hi);
@@ -650,7 +654,7 @@ template <int MP>
 __device__ __forceinline__ void sk_reduced_store(const SkParams &p, int nb, int m, const float4 v) {
     if (p.epi.mode == QASR_GEMM_SWIGLU_SPLIT) { // (gate, up) pairs sit inside the float4
         const GemmEpilogue &e = p.epi;
-        const float r[2] = {silu(v.x) * v.y, silu(v.z) * v.w};
+        const float r[2] = {silu_fast(v.x) * v.y, silu_fast(v.z) * v.w};
 #pragma unroll
         for (int j = 0; j < 2; j++)
             if (nb + 2 * j + 1 < p.N) {
@@ -666,7 +670,11 @@ __device__ __forceinline__ void sk_reduced_store(const SkParams &p, int nb, int 
     }
 }
 
-#define SK_THREADS 224 /* warps: 0 W producer, 1 MMA, 2-5 epilogue, 6 activation producer */
+// warps: 0 W producer, 1 MMA, 2 .. 2 + EPW - 1 epilogue, 2 + EPW activation producer.  One epilogue warp per TMEM lane quarter (4 warps,
+// one per scheduler) left a CTA 10-20 us in its epilogue - 128 dependent (ld, SiLU, split, store) sequences per thread with nothing to hide
+// their latency, and the next CTA cannot start before this one leaves (profiles/r02_batched_path.txt: pre.gu 22.5 us with, 12.3 us without the
+// epilogue).  EPW = 8 (MP = 64) or 16 warps: warp e works on lane quarter e % 4 and the column block e / 4 of the accumulator.
+template <int MP> struct SkWarps { static constexpr int EPW = MP <= 64 ? 8 : 16, CW = MP / (EPW / 4), THREADS = (3 + EPW) * 32; };
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -678,7 +686,7 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 // k-block (a TMA op costs ~0.1 us of issue time on the issuing thread, so ops are kept few and the
 // weight and activation streams are issued by different warps).
 template <int MP, int STAGES>
-__global__ void __launch_bounds__(SK_THREADS, 1)
+__global__ void __launch_bounds__(SkWarps<MP>::THREADS, 1)
 gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmA, const SkParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr uint32_t W_BYTES = 128 * TC_BK * 2;  // 16 KB
@@ -697,6 +705,10 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     const int tile = blockIdx.x, split = blockIdx.y, n0 = tile * 128;
     const int total_kb = (p.K + TC_BK - 1) / TC_BK;
     const int kb0 = split * p.kb_per, kb1 = min(total_kb, kb0 + p.kb_per), num_kb = kb1 - kb0;
+    // Every CTA needs the SAME activation k-blocks; walked in the same order by all CTAs at the same time, the few L2 slices that
+    // hold the current k-block serve all 148 SMs while the others idle.  CTA `tile` therefore starts `tile` k-blocks into its
+    // range (the sum over k is order-independent up to f32 rounding; the order is fixed per tile, so results stay deterministic).
+    const int rot = p.rotate_k ? tile % num_kb : 0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -721,20 +733,26 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     if (warp == 0) {
         if (lane == 0) {
             const uint32_t tx = W_BYTES + (p.nsplit == 2 ? 2 * A_BYTES : A_BYTES);
+            unsigned long long w_pol; // weights are read once per GEMM: L2 evict-first
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(w_pol));
             for (int i = 0; i < num_kb; i++) {
                 const int s = i % STAGES;
                 mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
                 uint8_t *st = smem + s * STAGE_BYTES;
                 mbar_expect_tx(&full_bar[s], tx); // covers both producers' bytes; the phase cannot complete before this arrive
-                tma_load_2d(st, &tmW, &full_bar[s], (kb0 + i) * TC_BK, n0);
+                const int kb = kb0 + (i + rot) % num_kb;
+                if (p.w_tiled)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(st)),
+                                 "l"(p.w_tiled + ((size_t)tile * p.total_kb + kb) * W_BYTES), "r"(W_BYTES), "r"(smem_u32(&full_bar[s])), "l"(w_pol) : "memory");
+                else tma_load_2d(st, &tmW, &full_bar[s], kb * TC_BK, n0);
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 2 + SkWarps<MP>::EPW) {
         if (lane == 0) { // activation producer
             for (int i = 0; i < num_kb; i++) {
                 const int s = i % STAGES;
                 mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
-                tma_load_3d(smem + s * STAGE_BYTES + W_BYTES, &tmA, &full_bar[s], (kb0 + i) * TC_BK, 0, 0);
+                tma_load_3d(smem + s * STAGE_BYTES + W_BYTES, &tmA, &full_bar[s], (kb0 + (i + rot) % num_kb) * TC_BK, 0, 0);
             }
         }
     } else if (warp == 1) {
@@ -771,16 +789,17 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             }
             tc_commit(tmem_full_bar);
         }
-    } else if (warp < 6) {
-        // ===== epilogue warps 2..5: thread <-> weight row n, loops over the activation rows m
+    } else if (warp < 2 + SkWarps<MP>::EPW) {
+        // ===== epilogue warps: thread <-> weight row n (TMEM lane quarter warp % 4), activation rows m of this warp's column block
+        constexpr int CW = SkWarps<MP>::CW;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const int q = warp & 3, nl = q * 32 + lane, n = n0 + nl;
+        const int q = warp & 3, nl = q * 32 + lane, n = n0 + nl, cb = (warp - 2) >> 2;
         float *wsp = p.cluster ? reinterpret_cast<float *>(smem) + nl // every stage has been consumed: the MMAs that read them are complete
                                : p.ws + ((size_t)(tile * p.S + split) * MP) * 128 + nl;
 #pragma unroll 1
-        for (int c0 = 0; c0 < MP; c0 += 32) {
-            if (c0 >= p.M) break; // columns beyond M hold products with zero-filled rows
+        for (int c0 = cb * CW; c0 < (cb + 1) * CW; c0 += 32) {
+            if (c0 >= p.M || (p.rotate_k & 2)) break; // columns beyond M hold products with zero-filled rows (bit 1: timing experiment without the epilogue)
             uint32_t r[32];
             tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             if (MP <= 128 && p.fuse_planes) {
@@ -814,7 +833,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 #pragma unroll
         for (int sp = 0; sp < 8; sp++)
             asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer[sp]) : "r"(smem_u32(smem)), "r"(sp < p.S ? sp : 0));
-        for (int idx = mlo * 32 + threadIdx.x; idx < mhi * 32; idx += SK_THREADS) {
+        for (int idx = mlo * 32 + threadIdx.x; idx < mhi * 32; idx += SkWarps<MP>::THREADS) {
             const int m = idx >> 5, c4 = idx & 31;
             const uint32_t off = (uint32_t)(m * 128 + c4 * 4) * 4u;
             float4 t[8];
@@ -846,7 +865,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     __threadfence();
     const float *wst = p.ws + ((size_t)tile * p.S * MP) * 128;
     // 4 output float4s per thread per pass, all S x 4 loads issued before the first add (one L2 round trip per pass)
-    for (int base = 0; base < p.M * 32; base += SK_THREADS * 4) {
+    for (int base = 0; base < p.M * 32; base += SkWarps<MP>::THREADS * 4) {
         float4 acc4[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) acc4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -854,7 +873,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             float4 t[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                const int idx = base + u * SK_THREADS + threadIdx.x;
+                const int idx = base + u * SkWarps<MP>::THREADS + threadIdx.x;
                 t[u] = idx < p.M * 32 ? __ldcg(reinterpret_cast<const float4 *>(wst + ((size_t)sp * MP + (idx >> 5)) * 128) + (idx & 31))
                                       : make_float4(0.f, 0.f, 0.f, 0.f);
             }
@@ -863,7 +882,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-        const int idx = base + u * SK_THREADS + threadIdx.x;
+        const int idx = base + u * SkWarps<MP>::THREADS + threadIdx.x;
         if (idx >= p.M * 32) continue;
         sk_reduced_store<MP>(p, n0 + (idx & 31) * 4, idx >> 5, acc4[u]);
         }
@@ -984,8 +1003,25 @@ int tc_encode_map(void *out_map64, const bf16_t *ptr, int rows, int K, int box_c
 // Skinny path (M <= 256): activation columns MP, weight tiles of 128 rows, split factor S (<= 8 = the portable cluster
 // size, also without clusters so that QASR_GEMM_SK_CLUSTER only changes where the partials travel) and k-blocks per split.
 struct SkPlan { int MP, n_tiles, total_kb, S, kb_per; bool cluster_mode; };
+
+// ---- tile-major weight copies for the skinny kernel ------------------------------------------------
+// A 2-D TMA box of a row-major [N, K] weight matrix is 128 rows x 128 bytes: 128 separate 128-byte pieces, one per DRAM page
+// (3.6 TB/s at best, profiles/r01_stream_microbench.txt).  The weight-streaming GEMMs (M <= 256: single-utterance prefill / encoder,
+// every GEMM of a batched decode step) therefore read a second copy of W laid out tile-major, [n tile][k block][128 rows x 64 columns
+// already in the 128B-swizzled operand layout], 16 KB contiguous per k-block: one bulk copy, sequential DRAM pages.
+struct TiledEntry { const bf16_t *W; int N, K; const uint8_t *tiled; };
+static TiledEntry g_tiled[1024];
+static int g_n_tiled = 0;
+static int g_tiled_mode = -1; // QASR_GEMM_TILED=0 switches the copies off (A/B runs)
+static const uint8_t *gemm_tc_lookup_tiled(const bf16_t *W, int N, int K) {
+    if (g_tiled_mode == -2) return reinterpret_cast<const uint8_t *>(W); // timing experiment only (wrong results): bulk copies straight from the row-major matrix
+    for (int i = 0; i < g_n_tiled; i++)
+        if (g_tiled[i].W == W && g_tiled[i].N == N && g_tiled[i].K == K) return g_tiled[i].tiled;
+    return nullptr;
+}
 static SkPlan sk_plan(int M, int K, int N) {
     static int target_ctas = 0, min_kb = 0, sk_cluster = -1;
+    if (g_tiled_mode == -1) { const char *e = getenv("QASR_GEMM_TILED"); g_tiled_mode = e && !strcmp(e, "fake") ? -2 : (e && e[0] == '0' ? 0 : 1); }
     if (!target_ctas) {
         const char *e = getenv("QASR_GEMM_TARGET_CTAS"), *m = getenv("QASR_GEMM_MIN_KB"), *ev = getenv("QASR_GEMM_SK_CLUSTER");
         target_ctas = e && atoi(e) > 0 ? atoi(e) : 74;
@@ -1041,6 +1077,9 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
         sp.M = M; sp.N = N; sp.K = K; sp.nsplit = A_lo ? 2 : 1; sp.S = S; sp.kb_per = kb_per;
         sp.ws = sc.ws; sp.tickets = sc.tickets; sp.epi = epi;
         sp.cluster = sk_cluster && S > 1;
+        sp.total_kb = pl.total_kb;
+        { static int rk = -1; if (rk < 0) { const char *ev = getenv("QASR_GEMM_SK_ROTATE"); rk = ev ? atoi(ev) : 1; } sp.rotate_k = rk; }
+        sp.w_tiled = gemm_tc_lookup_tiled(W, N, K);
         static int sk_fuse = -1;
         if (sk_fuse < 0) { const char *ev = getenv("QASR_GEMM_SK_FUSE"); sk_fuse = !(ev && ev[0] == '0'); }
         sp.fuse_planes = sk_fuse && A_lo && MP <= 128;
@@ -1061,9 +1100,9 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
             if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(3d) failed (%d) M=%d K=%d", (int)r, M, K); return -1; }
         }
         dim3 grid(n_tiles, S);
-        if (MP == 64) launch_pdl_cluster(gemm_tc_skinny_kernel<64, 6>, grid, SK_THREADS, sk_smem_bytes<64, 6>(), s, sp.cluster ? S : 1, mw, ma, sp);
-        else if (MP == 128) launch_pdl_cluster(gemm_tc_skinny_kernel<128, 4>, grid, SK_THREADS, sk_smem_bytes<128, 4>(), s, sp.cluster ? S : 1, mw, ma, sp);
-        else launch_pdl_cluster(gemm_tc_skinny_kernel<256, 2>, grid, SK_THREADS, sk_smem_bytes<256, 2>(), s, sp.cluster ? S : 1, mw, ma, sp);
+        if (MP == 64) launch_pdl_cluster(gemm_tc_skinny_kernel<64, 6>, grid, SkWarps<64>::THREADS, sk_smem_bytes<64, 6>(), s, sp.cluster ? S : 1, mw, ma, sp);
+        else if (MP == 128) launch_pdl_cluster(gemm_tc_skinny_kernel<128, 4>, grid, SkWarps<128>::THREADS, sk_smem_bytes<128, 4>(), s, sp.cluster ? S : 1, mw, ma, sp);
+        else launch_pdl_cluster(gemm_tc_skinny_kernel<256, 2>, grid, SkWarps<256>::THREADS, sk_smem_bytes<256, 2>(), s, sp.cluster ? S : 1, mw, ma, sp);
         cudaError_t le = cudaGetLastError();
         if (le != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc skinny launch: %s", cudaGetErrorString(le)); return -1; }
         return 0;

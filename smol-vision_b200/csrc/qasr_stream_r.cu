@@ -69,6 +69,9 @@ __device__ __forceinline__ void sr_bulk_load(uint32_t dst, const void *src, uint
 __device__ __forceinline__ void sr_bulk_prefetch_l2(const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void sr_bulk_prefetch_l2_hint(const void *src, uint32_t bytes, u64 pol) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
+}
 
 struct SrLayout { // dynamic shared memory: ring | xf | x | partial | small | barriers
     static __host__ __device__ size_t ring_bytes(int nslot) { return (size_t)nslot * SR_ROUND; }
@@ -121,6 +124,8 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
             uint32_t total = rounds_per_step * (uint32_t)p.n_steps;
             u64 pol;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            u64 pol_last;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
             const uint32_t ahead = q == 0 ? (uint32_t)min(p.l2_ahead_units, 64) : 0u;
             for (uint32_t r = 0; r < ahead && r < rounds_per_step; r++) sr_bulk_prefetch_l2(src + (size_t)r * SR_ROUND, SR_ROUND);
             uint32_t slot = 0, pass = 0, rr = 0, pr = ahead % rounds_per_step; // ring slot, ring pass, round within the step, prefetch cursor
@@ -146,7 +151,11 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
                 const uint32_t dst = sk_smem_u32(sm_ring + (size_t)slot * SR_ROUND);
                 const uint8_t *g = src + (size_t)rr * SR_ROUND;
                 for (uint32_t c = q; c < chunks_per_round; c += n_prod) sr_bulk_load(dst + c * chunk, g + (size_t)c * chunk, chunk, bar_full + 8 * slot, pol);
-                if (ahead) { sr_bulk_prefetch_l2(src + (size_t)pr * SR_ROUND, SR_ROUND); if (++pr == rounds_per_step) pr = 0; }
+                if (ahead) {
+                    if (p.debug & 512) sr_bulk_prefetch_l2_hint(src + (size_t)pr * SR_ROUND, SR_ROUND, pol_last);
+                    else sr_bulk_prefetch_l2(src + (size_t)pr * SR_ROUND, SR_ROUND);
+                    if (++pr == rounds_per_step) pr = 0;
+                }
                 if (++rr == rounds_per_step) rr = 0;
                 if (++slot == (uint32_t)nslot) { slot = 0; pass++; }
             }

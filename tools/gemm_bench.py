@@ -5,6 +5,9 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as ge
 pkg = ge.load_package()
 eng = pkg.QasrCuda(0)
+if os.environ.get("QASR_SPLIT"):  # 1 = plain bf16 activations (one plane): timing experiments
+    eng.lib.qasr_cuda_set_gemm_split.argtypes = [C.c_void_p, C.c_int]
+    print("set_gemm_split rc", eng.lib.qasr_cuda_set_gemm_split(eng.ctx, int(os.environ["QASR_SPLIT"])))
 f = eng.lib.qasr_debug_gemm_bench
 f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
 shapes = [("pre.qkv", 61, 2048, 4096), ("pre.wo", 61, 2048, 2048), ("pre.gu", 61, 2048, 12288), ("pre.down", 61, 6144, 2048),
