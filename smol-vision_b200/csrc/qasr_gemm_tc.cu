@@ -613,10 +613,6 @@ struct SkParams {
     unsigned *tickets;              // [n_tiles], zero between launches
     int fuse_planes;                // 1 (MP <= 128, nsplit == 2): ONE N = 2*MP MMA per k-step over the [hi | lo] planes, two accumulators
     int cluster;                    // 1: the S splits of a tile form one thread-block cluster (1, S, 1) and reduce through DSMEM
-    const uint8_t *w_tiled;         // tile-major copy of W ([n tile][k block][16 KB in the swizzled operand layout]) or NULL: the weight producer
-                                    // then issues ONE contiguous bulk copy per k-block instead of a 2-D box of 128 rows x 128 bytes
-    int total_kb;
-    int rotate_k;                   // 1: CTA `tile` walks its k-blocks starting at tile % num_kb (spreads the activation reads over the L2 slices)
     GemmEpilogue epi;
 };
 
@@ -673,7 +669,7 @@ __device__ __forceinline__ void sk_reduced_store(const SkParams &p, int nb, int 
 // warps: 0 W producer, 1 MMA, 2 .. 2 + EPW - 1 epilogue, 2 + EPW activation producer.  One epilogue warp per TMEM lane quarter (4 warps,
 // one per scheduler) left a CTA 10-20 us in its epilogue - 128 dependent (ld, SiLU, split, store) sequences per thread with nothing to hide
 // their latency, and the next CTA cannot start before this one leaves (profiles/r02_batched_path.txt: pre.gu 22.5 us with, 12.3 us without the
-// epilogue).  EPW = 8 (MP = 64) or 16 warps: warp e works on lane quarter e % 4 and the column block e / 4 of the accumulator.
+// epilogue; contiguous bulk copies of pre-tiled weights, a rotated k order per CTA and a single activation plane all changed nothing).  EPW = 8 (MP = 64) or 16 warps: warp e works on lane quarter e % 4 and the column block e / 4 of the accumulator.
 template <int MP> struct SkWarps { static constexpr int EPW = MP <= 64 ? 8 : 16, CW = MP / (EPW / 4), THREADS = (3 + EPW) * 32; };
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
     asm volatile(
@@ -705,10 +701,6 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     const int tile = blockIdx.x, split = blockIdx.y, n0 = tile * 128;
     const int total_kb = (p.K + TC_BK - 1) / TC_BK;
     const int kb0 = split * p.kb_per, kb1 = min(total_kb, kb0 + p.kb_per), num_kb = kb1 - kb0;
-    // Every CTA needs the SAME activation k-blocks; walked in the same order by all CTAs at the same time, the few L2 slices that
-    // hold the current k-block serve all 148 SMs while the others idle.  CTA `tile` therefore starts `tile` k-blocks into its
-    // range (the sum over k is order-independent up to f32 rounding; the order is fixed per tile, so results stay deterministic).
-    const int rot = p.rotate_k ? tile % num_kb : 0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -733,18 +725,12 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     if (warp == 0) {
         if (lane == 0) {
             const uint32_t tx = W_BYTES + (p.nsplit == 2 ? 2 * A_BYTES : A_BYTES);
-            unsigned long long w_pol; // weights are read once per GEMM: L2 evict-first
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(w_pol));
             for (int i = 0; i < num_kb; i++) {
                 const int s = i % STAGES;
                 mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
                 uint8_t *st = smem + s * STAGE_BYTES;
                 mbar_expect_tx(&full_bar[s], tx); // covers both producers' bytes; the phase cannot complete before this arrive
-                const int kb = kb0 + (i + rot) % num_kb;
-                if (p.w_tiled)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(st)),
-                                 "l"(p.w_tiled + ((size_t)tile * p.total_kb + kb) * W_BYTES), "r"(W_BYTES), "r"(smem_u32(&full_bar[s])), "l"(w_pol) : "memory");
-                else tma_load_2d(st, &tmW, &full_bar[s], kb * TC_BK, n0);
+                tma_load_2d(st, &tmW, &full_bar[s], (kb0 + i) * TC_BK, n0);
             }
         }
     } else if (warp == 2 + SkWarps<MP>::EPW) {
@@ -752,7 +738,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
             for (int i = 0; i < num_kb; i++) {
                 const int s = i % STAGES;
                 mbar_wait(&empty_bar[s], ((i / STAGES) & 1) ^ 1);
-                tma_load_3d(smem + s * STAGE_BYTES + W_BYTES, &tmA, &full_bar[s], (kb0 + (i + rot) % num_kb) * TC_BK, 0, 0);
+                tma_load_3d(smem + s * STAGE_BYTES + W_BYTES, &tmA, &full_bar[s], (kb0 + i) * TC_BK, 0, 0);
             }
         }
     } else if (warp == 1) {
@@ -799,7 +785,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                                : p.ws + ((size_t)(tile * p.S + split) * MP) * 128 + nl;
 #pragma unroll 1
         for (int c0 = cb * CW; c0 < (cb + 1) * CW; c0 += 32) {
-            if (c0 >= p.M || (p.rotate_k & 2)) break; // columns beyond M hold products with zero-filled rows (bit 1: timing experiment without the epilogue)
+            if (c0 >= p.M) break; // columns beyond M hold products with zero-filled rows
             uint32_t r[32];
             tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             if (MP <= 128 && p.fuse_planes) {
@@ -1004,24 +990,8 @@ int tc_encode_map(void *out_map64, const bf16_t *ptr, int rows, int K, int box_c
 // size, also without clusters so that QASR_GEMM_SK_CLUSTER only changes where the partials travel) and k-blocks per split.
 struct SkPlan { int MP, n_tiles, total_kb, S, kb_per; bool cluster_mode; };
 
-// ---- tile-major weight copies for the skinny kernel ------------------------------------------------
-// A 2-D TMA box of a row-major [N, K] weight matrix is 128 rows x 128 bytes: 128 separate 128-byte pieces, one per DRAM page
-// (3.6 TB/s at best, profiles/r01_stream_microbench.txt).  The weight-streaming GEMMs (M <= 256: single-utterance prefill / encoder,
-// every GEMM of a batched decode step) therefore read a second copy of W laid out tile-major, [n tile][k block][128 rows x 64 columns
-// already in the 128B-swizzled operand layout], 16 KB contiguous per k-block: one bulk copy, sequential DRAM pages.
-struct TiledEntry { const bf16_t *W; int N, K; const uint8_t *tiled; };
-static TiledEntry g_tiled[1024];
-static int g_n_tiled = 0;
-static int g_tiled_mode = -1; // QASR_GEMM_TILED=0 switches the copies off (A/B runs)
-static const uint8_t *gemm_tc_lookup_tiled(const bf16_t *W, int N, int K) {
-    if (g_tiled_mode == -2) return reinterpret_cast<const uint8_t *>(W); // timing experiment only (wrong results): bulk copies straight from the row-major matrix
-    for (int i = 0; i < g_n_tiled; i++)
-        if (g_tiled[i].W == W && g_tiled[i].N == N && g_tiled[i].K == K) return g_tiled[i].tiled;
-    return nullptr;
-}
 static SkPlan sk_plan(int M, int K, int N) {
     static int target_ctas = 0, min_kb = 0, sk_cluster = -1;
-    if (g_tiled_mode == -1) { const char *e = getenv("QASR_GEMM_TILED"); g_tiled_mode = e && !strcmp(e, "fake") ? -2 : (e && e[0] == '0' ? 0 : 1); }
     if (!target_ctas) {
         const char *e = getenv("QASR_GEMM_TARGET_CTAS"), *m = getenv("QASR_GEMM_MIN_KB"), *ev = getenv("QASR_GEMM_SK_CLUSTER");
         target_ctas = e && atoi(e) > 0 ? atoi(e) : 74;
@@ -1077,9 +1047,6 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
         sp.M = M; sp.N = N; sp.K = K; sp.nsplit = A_lo ? 2 : 1; sp.S = S; sp.kb_per = kb_per;
         sp.ws = sc.ws; sp.tickets = sc.tickets; sp.epi = epi;
         sp.cluster = sk_cluster && S > 1;
-        sp.total_kb = pl.total_kb;
-        { static int rk = -1; if (rk < 0) { const char *ev = getenv("QASR_GEMM_SK_ROTATE"); rk = ev ? atoi(ev) : 1; } sp.rotate_k = rk; }
-        sp.w_tiled = gemm_tc_lookup_tiled(W, N, K);
         static int sk_fuse = -1;
         if (sk_fuse < 0) { const char *ev = getenv("QASR_GEMM_SK_FUSE"); sk_fuse = !(ev && ev[0] == '0'); }
         sp.fuse_planes = sk_fuse && A_lo && MP <= 128;

@@ -32,20 +32,7 @@
 #define SR_ATT_BATCH 4        /* cached keys per warp and batch: 8 warps x 4 = 32 keys per split, as in the ring kernel */
 #define SR_ATT_STRIDE SK_ATT_STRIDE
 #define SR_HEAD_STRIDE 4
-#ifndef SR_CHAINS
-#define SR_CHAINS 2           /* independent MMA accumulator chains per round (2 or 4) */
-#endif
-#ifndef SR_ROUND_INFLIGHT
-#define SR_ROUND_INFLIGHT 0   /* 1: all 16 operand loads of a round in flight before the first MMA (48 operand registers instead of 24) */
-#endif
-#ifndef SR_FAST_EXP
-#define SR_FAST_EXP 0
-#endif
-#if SR_FAST_EXP
-#define sr_exp __expf
-#else
-#define sr_exp expf
-#endif
+#define SR_CHAINS 2           /* independent MMA accumulator chains per round (4 chains, all 16 operand loads of a round in flight, __expf in the softmax: all within noise) */
 #ifndef SR_MERGE_PG
 #define SR_MERGE_PG 2         /* pairs per thread whose S x 4 exchange words are in flight together when the keys are split */
 #endif      /* words per CTA in the head exchange (one sector) */
@@ -68,9 +55,6 @@ __device__ __forceinline__ void sr_bulk_load(uint32_t dst, const void *src, uint
 }
 __device__ __forceinline__ void sr_bulk_prefetch_l2(const void *src, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void sr_bulk_prefetch_l2_hint(const void *src, uint32_t bytes, u64 pol) {
-    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
 }
 
 struct SrLayout { // dynamic shared memory: ring | xf | x | partial | small | barriers
@@ -124,8 +108,6 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
             uint32_t total = rounds_per_step * (uint32_t)p.n_steps;
             u64 pol;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-            u64 pol_last;
-            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
             const uint32_t ahead = q == 0 ? (uint32_t)min(p.l2_ahead_units, 64) : 0u;
             for (uint32_t r = 0; r < ahead && r < rounds_per_step; r++) sr_bulk_prefetch_l2(src + (size_t)r * SR_ROUND, SR_ROUND);
             uint32_t slot = 0, pass = 0, rr = 0, pr = ahead % rounds_per_step; // ring slot, ring pass, round within the step, prefetch cursor
@@ -151,11 +133,7 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
                 const uint32_t dst = sk_smem_u32(sm_ring + (size_t)slot * SR_ROUND);
                 const uint8_t *g = src + (size_t)rr * SR_ROUND;
                 for (uint32_t c = q; c < chunks_per_round; c += n_prod) sr_bulk_load(dst + c * chunk, g + (size_t)c * chunk, chunk, bar_full + 8 * slot, pol);
-                if (ahead) {
-                    if (p.debug & 512) sr_bulk_prefetch_l2_hint(src + (size_t)pr * SR_ROUND, SR_ROUND, pol_last);
-                    else sr_bulk_prefetch_l2(src + (size_t)pr * SR_ROUND, SR_ROUND);
-                    if (++pr == rounds_per_step) pr = 0;
-                }
+                if (ahead) { sr_bulk_prefetch_l2(src + (size_t)pr * SR_ROUND, SR_ROUND); if (++pr == rounds_per_step) pr = 0; }
                 if (++rr == rounds_per_step) rr = 0;
                 if (++slot == (uint32_t)nslot) { slot = 0; pass++; }
             }
@@ -181,21 +159,6 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
     // one round for this warp: 16 rows x (64 + 64) columns against the phase input, two independent accumulator chains
     auto do_round = [&](int j, float(&c)[SR_CHAINS][4]) {
         const uint2 *xb = reinterpret_cast<const uint2 *>(sm_xf) + (size_t)(warp + 16 * j) * 32 + (lane & 7);
-#if SR_ROUND_INFLIGHT
-        uint2 b0[4], b1[4];
-#pragma unroll
-        for (int kb = 0; kb < 4; kb++) { b0[kb] = xb[kb * 8]; b1[kb] = xb[SR_WARPS * 32 + kb * 8]; } // lanes >= 8 feed D columns nobody reads
-        while (!sr_mbar_try(bar_full + 8 * cslot, cpar)) {}
-        const uint4 *ring = reinterpret_cast<const uint4 *>(sm_ring + (size_t)cslot * SR_ROUND + (size_t)warp * (2 * SK_UNIT)) + lane;
-        uint4 a0[4], a1[4];
-#pragma unroll
-        for (int kb = 0; kb < 4; kb++) { a0[kb] = ring[kb * 32]; a1[kb] = ring[128 + kb * 32]; }
-        if (finer) mark();
-#pragma unroll
-        for (int kb = 0; kb < 4; kb++) sr_mma(c[kb & (SR_CHAINS - 1)], a0[kb], b0[kb]);
-#pragma unroll
-        for (int kb = 0; kb < 4; kb++) sr_mma(c[kb & (SR_CHAINS - 1)], a1[kb], b1[kb]);
-#else
         uint2 b0[4];
 #pragma unroll
         for (int kb = 0; kb < 4; kb++) b0[kb] = xb[kb * 8]; // lanes >= 8 feed D columns nobody reads
@@ -217,7 +180,6 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
 #pragma unroll
             for (int kb = 0; kb < 4; kb++) sr_mma(c[kb & (SR_CHAINS - 1)], a1[kb], b1[kb]);
         }
-#endif
         __syncwarp();
         if (lane == 0) sr_mbar_arrive(bar_empty + 8 * cslot); // operands were read at issue: the slot may be refilled
         if (finer) mark();
@@ -249,13 +211,8 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
                 if (grp + 1 == cg1) flush_ss(); // shuffles overlap the latency of the last MMAs
                 if (tig == 0) { // D columns 0 / 1 = x_hi / x_lo sums; rows gid and gid + 8
                     const int r = (grp - cg0) * 16 + gid;
-#if SR_CHAINS == 4
-                    part[r][warp] = ((c[0][0] + c[1][0]) + (c[2][0] + c[3][0])) + ((c[0][1] + c[1][1]) + (c[2][1] + c[3][1]));
-                    part[r + 8][warp] = ((c[0][2] + c[1][2]) + (c[2][2] + c[3][2])) + ((c[0][3] + c[1][3]) + (c[2][3] + c[3][3]));
-#else
                     part[r][warp] = (c[0][0] + c[1][0]) + (c[0][1] + c[1][1]);
                     part[r + 8][warp] = (c[0][2] + c[1][2]) + (c[0][3] + c[1][3]);
-#endif
                 }
             }
             if (fine && layer_phase) mark();
@@ -455,12 +412,12 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
                         if (j < k1) {
                             const float s = sc8[i];
                             if (s > m) {
-                                const float cc = sr_exp(m - s);
+                                const float cc = expf(m - s);
                                 lsum = lsum * cc + 1.0f;
                                 acc.x = acc.x * cc + vr[i].x; acc.y = acc.y * cc + vr[i].y; acc.z = acc.z * cc + vr[i].z; acc.w = acc.w * cc + vr[i].w;
                                 m = s;
                             } else {
-                                const float w = sr_exp(s - m);
+                                const float w = expf(s - m);
                                 lsum += w;
                                 acc.x += w * vr[i].x; acc.y += w * vr[i].y; acc.z += w * vr[i].z; acc.w += w * vr[i].w;
                             }
@@ -478,7 +435,7 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
                     float Ls = 0.0f, Aa = 0.0f;
 #pragma unroll
                     for (int w = 0; w < SR_WARPS; w++) {
-                        const float e = sr_exp(wml[w * 2] - M);
+                        const float e = expf(wml[w * 2] - M);
                         Ls += wml[w * 2 + 1] * e;
                         Aa += wacc[w * 128 + tid] * e;
                     }

@@ -63,7 +63,7 @@ tests pin what the bench times. 8 GPUs: {d8['value']:.0f} x (one replica per GPU
 | configs[4]: 256 x 30 s utterances, 1.7B, 128 tokens each | **{st['configs[4]']['value']:.0f} x** ({st['configs[4]']['ms_per_step'] / 1e3:.2f} s for 7680 s of audio, {st['configs[4]']['decoder_tok_s']:.0f} tokens/s; round 1: 405 x) | {st2['configs[4]']['value']:.0f} x | {st8['configs[4]']['value']:.0f} x | {st['configs[4]']['sequences_per_decode_step']} / {st2['configs[4]']['sequences_per_decode_step']} / {st8['configs[4]']['sequences_per_decode_step']} | {st['configs[4]']['roofline']['frac']:.2f} of the HBM peak (weights once + f32 KV rows of every sequence) |
 | configs[2]: 3600 s recording, -S 20 -W 3, 180 segments, 0.6B | **{st['configs[2]']['value']:.0f} x** ({st['configs[2]']['ms_per_step'] / 1e3:.2f} s, {st['configs[2]']['decoder_tok_s']:.0f} tokens/s; round 1: 770 x) | {st2['configs[2]']['value']:.0f} x | {st8['configs[2]']['value']:.0f} x | {st['configs[2]']['sequences_per_decode_step']} / {st2['configs[2]']['sequences_per_decode_step']} / {st8['configs[2]']['sequences_per_decode_step']} | {st['configs[2]']['roofline']['frac']:.2f} |
 
-(The 2-GPU line predates the 2-CTA GEMM, the implicit-GEMM conv and the tensor-core attention: 2.00 x of the one-GPU numbers of its day, 3020 / 3986 x.)
+2 GPUs: {st2['configs[4]']['value'] / st['configs[4]']['value']:.2f} x / {st2['configs[2]']['value'] / st['configs[2]']['value']:.2f} x of one GPU; 8 GPUs: {st8['configs[4]']['value'] / st['configs[4]']['value']:.2f} x / {st8['configs[2]']['value'] / st['configs[2]']['value']:.2f} x; configs[1] replicas (weak): {d2['value']:.0f} x and {d8['value']:.0f} x = {d8['value'] / d['value'] / 8:.2f} of linear at 8.
 Strong scaling is bounded by the shard size, not by a collective (there is none): at 8 GPUs a rank holds 32 utterances / 22-23 segments, so
 32 / 23 sequences share each pass over the weights instead of 128 / 90 (one GPU, 1.7B: 24.2k / 17.5k / 12.2k tokens/s at 128 / 64 / 32 sequences per
 step) and the encoder / prefill GEMMs run at a quarter of the rows; slowest / mean rank {st8['configs[4]']['rank_ms']['imbalance']:.3f} (configs[4]) and {st8['configs[2]']['rank_ms']['imbalance']:.3f} (configs[2]).
