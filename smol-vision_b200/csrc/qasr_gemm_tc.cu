@@ -29,7 +29,11 @@
 #define TC_BM 128
 #define TC_BK 64
 #define TC_STAGES 4
-#define TC_THREADS 192
+#define TC_EPI_WARPS 8 /* at most; the launch picks 4 or 8 epilogue warps (warp e drains TMEM lane quarter e % 4, column part e / 4 of the tile).
+                           Measured (profiles/r02_batched_path.txt): 8 warps help where the epilogue is exposed - short mainloops (K <= 1024: 0.6B
+                           prefill gate/up M = 16440 327 -> 296 us) and few tiles per CTA (encoder fc1 / fc2 at M = 3120: 76 -> 62, 87 -> 71 us) - and cost
+                           4-7 % on the long steady-state GEMMs (1.7B prefill at M = 25856), where the epilogue hides behind the next mainloop anyway */
+#define TC_THREADS ((2 + TC_EPI_WARPS) * 32)
 
 static char g_tc_err[256] = "";
 const char *gemm_tc_error(void) { return g_tc_err; }
@@ -258,7 +262,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         if (p.nsplit == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
         for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], GATHER ? 1 + TC_GATHER_THREADS : 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], (blockDim.x >> 5) - 2 - (GATHER ? TC_GATHER_THREADS / 32 : 0)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) { // TMEM allocation: two accumulator stages of BN f32 columns x 128 lanes
@@ -326,9 +330,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
                 tc_commit(&tmem_full_bar[as]); // accumulator of this tile complete
             }
         }
-    } else if (GATHER && warp >= 6) {
-        // ===== A-operand gather warps 6..9 (conv stem): thread = row r of the tile =====
-        const int r = threadIdx.x - TC_THREADS;
+    } else if (GATHER && warp >= (int)(blockDim.x >> 5) - TC_GATHER_THREADS / 32) {
+        // ===== A-operand gather warps (after the epilogue warps; conv stem): thread = row r of the tile =====
+        const int r = threadIdx.x - ((int)blockDim.x - TC_GATHER_THREADS);
         const int Hin = cg.Hin, Hout = Hin >> 1;
         const uint32_t row_sm = (uint32_t)r * 128u, sw = (uint32_t)(r & 7);
         // A gather thread publishes k-block i as soon as its copies have landed and never blocks on a ring slot with more than
@@ -384,8 +388,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         for (; arrived < it; arrived++) mbar_arrive(&full_bar[arrived % STAGES]);
     } else {
-        // ===== epilogue warps 2..5: TMEM lane quarter q = rows m0 + 32 q .. + 31, thread = row =====
-        const int q = warp & 3;
+        // ===== epilogue warps: TMEM lane quarter q = rows m0 + 32 q .. + 31 (thread = row), column part (warp - 2) / 4 of the tile =====
+        const int q = warp & 3, cpart = (warp - 2) >> 2;
+        const int cwidth = BN / ((((int)(blockDim.x >> 5) - 2 - (GATHER ? TC_GATHER_THREADS / 32 : 0))) >> 2);
         const GemmEpilogue &e = p.epi;
         const int width = e.mode == QASR_GEMM_SWIGLU_SPLIT ? 2 : 1;
         const bool aligned = (e.ldo % 8 == 0) && ((e.mode == QASR_GEMM_F32 || e.mode == QASR_GEMM_RESIDUAL)
@@ -400,7 +405,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < p.M;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = cpart * cwidth; c0 < (cpart + 1) * cwidth; c0 += 32) {
                 const int n = n0 + c0;
                 if (n >= p.N) break;
                 uint32_t r[32];
@@ -489,7 +494,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         if (p.nsplit == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA_lo) : "memory");
         for (int s = 0; s < TC2_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 8); } // 4 epilogue warps x 2 CTAs
+        for (int s = 0; s < 2; s++) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 2 * ((blockDim.x >> 5) - 2)); } // epilogue warps of both CTAs
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) { // both CTAs of the pair take part in the allocation (same columns in both tensor memories)
@@ -553,8 +558,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             }
         }
     } else {
-        // ===== epilogue warps 2..5 of both CTAs: this CTA's 128 rows of the pair tile =====
-        const int q = warp & 3;
+        // ===== epilogue warps of both CTAs: this CTA's 128 rows of the pair tile, column part (warp - 2) / 4 =====
+        const int q = warp & 3, cpart = (warp - 2) >> 2;
+        const int cwidth = BN / (((int)(blockDim.x >> 5) - 2) >> 2);
         const GemmEpilogue &e = p.epi;
         const int width = e.mode == QASR_GEMM_SWIGLU_SPLIT ? 2 : 1;
         const bool aligned = (e.ldo % 8 == 0) && ((e.mode == QASR_GEMM_F32 || e.mode == QASR_GEMM_RESIDUAL)
@@ -569,7 +575,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < p.M;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = cpart * cwidth; c0 < (cpart + 1) * cwidth; c0 += 32) {
                 const int n = n0 + c0;
                 if (n >= p.N) break;
                 uint32_t r[32];
@@ -581,7 +587,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { // "drained" goes to the leader's barrier (the MMA issuer waits there for all 8 epilogue warps)
+            if (lane == 0) { // "drained" goes to the leader's barrier (the MMA issuer waits there for the epilogue warps of both CTAs)
                 const uint32_t lbar = mapa_u32(smem_u32(&tmem_empty_bar[as]), 0);
                 asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lbar) : "memory");
             }
@@ -1088,6 +1094,13 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
     p.M = M; p.N = N; p.K = K;
     p.nsplit = A_lo ? 2 : 1;
     p.epi = epi;
+    // epilogue warps: 8 where the epilogue is exposed (short mainloop, or so few tiles per CTA that its tail shows), else 4 (see TC_EPI_WARPS)
+    static int force_epw = -1;
+    if (force_epw < 0) { const char *ev = getenv("QASR_GEMM_EPI_WARPS"); force_epw = ev ? atoi(ev) : 0; }
+    const int bn_sel = bn64 ? 64 : (bn256 ? 256 : 128);
+    const long long tiles_sel = (long long)((M + TC_BM - 1) / TC_BM) * ((N + bn_sel - 1) / bn_sel);
+    const bool wide_epi = force_epw ? force_epw == 8 : (K <= 1024 || tiles_sel <= 3 * 148);
+    const int epi_threads = (2 + (wide_epi ? 8 : 4)) * 32, bn64_threads = (2 + 4) * 32; // 64-wide tiles: one 32-column chunk per quarter, nothing to split
     static int use_2cta = -1; // QASR_GEMM_2CTA=0: keep the one-CTA 128 x 256 tiles (A/B runs)
     if (use_2cta < 0) { const char *ev = getenv("QASR_GEMM_2CTA"); use_2cta = !(ev && ev[0] == '0'); }
     if (bn256 && use_2cta && M > 128) { // CTA pairs, 256 x 256 tiles
@@ -1102,7 +1115,7 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long total = (long long)p.tiles_m * p.tiles_n;
         const long long pairs = total < sms / 2 ? total : sms / 2;
-        launch_pdl(gemm_tc2_kernel, dim3((unsigned)(2 * pairs)), TC_THREADS, tc2_smem_bytes(), s, ma, ml, mb, p);
+        launch_pdl(gemm_tc2_kernel, dim3((unsigned)(2 * pairs)), epi_threads, tc2_smem_bytes(), s, ma, ml, mb, p);
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc 2-CTA launch: %s", cudaGetErrorString(e2)); return -1; }
         return 0;
@@ -1120,9 +1133,9 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
     const long long total = (long long)p.tiles_m * p.tiles_n;
     dim3 grid((unsigned)(total < sms ? total : sms)); // persistent: one CTA per SM walks the tile list
     const ConvGather none = {};
-    if (bn256) launch_pdl(gemm_tc_kernel<256>, grid, TC_THREADS, tc_smem_bytes<256>(), s, ma, ml, mb, p, none);
-    else if (bn64) launch_pdl(gemm_tc_kernel<64>, grid, TC_THREADS, tc_smem_bytes<64>(), s, ma, ml, mb, p, none);
-    else launch_pdl(gemm_tc_kernel<128>, grid, TC_THREADS, tc_smem_bytes<128>(), s, ma, ml, mb, p, none);
+    if (bn256) launch_pdl(gemm_tc_kernel<256>, grid, epi_threads, tc_smem_bytes<256>(), s, ma, ml, mb, p, none);
+    else if (bn64) launch_pdl(gemm_tc_kernel<64>, grid, bn64_threads, tc_smem_bytes<64>(), s, ma, ml, mb, p, none);
+    else launch_pdl(gemm_tc_kernel<128>, grid, epi_threads, tc_smem_bytes<128>(), s, ma, ml, mb, p, none);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc launch: %s", cudaGetErrorString(e));
@@ -1161,8 +1174,8 @@ int launch_conv_gemm_tc(cudaStream_t s, const bf16_t *src_hi, const bf16_t *src_
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long total = (long long)p.tiles_m * p.tiles_n;
     dim3 grid((unsigned)(total < sms ? total : sms));
-    if (bn256) launch_pdl(gemm_tc_kernel<256, true>, grid, TC_THREADS + TC_GATHER_THREADS, tc_smem_bytes<256>(), s, mb, mb, mb, p, cg);
-    else launch_pdl(gemm_tc_kernel<128, true>, grid, TC_THREADS + TC_GATHER_THREADS, tc_smem_bytes<128>(), s, mb, mb, mb, p, cg);
+    if (bn256) launch_pdl(gemm_tc_kernel<256, true>, grid, 192 + TC_GATHER_THREADS, tc_smem_bytes<256>(), s, mb, mb, mb, p, cg);
+    else launch_pdl(gemm_tc_kernel<128, true>, grid, 192 + TC_GATHER_THREADS, tc_smem_bytes<128>(), s, mb, mb, mb, p, cg);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "conv gemm launch: %s", cudaGetErrorString(e)); return -1; }
     return 0;
