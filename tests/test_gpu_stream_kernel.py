@@ -192,6 +192,17 @@ def test_config4_stream_real_parameters_vs_reference(pkg, model06, gpu06, ref_li
     assert any(want[i]["reused"] == n_pre and want[i - 1]["reused"] > n_pre for i in range(1, 22))   # the eviction chunk reuses the prompt prefix only
 
 
+_EOS_CHILD = r"""
+import sys, json
+sys.path.insert(0, {root!r})
+import __graft_entry__ as ge
+pkg = ge.load_package()
+eng = pkg.QasrCuda(0).load({vdir!r})
+out = [eng.transcribe_ids(pkg.synth_audio(1.0 + 0.37 * i, seed=500 + i), 40)[0].tolist() for i in range(4) for _ in range(2)]
+print("IDS " + json.dumps(out))
+"""
+
+
 def test_single_sequence_eos_stop_matches_reference(pkg, model06, ref_lib, oracle_lib):
     """Early stop of the persistent single-sequence kernel (reference qwen_asr.c:788-793): on the EOS-capable checkpoint the launch
     ends before its step budget, the producer warp of decode_rounds_kernel drains what it has in flight, and the next
@@ -211,6 +222,15 @@ def test_single_sequence_eos_stop_matches_reference(pkg, model06, ref_lib, oracl
                 assert eng.transcribe_ids(u, 40)[0].tolist() == w
     finally:
         eng.close()
+    # the same with several producer warps: every producer must issue its share of the last rounds and drain them (child process: the
+    # knobs are read once per process)
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, QASR_SR_PRODUCERS="4", QASR_SR_CHUNK="2048")
+    r = subprocess.run([sys.executable, "-c", _EOS_CHILD.format(root=root, vdir=vdir)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.loads([l for l in r.stdout.splitlines() if l.startswith("IDS ")][-1][4:])
+    assert got == [w for w in want for _ in range(2)]
 
 
 _OTHER_KERNEL = r"""
@@ -240,9 +260,10 @@ def test_ring_and_rounds_kernels_decode_the_same_ids(pkg, ref_lib, oracle_lib):
             want[variant] = [cpu.transcribe_ids(pkg.synth_audio(s, seed=900 + i), 10)[0].tolist() for i, s in enumerate((1.3, 3.64, 7.0))]
         finally:
             cpu.close()
-    for kernel in ("ring", "rounds"):
-        env = dict(os.environ, QASR_DECODE_KERNEL=kernel)
+    # the third run exercises the optional knobs of the rounds kernel: three producer warps sharing the copies of a round, a two-slot ring
+    for kernel, extra in (("ring", {}), ("rounds", {}), ("rounds", {"QASR_SR_PRODUCERS": "3", "QASR_SR_CHUNK": "4096", "QASR_SR_SLOTS": "2", "QASR_SR_L2AHEAD": "0"})):
+        env = dict(os.environ, QASR_DECODE_KERNEL=kernel, **extra)
         r = subprocess.run([sys.executable, "-c", _OTHER_KERNEL.format(root=root)], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         got = json.loads([l for l in r.stdout.splitlines() if l.startswith("IDS ")][-1][4:])
-        assert got == want, kernel
+        assert got == want, (kernel, extra)
