@@ -11,12 +11,14 @@
 // Here no consumer ever issues a weight load:
 //  * the image is laid out round-major: a round = the 16 units (16 rows x 1024 columns, 32 KB) that the consumer warps
 //    need together, contiguous in HBM in consumption order of the CTA;
-//  * the producer warp (one elected lane) keeps up to 6 rounds in flight: mbarrier expect_tx + ONE cp.async.bulk of
-//    32 KB per round, and a cp.async.bulk.prefetch.L2 a fixed number of rounds further ahead;
+//  * the producer warp (one elected lane) keeps a short ring of rounds in flight (3 slots for the 0.6B dims, 5 for 1.7B): mbarrier
+//    expect_tx + the round as four or eight cp.async.bulk copies (1-D TMA, L2 evict-first), and a cp.async.bulk.prefetch.L2 a
+//    few rounds further ahead; it waits on the `empty` barrier of a slot and on nothing else;
 //  * consumer warp w reads its 4 KB of a round (column slices w + 16 j and w + 8 + 16 j of the same 16 rows) with eight
 //    conflict-free LDS.128 after an mbarrier wait that has normally long completed, runs 8 MMAs on two independent
 //    accumulator chains and releases the slot with one arrive per warp.
-// 8 consumer warps x <= 224 registers leave room for every exchange word of a thread to be in flight at once.
+// 9 - 12 warps put three warps on one scheduler: the kernel is held to 168 registers and must not spill (with spills, a
+// larger ring - i.e. a smaller L1 - was measurably slower; tests/test_abi.py checks registers and stack).
 #include "qasr_stream_common.cuh"
 
 #define SR_WARPS 8            /* consumer warps */
@@ -31,11 +33,8 @@
 #define SR_PSTRIDE 9
 #define SR_ATT_BATCH 4        /* cached keys per warp and batch: 8 warps x 4 = 32 keys per split, as in the ring kernel */
 #define SR_ATT_STRIDE SK_ATT_STRIDE
-#define SR_HEAD_STRIDE 4
+#define SR_HEAD_STRIDE 4      /* words per CTA in the head exchange (one sector) */
 #define SR_CHAINS 2           /* independent MMA accumulator chains per round (4 chains, all 16 operand loads of a round in flight, __expf in the softmax: all within noise) */
-#ifndef SR_MERGE_PG
-#define SR_MERGE_PG 2         /* pairs per thread whose S x 4 exchange words are in flight together when the keys are split */
-#endif      /* words per CTA in the head exchange (one sector) */
 
 __device__ __forceinline__ void sr_csync() { asm volatile("bar.sync 1, %0;" ::"n"(SR_THREADS) : "memory"); }
 __device__ __forceinline__ void sr_mma(float (&c)[4], const uint4 a, const uint2 b) {
@@ -88,7 +87,7 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
 
     if (tid == 0) {
         for (int i = 0; i < nslot; i++) { sr_mbar_init(bar_full + 8 * i, 1); sr_mbar_init(bar_empty + 8 * i, SR_WARPS); }
-        sm_ctl[0] = 0; sm_ctl[1] = 0; sm_ctl[2] = 0;
+        sm_ctl[0] = 0; sm_ctl[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int e = tid; e < H; e += blockDim.x) sm_x[e] = p.x_io[e];
