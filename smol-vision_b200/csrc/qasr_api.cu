@@ -622,8 +622,9 @@ int qasr_cuda_mel(qasr_ctx_t *c, const float *samples, int n_samples, float *mel
 
 // ------------------------------------------------------------------ encoder
 int gemm(qasr_ctx_t *c, const bf16_t *a_hi, const bf16_t *a_lo, int M, int K, const bf16_t *W, int N, int mode,
-                float *of, bf16_t *ohi, bf16_t *olo, const float *bias, int ldo) {
+                float *of, bf16_t *ohi, bf16_t *olo, const float *bias, int ldo, const GemmEpilogue *norm) {
     GemmEpilogue e;
+    if (norm) { e = *norm; if (c->nsplit != 2) e.nx_lo = nullptr; }
     e.mode = mode; e.out_f32 = of; e.out_hi = ohi; e.out_lo = (c->nsplit == 2) ? olo : nullptr; e.bias = bias; e.ldo = ldo;
     if (launch_gemm_tc(c->stream, a_hi, c->nsplit == 2 ? a_lo : nullptr, M, K, W, N, e) != 0)
         return set_err(QASR_ERR_CUDA, "%s", gemm_tc_error());
@@ -801,9 +802,11 @@ static int prefill_device(qasr_ctx_t *c, int P, int kv_len) {
     size_t off = align_up((size_t)P * H * 4, 256);
     auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
     const size_t o_xn = carve((size_t)P * H * 4), o_qkv = carve((size_t)P * 4096 * 4), o_q = carve((size_t)P * 2048 * 4),
-                 o_att = carve((size_t)P * 2048 * 4), o_act = carve((size_t)P * I * 4);
+                 o_att = carve((size_t)P * 2048 * 4), o_act = carve((size_t)P * I * 4), o_ssq = carve((size_t)P * (H >> 7) * 4);
     if (off > c->ws_pre.cap) return set_err(QASR_ERR_STATE, "prefill workspace not reserved");
     float *x = reinterpret_cast<float *>(B);
+    float *ssq = reinterpret_cast<float *>(B + o_ssq); // [P][H / 128] sums of squares of the fused RMSNorms
+    const bool fuse = gemm_tc_can_fuse_norm(P, 2048, H) && gemm_tc_can_fuse_norm(P, I, H);
     bf16_t *xn_hi = reinterpret_cast<bf16_t *>(B + o_xn), *xn_lo = xn_hi + (size_t)P * H;
     float *qkv = reinterpret_cast<float *>(B + o_qkv), *q = reinterpret_cast<float *>(B + o_q);
     bf16_t *at_hi = reinterpret_cast<bf16_t *>(B + o_att), *at_lo = at_hi + (size_t)P * 2048;
@@ -821,15 +824,23 @@ static int prefill_device(qasr_ctx_t *c, int P, int kv_len) {
     for (int l = 0; l < c->dec_layers; l++) {
         const DecLayerW &L = c->dec[l];
         float *kc = c->kv_k + (size_t)l * c->kv_max * kvd, *vc = c->kv_v + (size_t)l * c->kv_max * kvd;
-        if (!(ablate & 1)) launch_rmsnorm(s, x, L.in_norm, 1e-6f, P, H, nullptr, xn_hi, two ? xn_lo : nullptr);
-        if (!(ablate & 8)) CKR(gemm(c, xn_hi, xn_lo, P, H, L.wqkv, 4096, QASR_GEMM_F32, qkv, nullptr, nullptr, nullptr, 4096));
+        // RMSNorm: a stand-alone launch (layer 0, long prompts, ablation runs), or fused across the GEMMs on both sides of it: the
+        // producer of x writes the planes of x * gamma and per-tile sums of squares, the consumer scales its rows (GemmEpilogue::nx_*)
+        GemmEpilogue from_x, to_post, to_next; // consumer side of both norms; producer side of the post-attention / next input norm
+        from_x.in_ssq = ssq; from_x.in_tiles = H >> 7; from_x.in_eps = 1e-6f;
+        to_post.nx_gamma = L.post_norm; to_post.nx_hi = xn_hi; to_post.nx_lo = xn_lo; to_post.nx_ssq = ssq;
+        to_next = to_post;
+        to_next.nx_gamma = l + 1 < c->dec_layers ? c->dec[l + 1].in_norm : nullptr;
+        const bool next_fused = fuse && to_next.nx_gamma;
+        if (!(ablate & 1) && !(fuse && l > 0)) launch_rmsnorm(s, x, L.in_norm, 1e-6f, P, H, nullptr, xn_hi, two ? xn_lo : nullptr);
+        if (!(ablate & 8)) CKR(gemm(c, xn_hi, xn_lo, P, H, L.wqkv, 4096, QASR_GEMM_F32, qkv, nullptr, nullptr, nullptr, 4096, fuse && l > 0 ? &from_x : nullptr));
         if (!(ablate & 2)) launch_qk_norm_rope_store(s, qkv, L.qn, L.kn, c->rope_cos, c->rope_sin, kv_len, P, 1e-6f, q, kc, vc);
         if (!(ablate & 4)) launch_attn_prefill(s, q, kc, vc, kv_len, P, kv_len + P, c->heads, c->kv_heads, scale, nullptr, at_hi, two ? at_lo : nullptr);
-        if (!(ablate & 16)) CKR(gemm(c, at_hi, at_lo, P, 2048, L.wo, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H));
-        if (!(ablate & 1)) launch_rmsnorm(s, x, L.post_norm, 1e-6f, P, H, nullptr, xn_hi, two ? xn_lo : nullptr);
-        if (!(ablate & 32)) CKR(gemm(c, xn_hi, xn_lo, P, H, L.wgu, 2 * I, QASR_GEMM_SWIGLU_SPLIT, nullptr, ac_hi, ac_lo, nullptr, I));
-        if (!(ablate & 64)) CKR(gemm(c, ac_hi, ac_lo, P, I, L.wdown, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H));
-        c->launches += 4;
+        if (!(ablate & 16)) CKR(gemm(c, at_hi, at_lo, P, 2048, L.wo, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H, fuse ? &to_post : nullptr));
+        if (!(ablate & 1) && !fuse) launch_rmsnorm(s, x, L.post_norm, 1e-6f, P, H, nullptr, xn_hi, two ? xn_lo : nullptr);
+        if (!(ablate & 32)) CKR(gemm(c, xn_hi, xn_lo, P, H, L.wgu, 2 * I, QASR_GEMM_SWIGLU_SPLIT, nullptr, ac_hi, ac_lo, nullptr, I, fuse ? &from_x : nullptr));
+        if (!(ablate & 64)) CKR(gemm(c, ac_hi, ac_lo, P, I, L.wdown, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H, next_fused ? &to_next : nullptr));
+        c->launches += fuse ? (l > 0 ? 2 : 3) : 4;
     }
     return 0;
     };
@@ -844,7 +855,8 @@ static int prefill_device(qasr_ctx_t *c, int P, int kv_len) {
 
 static int reserve_prefill(qasr_ctx_t *c, int P) {
     const size_t H = c->H, I = c->I, p = P;
-    size_t bytes = align_up(p * H * 4, 256) * 2 + align_up(p * 4096 * 4, 256) + align_up(p * 2048 * 4, 256) * 2 + align_up(p * I * 4, 256);
+    size_t bytes = align_up(p * H * 4, 256) * 2 + align_up(p * 4096 * 4, 256) + align_up(p * 2048 * 4, 256) * 2 + align_up(p * I * 4, 256) +
+                   align_up(p * (H >> 7) * 4, 256);
     if (c->ws_pre.reserve(bytes)) return set_err(QASR_ERR_NOMEM, "prefill workspace (%zu bytes)", bytes);
     return 0;
 }

@@ -101,8 +101,15 @@ static int enqueue_batch_step(qasr_ctx_t *c, BatchState *b, int B, float *xb, ui
     const bool two = c->nsplit == 2;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 256); return o; };
-    const size_t o_xn = carve((size_t)B * H * 4), o_qkv = carve((size_t)B * 4096 * 4), o_att = carve((size_t)B * 2048 * 4), o_act = carve((size_t)B * I * 4);
+    const size_t o_xn = carve((size_t)B * H * 4), o_qkv = carve((size_t)B * 4096 * 4), o_att = carve((size_t)B * 2048 * 4), o_act = carve((size_t)B * I * 4),
+                 o_ssq = carve((size_t)B * (H >> 7) * 4);
     bf16_t *xn_hi = reinterpret_cast<bf16_t *>(W + o_xn), *xn_lo = xn_hi + (size_t)B * H;
+    // RMSNorms fused across the GEMMs around them (GemmEpilogue::nx_* / in_ssq, qasr_internal.h): only the first norm of a step is a launch
+    float *ssq = reinterpret_cast<float *>(W + o_ssq);
+    const bool fuse = gemm_tc_can_fuse_norm(B, 2048, H) && gemm_tc_can_fuse_norm(B, I, H);
+    GemmEpilogue from_x, to_x;
+    from_x.in_ssq = ssq; from_x.in_tiles = H >> 7; from_x.in_eps = 1e-6f;
+    to_x.nx_hi = xn_hi; to_x.nx_lo = xn_lo; to_x.nx_ssq = ssq;
     float *qkv = reinterpret_cast<float *>(W + o_qkv);
     bf16_t *at_hi = reinterpret_cast<bf16_t *>(W + o_att), *at_lo = at_hi + (size_t)B * 2048;
     bf16_t *ac_hi = reinterpret_cast<bf16_t *>(W + o_act), *ac_lo = ac_hi + (size_t)B * I;
@@ -110,26 +117,29 @@ static int enqueue_batch_step(qasr_ctx_t *c, BatchState *b, int B, float *xb, ui
     for (int l = 0; l < c->dec_layers; l++) { // reference qwen_asr_decoder.c:632-678, B rows at a time
         const DecLayerW &L = c->dec[l];
         float *kl = b->kv_k.as<float>() + (size_t)l * layer_stride, *vl = b->kv_v.as<float>() + (size_t)l * layer_stride;
-        launch_rmsnorm(s, xb, L.in_norm, 1e-6f, B, H, nullptr, xn_hi, two ? xn_lo : nullptr);
-        CKR(gemm(c, xn_hi, xn_lo, B, H, L.wqkv, 4096, QASR_GEMM_F32, qkv, nullptr, nullptr, nullptr, 4096));
+        const bool in_fused = fuse && l > 0;
+        if (!in_fused) launch_rmsnorm(s, xb, L.in_norm, 1e-6f, B, H, nullptr, xn_hi, two ? xn_lo : nullptr);
+        CKR(gemm(c, xn_hi, xn_lo, B, H, L.wqkv, 4096, QASR_GEMM_F32, qkv, nullptr, nullptr, nullptr, 4096, in_fused ? &from_x : nullptr));
         launch_attn_decode_batch(s, qkv, L.qn, L.kn, c->rope_cos, c->rope_sin, kl, vl, unit_stride, head_stride, b->d_pos, B, 1e-6f, scale, at_hi, two ? at_lo : nullptr);
-        CKR(gemm(c, at_hi, at_lo, B, 2048, L.wo, H, QASR_GEMM_RESIDUAL, xb, nullptr, nullptr, nullptr, H));
-        launch_rmsnorm(s, xb, L.post_norm, 1e-6f, B, H, nullptr, xn_hi, two ? xn_lo : nullptr);
-        CKR(gemm(c, xn_hi, xn_lo, B, H, L.wgu, 2 * I, QASR_GEMM_SWIGLU_SPLIT, nullptr, ac_hi, ac_lo, nullptr, I));
-        CKR(gemm(c, ac_hi, ac_lo, B, I, L.wdown, H, QASR_GEMM_RESIDUAL, xb, nullptr, nullptr, nullptr, H));
-        c->launches += 3;
+        to_x.nx_gamma = L.post_norm;
+        CKR(gemm(c, at_hi, at_lo, B, 2048, L.wo, H, QASR_GEMM_RESIDUAL, xb, nullptr, nullptr, nullptr, H, fuse ? &to_x : nullptr));
+        if (!fuse) launch_rmsnorm(s, xb, L.post_norm, 1e-6f, B, H, nullptr, xn_hi, two ? xn_lo : nullptr);
+        CKR(gemm(c, xn_hi, xn_lo, B, H, L.wgu, 2 * I, QASR_GEMM_SWIGLU_SPLIT, nullptr, ac_hi, ac_lo, nullptr, I, fuse ? &from_x : nullptr));
+        to_x.nx_gamma = l + 1 < c->dec_layers ? c->dec[l + 1].in_norm : c->final_norm; // the norm that reads x next
+        CKR(gemm(c, ac_hi, ac_lo, B, I, L.wdown, H, QASR_GEMM_RESIDUAL, xb, nullptr, nullptr, nullptr, H, fuse ? &to_x : nullptr));
+        c->launches += 1 + (in_fused ? 0 : 1) + (fuse ? 0 : 1);
     }
     // head: final RMSNorm -> tied lm_head (reference qwen_asr_decoder.c:683-684) -> argmax -> next input row
-    launch_rmsnorm(s, xb, c->final_norm, 1e-6f, B, H, nullptr, xn_hi, two ? xn_lo : nullptr);
-    CKR(gemm(c, xn_hi, xn_lo, B, H, c->emb, c->V, QASR_GEMM_F32, b->logits.as<float>(), nullptr, nullptr, nullptr, c->V));
+    if (!fuse) launch_rmsnorm(s, xb, c->final_norm, 1e-6f, B, H, nullptr, xn_hi, two ? xn_lo : nullptr);
+    CKR(gemm(c, xn_hi, xn_lo, B, H, c->emb, c->V, QASR_GEMM_F32, b->logits.as<float>(), nullptr, nullptr, nullptr, c->V, fuse ? &from_x : nullptr));
     launch_argmax_next(s, b->logits.as<float>(), c->V, c->emb, H, xb, b->d_pos, b->d_step, b->d_tokens, b->dh_tokens, B, BatchState::STEP_CHUNK);
-    c->launches += 3;
+    c->launches += fuse ? 2 : 3;
     return 0;
 }
 
 static size_t step_ws_bytes(const qasr_ctx_t *c, int B) {
     const size_t H = c->H, I = c->I, b = B;
-    return align_up(b * H * 4, 256) + align_up(b * 4096 * 4, 256) + align_up(b * 2048 * 4, 256) + align_up(b * I * 4, 256);
+    return align_up(b * H * 4, 256) + align_up(b * 4096 * 4, 256) + align_up(b * 2048 * 4, 256) + align_up(b * I * 4, 256) + align_up(b * (H >> 7) * 4, 256);
 }
 
 static int run_group(qasr_ctx_t *c, BatchState *b, const float *const *samples, const int *n_samples, int B, const int *max_new, int ids_stride,

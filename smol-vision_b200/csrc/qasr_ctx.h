@@ -170,7 +170,7 @@ static inline int run_cached_graph(qasr_ctx_t *c, long long k0, long long k1, lo
 int encode_units_device(qasr_ctx_t *c, const float *d_mel, int mel_stride, const int *unit_frames, int n_units, float *out, int *T_out);
 int ensure_rope(qasr_ctx_t *c, int need_pos);
 int gemm(qasr_ctx_t *c, const bf16_t *a_hi, const bf16_t *a_lo, int M, int K, const bf16_t *W, int N, int mode, float *of, bf16_t *ohi,
-         bf16_t *olo, const float *bias, int ldo);
+         bf16_t *olo, const float *bias, int ldo, const GemmEpilogue *norm = nullptr); // norm: nx_* / in_* fields of a fused RMSNorm (qasr_internal.h)
 // batched path (qasr_batch.cu): independent units through batched front end / encoder / prefill / decode
 int batch_transcribe(qasr_ctx_t *c, const float *const *samples, const int *n_samples, int count, const int *max_new, int ids_stride,
                      int *out_ids, int *out_n, double *timings_ms);

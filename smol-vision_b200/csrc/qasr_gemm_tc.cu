@@ -653,7 +653,30 @@ __device__ __forceinline__ void sk_epilogue_store(const SkParams &p, int n, int 
 
 // epilogue of 4 consecutive reduced outputs (row m, columns nb..nb+3) of a split-K tile
 template <int MP>
-__device__ __forceinline__ void sk_reduced_store(const SkParams &p, int nb, int m, const float4 v) {
+__device__ __forceinline__ void sk_reduced_store(const SkParams &p, int nb, int m, float4 v, const float *s_scale) {
+    if (p.epi.in_ssq) { const float sc = s_scale[m]; v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc; } // RMSNorm scalar of the input row
+    if (p.epi.nx_hi) {
+        // residual stream + the operand planes and sum of squares of the RMSNorm that follows (a warp = one row m, its 32 lanes =
+        // the 128 columns of this tile; N % 128 == 0 and ldo % 4 == 0 are checked on the host)
+        const GemmEpilogue &e = p.epi;
+        float4 x = *reinterpret_cast<const float4 *>(e.out_f32 + (size_t)m * e.ldo + nb);
+        if (e.bias) { const float4 b4 = *reinterpret_cast<const float4 *>(e.bias + nb); v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w; }
+        x.x += v.x; x.y += v.y; x.z += v.z; x.w += v.w;
+        *reinterpret_cast<float4 *>(e.out_f32 + (size_t)m * e.ldo + nb) = x;
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(e.nx_gamma + nb));
+        float r0, r1, r2, r3;
+        uint2 hi, lo;
+        hi.x = pack_hi2(x.x * g.x, x.y * g.y, r0, r1);
+        hi.y = pack_hi2(x.z * g.z, x.w * g.w, r2, r3);
+        *reinterpret_cast<uint2 *>(e.nx_hi + (size_t)m * p.N + nb) = hi;
+        if (e.nx_lo) {
+            lo.x = pack_bf2(r0, r1); lo.y = pack_bf2(r2, r3);
+            *reinterpret_cast<uint2 *>(e.nx_lo + (size_t)m * p.N + nb) = lo;
+        }
+        const float ss = warp_sum(fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, x.w * x.w))));
+        if ((threadIdx.x & 31) == 0) e.nx_ssq[(size_t)m * (p.N >> 7) + (nb >> 7)] = ss;
+        return;
+    }
     if (p.epi.mode == QASR_GEMM_SWIGLU_SPLIT) { // (gate, up) pairs sit inside the float4
         const GemmEpilogue &e = p.epi;
         const float r[2] = {silu_fast(v.x) * v.y, silu_fast(v.z) * v.w};
@@ -701,6 +724,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     uint64_t *tmem_full_bar = empty_bar + STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full_bar + 1);
     int *s_last = reinterpret_cast<int *>(tmem_slot + 1);
+    float *s_scale = reinterpret_cast<float *>(s_last + 1); // [256] RMSNorm scalars of the input rows (epi.in_ssq)
 
     pdl_trigger(); // the next grid of the chain may be scheduled right away (it waits for this one where it must)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -784,6 +808,15 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
     } else if (warp < 2 + SkWarps<MP>::EPW) {
         // ===== epilogue warps: thread <-> weight row n (TMEM lane quarter warp % 4), activation rows m of this warp's column block
         constexpr int CW = SkWarps<MP>::CW;
+        if (p.epi.in_ssq) { // row scalars of the fused RMSNorm, computed while the mainloop runs (reference qwen_asr_kernels.c:801-860)
+            for (int m = (int)threadIdx.x - 64; m < MP; m += SkWarps<MP>::EPW * 32) {
+                float t = 0.0f;
+                if (m < p.M)
+                    for (int i = 0; i < p.epi.in_tiles; i++) t += p.epi.in_ssq[(size_t)m * p.epi.in_tiles + i];
+                s_scale[m] = m < p.M ? 1.0f / sqrtf(t / (float)p.K + p.epi.in_eps) : 0.0f;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(SkWarps<MP>::EPW * 32) : "memory");
+        }
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int q = warp & 3, nl = q * 32 + lane, n = n0 + nl, cb = (warp - 2) >> 2;
@@ -801,6 +834,10 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
                 for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
             }
             if (p.S == 1) {
+                if (p.epi.in_ssq) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) r[j] = __float_as_uint(__uint_as_float(r[j]) * s_scale[c0 + j]);
+                }
 #pragma unroll
                 for (int j = 0; j < 32; j++) sk_epilogue_store<MP>(p, n, c0 + j, __uint_as_float(r[j]), lane);
             } else {
@@ -838,7 +875,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
 #pragma unroll
             for (int sp = 0; sp < 8; sp++)
                 if (sp < p.S) { v.x += t[sp].x; v.y += t[sp].y; v.z += t[sp].z; v.w += t[sp].w; }
-            sk_reduced_store<MP>(p, n0 + c4 * 4, m, v);
+            sk_reduced_store<MP>(p, n0 + c4 * 4, m, v, s_scale);
         }
         // nobody leaves while a peer may still read its shared memory
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -876,7 +913,7 @@ gemm_tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_cons
         for (int u = 0; u < 4; u++) {
         const int idx = base + u * SkWarps<MP>::THREADS + threadIdx.x;
         if (idx >= p.M * 32) continue;
-        sk_reduced_store<MP>(p, n0 + (idx & 31) * 4, idx >> 5, acc4[u]);
+        sk_reduced_store<MP>(p, n0 + (idx & 31) * 4, idx >> 5, acc4[u], s_scale);
         }
     }
 }
@@ -896,7 +933,7 @@ static constexpr size_t tc2_smem_bytes() { return (size_t)TC2_STAGES * (2 * TC_B
 
 template <int MP, int STAGES>
 static constexpr size_t sk_smem_bytes() {
-    return (size_t)STAGES * (128 * TC_BK * 2 + 2 * MP * TC_BK * 2) + 256 + 1024;
+    return (size_t)STAGES * (128 * TC_BK * 2 + 2 * MP * TC_BK * 2) + 256 + 1024 + 1024; // stages | barriers | row scalars | alignment
 }
 
 struct SkScratch { float *ws = nullptr; size_t ws_bytes = 0; unsigned *tickets = nullptr; };
@@ -1026,16 +1063,42 @@ extern "C" int qasr_debug_gemm_plan(int M, int K, int N, int *out) {
     return 0;
 }
 
+static int skinny_max_m_cfg() { // QASR_GEMM_SKINNY_MAX_M: largest M that takes the skinny kernel (experiments; default 256)
+    static int v = -1;
+    if (v < 0) { const char *ev = getenv("QASR_GEMM_SKINNY_MAX_M"); v = ev ? atoi(ev) : 256; if (v > 256) v = 256; }
+    return v;
+}
+// Fused RMSNorm (GemmEpilogue::nx_* / in_ssq) lives in the skinny kernel: the producer needs the split-K reduction path (a warp = one
+// row of the tile) and whole 128-column tiles, the consumer only the skinny kernel.  QASR_GEMM_FUSE_NORM=0 switches it off (A/B runs).
+static bool fuse_norm_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *ev = getenv("QASR_GEMM_FUSE_NORM"); v = !(ev && ev[0] == '0'); }
+    return v != 0;
+}
+bool gemm_tc_can_scale_rows(int M) { return fuse_norm_enabled() && M > 0 && M <= skinny_max_m_cfg(); }
+bool gemm_tc_can_fuse_norm(int M, int K, int N) {
+    if (!gemm_tc_can_scale_rows(M) || K <= 0 || N <= 0 || (N & 127)) return false;
+    return sk_plan(M, K, N).S > 1;
+}
+
 int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M, int K, const bf16_t *W, int N,
                    const GemmEpilogue &epi) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     if (gemm_tc_init() != 0) return -1;
+    if (epi.nx_hi && (epi.mode != QASR_GEMM_RESIDUAL || !epi.nx_gamma || !epi.nx_ssq || (epi.ldo & 3) || ((uintptr_t)epi.out_f32 & 15) ||
+                      ((uintptr_t)epi.nx_hi & 7) || ((uintptr_t)epi.nx_lo & 7) || !gemm_tc_can_fuse_norm(M, K, N))) {
+        snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: fused norm output needs a RESIDUAL skinny split-K GEMM with N %% 128 == 0 (M=%d K=%d N=%d)", M, K, N);
+        return -1;
+    }
+    if (epi.in_ssq && (!gemm_tc_can_scale_rows(M) || epi.in_tiles <= 0)) {
+        snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: row scalars need the skinny kernel (M=%d)", M);
+        return -1;
+    }
     if ((K & 7) || ((uintptr_t)A_hi & 15) || ((uintptr_t)W & 15) || (A_lo && ((uintptr_t)A_lo & 15))) {
         snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: K must be a multiple of 8 and operands 16-byte aligned (K=%d)", K);
         return -1;
     }
-    static int skinny_max_m = -1; // QASR_GEMM_SKINNY_MAX_M: largest M that takes the skinny kernel (experiments; default 256)
-    if (skinny_max_m < 0) { const char *ev = getenv("QASR_GEMM_SKINNY_MAX_M"); skinny_max_m = ev ? atoi(ev) : 256; if (skinny_max_m > 256) skinny_max_m = 256; }
+    const int skinny_max_m = skinny_max_m_cfg();
     if (M <= skinny_max_m) { // weight-streaming regime: skinny-M kernel with split-K over ~148 CTAs
         int dev = 0;
         cudaGetDevice(&dev);

@@ -74,6 +74,16 @@ struct GemmEpilogue {
     bf16_t *out_lo;    // may be NULL (nsplit == 1)
     const float *bias; // [N] or NULL
     int ldo;           // leading dimension of the output (N, or N/2 for SWIGLU)
+    // RMSNorm fused across two GEMMs (skinny kernel only, gemm_tc_can_fuse_norm): the scalar 1/sqrt(mean x^2 + eps) of a row commutes
+    // with the product, so the PRODUCER of the residual stream (mode RESIDUAL) also writes the next GEMM's operand planes hi/lo of
+    // x * gamma and the sum of x^2 over its 128 columns of every row; the CONSUMER multiplies row m of its accumulator by
+    // rsqrt(sum_t in_ssq[m][t] / K + eps) before anything else.  Reference: qwen_rms_norm, qwen_asr_kernels.c:801-860.
+    const float *nx_gamma = nullptr; // producer: [N] weight of the norm that follows
+    bf16_t *nx_hi = nullptr, *nx_lo = nullptr; // producer: planes [M, N] (lo may be NULL)
+    float *nx_ssq = nullptr;         // producer: [M][N / 128] partial sums of squares
+    const float *in_ssq = nullptr;   // consumer: [M][in_tiles] partial sums written by the producer of its input
+    int in_tiles = 0;
+    float in_eps = 0.0f;
 };
 
 // ---- decode-step kernels (qasr_decode.cu)
@@ -199,6 +209,8 @@ int gemm_tc_init(void); // resolves cuTensorMapEncodeTiled, sets smem attributes
 int gemm_tc_prepare(void); // per-device split-K scratch (call once per device, outside stream capture)
 int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M, int K, const bf16_t *W, int N,
                    const GemmEpilogue &epi);
+bool gemm_tc_can_fuse_norm(int M, int K, int N); // a RESIDUAL GEMM of this shape can carry nx_* (skinny kernel, split-K reduction path)
+bool gemm_tc_can_scale_rows(int M);              // a GEMM with M rows can carry in_ssq (skinny kernel)
 const char *gemm_tc_error(void);
 // conv stem stage 2 / 3 as an implicit GEMM: the 3 x 3 patches are gathered into the operand stage by the kernel itself
 int launch_conv_gemm_tc(cudaStream_t s, const bf16_t *src_hi, const bf16_t *src_lo, const ConvGeom &g, int stage, const bf16_t *W,

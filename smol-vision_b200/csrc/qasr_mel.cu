@@ -47,6 +47,7 @@ mel_pass1_kernel(const float *__restrict__ samples, int n, int frames, const flo
         float re[MEL_FPB], im[MEL_FPB];
 #pragma unroll
         for (int f = 0; f < MEL_FPB; f++) re[f] = im[f] = 0.0f;
+#pragma unroll 8 // the 16 table loads of 8 iterations are issued together: the loop was bound by one L2 round trip per iteration
         for (int j = 0; j < MEL_NFFT; j++) {
             const float c = ct[j * MEL_TSTRIDE + tid], s = st[j * MEL_TSTRIDE + tid];
 #pragma unroll
@@ -62,6 +63,7 @@ mel_pass1_kernel(const float *__restrict__ samples, int n, int frames, const flo
     __syncthreads();
     const int m = tid & 127, fg = tid >> 7; // 2 groups x 4 frames
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
     for (int k = 0; k < MEL_NFREQ; k++) {
         const float w = fb[k * 128 + m];
 #pragma unroll

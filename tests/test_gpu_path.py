@@ -354,3 +354,48 @@ def test_encoder_tables_cached_per_length(gpu06, pkg):
     ea = gpu06.encode(gpu06.mel(a))
     gpu06.encode(gpu06.mel(b))
     assert np.array_equal(ea, gpu06.encode(gpu06.mel(a)))
+
+
+_FUSE_CHILD = r"""
+import sys, json
+import numpy as np
+sys.path.insert(0, {root!r})
+import __graft_entry__ as ge
+pkg = ge.load_package()
+out = {{}}
+for variant, secs in (("0.6b", (1.3, 3.64, 2.2, 0.9, 5.0, 1.7)), ("1.7b", (3.64, 1.3, 2.6))):
+    eng = pkg.QasrCuda(0).load(pkg.ensure_model_dir(variant))
+    units = [pkg.synth_audio(s, seed=700 + i) for i, s in enumerate(secs)]
+    ids, info = eng.transcribe_ids(units[0], 12)            # prefill chain with P <= 256 rows: norms fused into WO / down / QKV / gate-up
+    P = int(info["enc_tokens"]) + 14
+    k, v = eng.read_kv(27, P)
+    got, _ = eng.transcribe_batch(units, [10] * len(units))  # batched decode steps: every norm but the first of a step is fused
+    out[variant] = dict(ids=ids.tolist(), k=np.asarray(k, np.float64).ravel()[::37].tolist(), v=np.asarray(v, np.float64).ravel()[::41].tolist(),
+                        batch=[g.tolist() for g in got], launches=int(eng.launch_count))
+    eng.close()
+print("OUT " + json.dumps(out))
+"""
+
+
+@pytest.mark.gpu
+def test_fused_rmsnorm_equals_standalone_norm(pkg):
+    """RMSNorm fused across the skinny GEMMs (producer writes x * gamma planes + per-tile sums of squares, consumer scales its rows;
+    GemmEpilogue::nx_* / in_ssq, reference qwen_rms_norm qwen_asr_kernels.c:801-860) against the stand-alone rmsnorm_rows_kernel
+    (QASR_GEMM_FUSE_NORM=0): same greedy ids on the single and the batched path, KV rows of the last layer equal to 1e-4 (the hi/lo split rounds x * gamma instead of x * gamma * s),
+    and fewer launches.  The switch is read once per process, hence child processes; ids vs the CPU reference are covered by the other tests
+    (which run the fused default)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for fuse in ("1", "0"):
+        env = dict(os.environ, QASR_GEMM_FUSE_NORM=fuse, QASR_BATCH="gemm")
+        r = subprocess.run([sys.executable, "-c", _FUSE_CHILD.format(root=root)], env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[fuse] = json.loads([l for l in r.stdout.splitlines() if l.startswith("OUT ")][-1][4:])
+    for variant in ("0.6b", "1.7b"):
+        a, b = res["1"][variant], res["0"][variant]
+        assert a["ids"] == b["ids"] and a["batch"] == b["batch"], variant
+        for key in ("k", "v"):
+            x, y = np.asarray(a[key]), np.asarray(b[key])
+            assert np.abs(x - y).max() <= 1e-4 * np.abs(y).max(), (variant, key, float(np.abs(x - y).max()), float(np.abs(y).max()))
+        assert a["launches"] < b["launches"], variant
