@@ -807,6 +807,7 @@ static int prefill_device(qasr_ctx_t *c, int P, int kv_len) {
     float *x = reinterpret_cast<float *>(B);
     float *ssq = reinterpret_cast<float *>(B + o_ssq); // [P][H / 128] sums of squares of the fused RMSNorms
     const bool fuse = gemm_tc_can_fuse_norm(P, 2048, H) && gemm_tc_can_fuse_norm(P, I, H);
+    const bool fuse_qk = gemm_tc_can_fuse_qk(P, H); // q/k-norm + RoPE + KV store in the QKV epilogue (GemmEpilogue::qk_*)
     bf16_t *xn_hi = reinterpret_cast<bf16_t *>(B + o_xn), *xn_lo = xn_hi + (size_t)P * H;
     float *qkv = reinterpret_cast<float *>(B + o_qkv), *q = reinterpret_cast<float *>(B + o_q);
     bf16_t *at_hi = reinterpret_cast<bf16_t *>(B + o_att), *at_lo = at_hi + (size_t)P * 2048;
@@ -833,14 +834,20 @@ static int prefill_device(qasr_ctx_t *c, int P, int kv_len) {
         to_next.nx_gamma = l + 1 < c->dec_layers ? c->dec[l + 1].in_norm : nullptr;
         const bool next_fused = fuse && to_next.nx_gamma;
         if (!(ablate & 1) && !(fuse && l > 0)) launch_rmsnorm(s, x, L.in_norm, 1e-6f, P, H, nullptr, xn_hi, two ? xn_lo : nullptr);
-        if (!(ablate & 8)) CKR(gemm(c, xn_hi, xn_lo, P, H, L.wqkv, 4096, QASR_GEMM_F32, qkv, nullptr, nullptr, nullptr, 4096, fuse && l > 0 ? &from_x : nullptr));
-        if (!(ablate & 2)) launch_qk_norm_rope_store(s, qkv, L.qn, L.kn, c->rope_cos, c->rope_sin, kv_len, P, 1e-6f, q, kc, vc);
+        GemmEpilogue qkv_epi; // consumer side of the input norm (layers > 0) + q/k-norm, RoPE and the KV store of this layer
+        if (fuse && l > 0) qkv_epi = from_x;
+        if (fuse_qk) {
+            qkv_epi.qk_q = q; qkv_epi.qk_kc = kc; qkv_epi.qk_vc = vc; qkv_epi.qk_qn = L.qn; qkv_epi.qk_kn = L.kn;
+            qkv_epi.qk_cos = c->rope_cos; qkv_epi.qk_sin = c->rope_sin; qkv_epi.qk_pos0 = kv_len; qkv_epi.qk_eps = 1e-6f;
+        }
+        if (!(ablate & 8)) CKR(gemm(c, xn_hi, xn_lo, P, H, L.wqkv, 4096, QASR_GEMM_F32, qkv, nullptr, nullptr, nullptr, 4096, &qkv_epi));
+        if (!(ablate & 2) && !fuse_qk) launch_qk_norm_rope_store(s, qkv, L.qn, L.kn, c->rope_cos, c->rope_sin, kv_len, P, 1e-6f, q, kc, vc);
         if (!(ablate & 4)) launch_attn_prefill(s, q, kc, vc, kv_len, P, kv_len + P, c->heads, c->kv_heads, scale, nullptr, at_hi, two ? at_lo : nullptr);
         if (!(ablate & 16)) CKR(gemm(c, at_hi, at_lo, P, 2048, L.wo, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H, fuse ? &to_post : nullptr));
         if (!(ablate & 1) && !fuse) launch_rmsnorm(s, x, L.post_norm, 1e-6f, P, H, nullptr, xn_hi, two ? xn_lo : nullptr);
         if (!(ablate & 32)) CKR(gemm(c, xn_hi, xn_lo, P, H, L.wgu, 2 * I, QASR_GEMM_SWIGLU_SPLIT, nullptr, ac_hi, ac_lo, nullptr, I, fuse ? &from_x : nullptr));
         if (!(ablate & 64)) CKR(gemm(c, ac_hi, ac_lo, P, I, L.wdown, H, QASR_GEMM_RESIDUAL, x, nullptr, nullptr, nullptr, H, next_fused ? &to_next : nullptr));
-        c->launches += fuse ? (l > 0 ? 2 : 3) : 4;
+        c->launches += (fuse ? (l > 0 ? 2 : 3) : 4) - (fuse_qk ? 1 : 0);
     }
     return 0;
     };

@@ -677,6 +677,28 @@ __device__ __forceinline__ void sk_reduced_store(const SkParams &p, int nb, int 
         if ((threadIdx.x & 31) == 0) e.nx_ssq[(size_t)m * (p.N >> 7) + (nb >> 7)] = ss;
         return;
     }
+    if (p.epi.qk_q) {
+        // QKV row m, head slot nb / 128 (16 q | 8 k | 8 v): this warp holds the head's 128 values, lane l dims 4l .. 4l+3; dims d and
+        // d +- 64 of the split-half RoPE sit in lanes l and l ^ 16
+        const GemmEpilogue &e = p.epi;
+        const int slot = nb >> 7, lane = threadIdx.x & 31, pos = e.qk_pos0 + m;
+        if (slot >= 24) { *reinterpret_cast<float4 *>(e.qk_vc + (size_t)pos * 1024 + (nb - 3072)) = v; return; }
+        const float ss = warp_sum(fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w))));
+        const float inv = 1.0f / sqrtf(ss / 128.0f + e.qk_eps);
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(slot < 16 ? e.qk_qn : e.qk_kn) + lane);
+        v.x = v.x * inv * w.x; v.y = v.y * inv * w.y; v.z = v.z * inv * w.z; v.w = v.w * inv * w.w;
+        float4 o;
+        o.x = __shfl_xor_sync(0xffffffffu, v.x, 16); o.y = __shfl_xor_sync(0xffffffffu, v.y, 16);
+        o.z = __shfl_xor_sync(0xffffffffu, v.z, 16); o.w = __shfl_xor_sync(0xffffffffu, v.w, 16);
+        const float4 c = __ldg(reinterpret_cast<const float4 *>(e.qk_cos + (size_t)pos * 64) + (lane & 15));
+        const float4 sn = __ldg(reinterpret_cast<const float4 *>(e.qk_sin + (size_t)pos * 64) + (lane & 15));
+        float4 r;
+        if (lane < 16) { r.x = v.x * c.x - o.x * sn.x; r.y = v.y * c.y - o.y * sn.y; r.z = v.z * c.z - o.z * sn.z; r.w = v.w * c.w - o.w * sn.w; }
+        else { r.x = v.x * c.x + o.x * sn.x; r.y = v.y * c.y + o.y * sn.y; r.z = v.z * c.z + o.z * sn.z; r.w = v.w * c.w + o.w * sn.w; }
+        if (slot < 16) *reinterpret_cast<float4 *>(e.qk_q + (size_t)m * 2048 + nb) = r;
+        else *reinterpret_cast<float4 *>(e.qk_kc + (size_t)pos * 1024 + (nb - 2048)) = r;
+        return;
+    }
     if (p.epi.mode == QASR_GEMM_SWIGLU_SPLIT) { // (gate, up) pairs sit inside the float4
         const GemmEpilogue &e = p.epi;
         const float r[2] = {silu_fast(v.x) * v.y, silu_fast(v.z) * v.w};
@@ -1081,10 +1103,17 @@ bool gemm_tc_can_fuse_norm(int M, int K, int N) {
     return sk_plan(M, K, N).S > 1;
 }
 
+bool gemm_tc_can_fuse_qk(int M, int K) { return gemm_tc_can_fuse_norm(M, K, 4096); }
+
 int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M, int K, const bf16_t *W, int N,
                    const GemmEpilogue &epi) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     if (gemm_tc_init() != 0) return -1;
+    if (epi.qk_q && (epi.mode != QASR_GEMM_F32 || N != 4096 || epi.bias || !epi.qk_kc || !epi.qk_vc || !epi.qk_qn || !epi.qk_kn || !epi.qk_cos ||
+                     !epi.qk_sin || ((uintptr_t)epi.qk_q & 15) || ((uintptr_t)epi.qk_kc & 15) || ((uintptr_t)epi.qk_vc & 15) || !gemm_tc_can_fuse_qk(M, K))) {
+        snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: fused q/k norm + RoPE needs the F32 QKV GEMM (N = 4096) on the skinny split-K path (M=%d K=%d N=%d)", M, K, N);
+        return -1;
+    }
     if (epi.nx_hi && (epi.mode != QASR_GEMM_RESIDUAL || !epi.nx_gamma || !epi.nx_ssq || (epi.ldo & 3) || ((uintptr_t)epi.out_f32 & 15) ||
                       ((uintptr_t)epi.nx_hi & 7) || ((uintptr_t)epi.nx_lo & 7) || !gemm_tc_can_fuse_norm(M, K, N))) {
         snprintf(g_tc_err, sizeof g_tc_err, "gemm_tc: fused norm output needs a RESIDUAL skinny split-K GEMM with N %% 128 == 0 (M=%d K=%d N=%d)", M, K, N);

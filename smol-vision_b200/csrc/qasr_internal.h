@@ -84,6 +84,13 @@ struct GemmEpilogue {
     const float *in_ssq = nullptr;   // consumer: [M][in_tiles] partial sums written by the producer of its input
     int in_tiles = 0;
     float in_eps = 0.0f;
+    // q/k per-head RMSNorm + NeoX RoPE + KV-cache store fused into the QKV GEMM (mode F32, N = 4096 = 16 q | 8 k | 8 v heads of 128,
+    // skinny split-K path: a warp of the reduction holds one head of one row).  Reference qwen_asr_decoder.c:510-524.
+    float *qk_q = nullptr;           // [M][2048] roped queries (replaces out_f32, which is not written)
+    float *qk_kc = nullptr, *qk_vc = nullptr; // this layer's cache rows [pos][1024]
+    const float *qk_qn = nullptr, *qk_kn = nullptr, *qk_cos = nullptr, *qk_sin = nullptr; // norm weights [128], RoPE tables [pos][64]
+    int qk_pos0 = 0;                 // row m sits at position qk_pos0 + m
+    float qk_eps = 0.0f;
 };
 
 // ---- decode-step kernels (qasr_decode.cu)
@@ -211,6 +218,7 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
                    const GemmEpilogue &epi);
 bool gemm_tc_can_fuse_norm(int M, int K, int N); // a RESIDUAL GEMM of this shape can carry nx_* (skinny kernel, split-K reduction path)
 bool gemm_tc_can_scale_rows(int M);              // a GEMM with M rows can carry in_ssq (skinny kernel)
+bool gemm_tc_can_fuse_qk(int M, int K);          // the QKV GEMM (N = 4096) of this shape can carry qk_*
 const char *gemm_tc_error(void);
 // conv stem stage 2 / 3 as an implicit GEMM: the 3 x 3 patches are gathered into the operand stage by the kernel itself
 int launch_conv_gemm_tc(cudaStream_t s, const bf16_t *src_hi, const bf16_t *src_lo, const ConvGeom &g, int stage, const bf16_t *W,

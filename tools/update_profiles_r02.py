@@ -92,6 +92,46 @@ Reading: the single-utterance chains are launch / latency bound (DRAM 8-22 %, 80
 on 32-64 CTAs). The batched GEMMs are tensor-pipe bound (74-92 %). `attn_decode_batch_kernel` streams the f32 KV rows (2.1 TB/s
 at 16 sequences / 128 CTAs, 4.6-5.3 TB/s at 64-128 sequences).
 """
+
+# ---- ncu launch list of the bench workload (2 utterances through the C ABI): shares must agree with the stage times of the bench line
+def launch_list_section(path):
+    import collections, csv, gzip, re
+    if not os.path.exists(path):
+        return ""
+    rows = list(csv.reader(l for l in gzip.open(path, "rt") if l.startswith('"')))
+    ki, vi = rows[0].index("Kernel Name"), rows[0].index("Metric Value")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[1:]:
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        n = re.sub(r"\(.*", "", r[ki]).replace("void ", "")
+        agg[n][0] += 1
+        agg[n][1] += v / 1e3
+    load_only = sum(v[1] for k, v in agg.items() if "sk_retile" in k)  # model load, not part of a step
+    tot = sum(v[1] for v in agg.values()) - load_only
+    t = ("\n## Launch list of the bench workload, round 2 (`r02_launches_default.csv.gz`; cold-cache, serialised: compare SHARES)\n\n"
+         "`ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/profile_utt.py 1.7b 2` after the same command exited 0 without ncu: "
+         f"2 utterances = {tot / 1e3:.2f} ms of serialised kernel time (without the load-time `sk_retile_kernel`, {load_only / 1e3:.2f} ms).\n\n"
+         "| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
+    dec = 0.0
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        if "sk_retile" in k or v[1] / tot < 0.0005:
+            continue
+        if "decode_rounds_kernel" in k or "decode_stream_kernel" in k:
+            dec += v[1]
+        t += f"| `{k}` | {v[0]} | {v[1]:.0f} | {v[1] / v[0]:.1f} | {100 * v[1] / tot:.1f} % |\n"
+    sm = d["stage_ms"]
+    step = sm["mel_ms"] + sm["enc_ms"] + sm["prefill_ms"] + sm["decode_ms"]
+    first = d["roofline"]["ms_per_launch"]  # the first greedy step runs inside the decode kernel but is booked under prefill_ms
+    t += (f"\nThe decode kernel's share of the serialised time is {100 * dec / tot:.1f} %; in the un-profiled bench line its launches take "
+          f"decode_ms + the first greedy step (booked under prefill_ms) = {sm['decode_ms']:.2f} + {first:.2f} of {step:.2f} ms = "
+          f"{100 * (sm['decode_ms'] + first) / step:.1f} %: the shares agree (the cold-cache, serialised list inflates the short encoder / prefill kernels).\n")
+    return t
+
+
+s += launch_list_section(os.path.join(P, "r02_launches_default.csv.gz"))
 readme = open(os.path.join(P, "README.md")).read()
 i = readme.find("\n\n# Round 2")
 open(os.path.join(P, "README.md"), "w").write((readme[:i] if i >= 0 else readme) + s)
