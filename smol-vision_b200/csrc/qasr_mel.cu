@@ -28,6 +28,13 @@ mel_pass1_kernel(const float *__restrict__ samples, int n, int frames, const flo
     __shared__ float pw[MEL_FPB][MEL_NFREQ + 3];
     __shared__ float red[8];
     const int t0 = blockIdx.x * MEL_FPB, tid = threadIdx.x;
+    // The DFT tables (2 x 333 KB) and the filterbank (103 KB) have usually been evicted by the decode weight stream of the previous
+    // utterance; without this every CTA walked them row by row at DRAM latency (~90 us for a 3.6 s utterance).  Pull them into L2 up front.
+    for (int i = tid; i < MEL_NFFT * MEL_TSTRIDE / 32; i += 256) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ct + (size_t)i * 32) : "memory");
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(st + (size_t)i * 32) : "memory");
+    }
+    for (int i = tid; i < MEL_NFREQ * 128 / 32; i += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(fb + (size_t)i * 32) : "memory");
     // windowed frames; padded[i]: i<200 -> x[200-i]; i<200+n -> x[i-200]; else x[n-2-(i-200-n)]  (:301-309)
     for (int e = tid; e < MEL_FPB * MEL_NFFT; e += 256) {
         const int f = e / MEL_NFFT, i = e % MEL_NFFT, t = t0 + f;
