@@ -721,7 +721,7 @@ __device__ __forceinline__ void sk_reduced_store(const SkParams &p, int nb, int 
 // one per scheduler) left a CTA 10-20 us in its epilogue - 128 dependent (ld, SiLU, split, store) sequences per thread with nothing to hide
 // their latency, and the next CTA cannot start before this one leaves (profiles/r02_batched_path.txt: pre.gu 22.5 us with, 12.3 us without the
 // epilogue; contiguous bulk copies of pre-tiled weights, a rotated k order per CTA and a single activation plane all changed nothing).  EPW = 8 (MP = 64) or 16 warps: warp e works on lane quarter e % 4 and the column block e / 4 of the accumulator.
-template <int MP> struct SkWarps { static constexpr int EPW = MP <= 64 ? 8 : 16, CW = MP / (EPW / 4), THREADS = (3 + EPW) * 32; };
+template <int MP> struct SkWarps { static constexpr int EPW = MP <= 32 ? 4 : (MP <= 64 ? 8 : 16), CW = MP / (EPW / 4), THREADS = (3 + EPW) * 32; };
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -986,6 +986,8 @@ int gemm_tc_init(void) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<128>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<256>());
     if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm_tc_skinny_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk_smem_bytes<32, 8>());
+    if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_skinny_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk_smem_bytes<64, 6>());
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_tc_skinny_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk_smem_bytes<128, 4>());
@@ -1064,7 +1066,11 @@ static SkPlan sk_plan(int M, int K, int N) {
         sk_cluster = !(ev && ev[0] == '0');
     }
     SkPlan pl;
-    pl.MP = M <= 64 ? 64 : (M <= 128 ? 128 : 256);
+    static int mp32 = -1; // QASR_GEMM_MP32=0: rows <= 32 take the 64-column instantiation as before (A/B runs)
+    if (mp32 < 0) { const char *e = getenv("QASR_GEMM_MP32"); mp32 = !(e && e[0] == '0'); }
+    // activation columns of the MMA: per k-block a CTA takes in 16 KB of weights + 2 planes x MP x 128 B of activations, and that intake
+    // (~84 GB/s per SM) is what paces the mainloop - up to 32 rows (batched decode on an 8-GPU shard, short prompts, stream deltas) use MP = 32
+    pl.MP = (M <= 32 && mp32) ? 32 : (M <= 64 ? 64 : (M <= 128 ? 128 : 256));
     pl.n_tiles = (N + 127) / 128;
     pl.total_kb = (K + TC_BK - 1) / TC_BK;
     int S = (target_ctas + pl.n_tiles - 1) / pl.n_tiles; // split K until ~target_ctas CTAs stream weights
@@ -1165,7 +1171,8 @@ int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M
             if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(3d) failed (%d) M=%d K=%d", (int)r, M, K); return -1; }
         }
         dim3 grid(n_tiles, S);
-        if (MP == 64) launch_pdl_cluster(gemm_tc_skinny_kernel<64, 6>, grid, SkWarps<64>::THREADS, sk_smem_bytes<64, 6>(), s, sp.cluster ? S : 1, mw, ma, sp);
+        if (MP == 32) launch_pdl_cluster(gemm_tc_skinny_kernel<32, 8>, grid, SkWarps<32>::THREADS, sk_smem_bytes<32, 8>(), s, sp.cluster ? S : 1, mw, ma, sp);
+        else if (MP == 64) launch_pdl_cluster(gemm_tc_skinny_kernel<64, 6>, grid, SkWarps<64>::THREADS, sk_smem_bytes<64, 6>(), s, sp.cluster ? S : 1, mw, ma, sp);
         else if (MP == 128) launch_pdl_cluster(gemm_tc_skinny_kernel<128, 4>, grid, SkWarps<128>::THREADS, sk_smem_bytes<128, 4>(), s, sp.cluster ? S : 1, mw, ma, sp);
         else launch_pdl_cluster(gemm_tc_skinny_kernel<256, 2>, grid, SkWarps<256>::THREADS, sk_smem_bytes<256, 2>(), s, sp.cluster ? S : 1, mw, ma, sp);
         cudaError_t le = cudaGetLastError();

@@ -104,7 +104,8 @@ def test_argmax_ties_and_ragged(gpu06):
 
 
 @pytest.mark.parametrize("M,K,N", [(61, 2048, 4096), (143, 896, 2688), (143, 3584, 896), (404, 1024, 6144),
-                                   (208, 4320, 480), (13, 7680, 896), (1, 1024, 2048), (130, 72, 40), (640, 264, 3200), (1300, 512, 2048)])
+                                   (208, 4320, 480), (13, 7680, 896), (1, 1024, 2048), (130, 72, 40), (640, 264, 3200), (1300, 512, 2048),
+                                   (32, 2048, 12288), (31, 1024, 4096), (20, 3072, 1000), (33, 1024, 1024)])  # <= 32 rows: the 32-column skinny instantiation
 def test_tcgen05_gemm_vs_oracle(gpu06, oracle_lib, M, K, N):
     """tcgen05/TMEM/TMA GEMM at encoder / prefill / conv shapes incl. ragged M, N, K tails."""
     L = oracle_lib().lib

@@ -177,11 +177,11 @@ def test_skinny_gemm_split_plan_invariants(pkg):
         assert plan(M, K, N, out) == 0
         return list(out)
 
-    for M in (1, 13, 47, 61, 64, 65, 128, 129, 143, 256):
+    for M in (1, 13, 32, 33, 47, 61, 64, 65, 128, 129, 143, 256):
         for K in (8, 64, 72, 896, 1024, 2048, 3584, 4320, 6144, 7680):
             for N in (40, 128, 480, 896, 1024, 2048, 4096, 12288, 151936):
                 path, MP, tiles, kb, S, per = get(M, K, N)
-                assert path == 0 and MP == (64 if M <= 64 else 128 if M <= 128 else 256)
+                assert path == 0 and MP == (32 if M <= 32 else 64 if M <= 64 else 128 if M <= 128 else 256)
                 assert tiles == -(-N // 128) and kb == -(-K // 64)
                 assert 1 <= S <= 8 and per >= 1
                 assert (S - 1) * per < kb <= S * per          # every split owns at least one k-block, all are covered

@@ -36,6 +36,9 @@ def pipeline_mode(name):   # the epilogue each shape has in the pipeline: 0 f32 
 if len(sys.argv) > 1 and sys.argv[1] == "decode":   # one decode step of the batched path at 128 sequences (1.7B and 0.6B)
     shapes = [("dec.qkv", 128, 2048, 4096), ("dec.wo", 128, 2048, 2048), ("dec.gu", 128, 2048, 12288), ("dec.down", 128, 6144, 2048), ("dec.head", 128, 2048, 151936),
               ("dec06.qkv", 128, 1024, 4096), ("dec06.wo", 128, 2048, 1024), ("dec06.gu", 128, 1024, 6144), ("dec06.down", 128, 3072, 1024), ("dec06.head", 128, 1024, 151936)]
+if len(sys.argv) > 1 and sys.argv[1] == "decode32":  # decode step of a 32-sequence group (an 8-GPU shard of configs[4]) and a 31-row prompt: QASR_GEMM_MP32=0|1
+    shapes = [("dec.qkv", 32, 2048, 4096), ("dec.wo", 32, 2048, 2048), ("dec.gu", 32, 2048, 12288), ("dec.down", 32, 6144, 2048), ("dec.head", 32, 2048, 151936),
+              ("dec06.qkv", 23, 1024, 4096), ("dec06.wo", 23, 2048, 1024), ("dec06.gu", 23, 1024, 6144), ("dec06.down", 23, 3072, 1024), ("dec06.head", 23, 1024, 151936)]
 for name, M, K, N in shapes:
     us = C.c_double(0)
     rc = f(eng.ctx, M, K, N, 64, pipeline_mode(name), C.byref(us))
