@@ -134,6 +134,7 @@ struct StreamParams {
     int l2_issue;                          // units prefetched per poll iteration
     int l2_ahead_units;                    // second-level prefetch distance into L2, in 2 KB units per warp (0 = off)
     int sr_chunk;                          // producer of qasr_stream_r.cu: bytes per bulk copy
+    int sr_chunk_head;                     // ... for the rounds of the lm_head phase (pure streaming: larger copies, fewer issues)
     float *dbg_logits;                     // test hook (NULL in production): [nseq][V] logits of the LAST step of the launch
     float *dbg_hidden;                     // test hook (NULL in production): [nseq][H] post-final-norm hidden state
 };

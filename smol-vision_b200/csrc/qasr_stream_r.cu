@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
             const uint32_t ahead = q == 0 ? (uint32_t)min(p.l2_ahead_units, 64) : 0u;
             for (uint32_t r = 0; r < ahead && r < rounds_per_step; r++) sr_bulk_prefetch_l2(src + (size_t)r * SR_ROUND, SR_ROUND);
             uint32_t slot = 0, pass = 0, rr = 0, pr = ahead % rounds_per_step; // ring slot, ring pass, round within the step, prefetch cursor
-            const uint32_t chunk = (uint32_t)p.sr_chunk, chunks_per_round = SR_ROUND / chunk;
+            // the rounds of the lm_head phase close every step: no exchange waits there, so a copy costs its ~0.1 us of issue time and
+            // nothing else - with the 4 KB copies that suit the layer phases of the 0.6B dims the head was issue-bound (8 copies per round)
+            const uint32_t head_from = rounds_per_step - (uint32_t)((sk_g0(p.V >> 4, b + 1, G) - sk_g0(p.V >> 4, b, G)) * (p.H >> 10));
             bool stopping = false;
             uint32_t drain_from = 0;
             for (uint32_t issued = 0; issued < total; issued++) {
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(SR_ALL_THREADS, 1) decode_rounds_kernel(const 
                 if (q == 0) sr_mbar_expect_tx(bar_full + 8 * slot, SR_ROUND);
                 const uint32_t dst = sk_smem_u32(sm_ring + (size_t)slot * SR_ROUND);
                 const uint8_t *g = src + (size_t)rr * SR_ROUND;
+                const uint32_t chunk = (uint32_t)(rr >= head_from ? p.sr_chunk_head : p.sr_chunk), chunks_per_round = SR_ROUND / chunk;
                 for (uint32_t c = q; c < chunks_per_round; c += n_prod) sr_bulk_load(dst + c * chunk, g + (size_t)c * chunk, chunk, bar_full + 8 * slot, pol);
                 if (ahead) { sr_bulk_prefetch_l2(src + (size_t)pr * SR_ROUND, SR_ROUND); if (++pr == rounds_per_step) pr = 0; }
                 if (++rr == rounds_per_step) rr = 0;
@@ -662,11 +665,12 @@ int launch_decode_rounds(cudaStream_t s, const StreamParams &p, int grid, char *
     const int kmax = p.I > 2048 ? p.I : 2048;
     int nslot = (int)((g_sr_slots_dev[dev & 31] - SrLayout::rest(kmax, p.H)) / SR_ROUND);
     if (nslot > SR_MAX_SLOTS) nslot = SR_MAX_SLOTS;
-    static int e_slots = -2, e_chunk = -2, e_ahead = -2, e_prod = -2, e_pad = -2;
+    static int e_slots = -2, e_chunk = -2, e_ahead = -2, e_prod = -2, e_pad = -2, e_chunk_head = -2;
     if (e_slots == -2) {
         const char *e;
         e = getenv("QASR_SR_SLOTS"); e_slots = e ? atoi(e) : -1;
         e = getenv("QASR_SR_CHUNK"); e_chunk = e ? atoi(e) : -1;
+        e = getenv("QASR_SR_CHUNK_HEAD"); e_chunk_head = e ? atoi(e) : -1;
         e = getenv("QASR_SR_L2AHEAD"); e_ahead = e ? atoi(e) : -1;
         e = getenv("QASR_SR_PRODUCERS"); e_prod = e ? atoi(e) : -1;
         e = getenv("QASR_SR_PAD_KB"); e_pad = e ? atoi(e) : 0;
@@ -677,6 +681,7 @@ int launch_decode_rounds(cudaStream_t s, const StreamParams &p, int grid, char *
     if (e_pad > 0 && smem + (size_t)e_pad * 1024 <= (size_t)g_sr_slots_dev[dev & 31]) smem += (size_t)e_pad * 1024; // experiment: unused shared memory (shrinks L1)
     StreamParams q = p;
     q.sr_chunk = (e_chunk >= 1024 && SR_ROUND % e_chunk == 0) ? e_chunk : (small ? 4096 : 8192);
+    q.sr_chunk_head = (e_chunk_head >= 1024 && SR_ROUND % e_chunk_head == 0) ? e_chunk_head : 8192;
     q.l2_ahead_units = e_ahead >= 0 ? e_ahead : (small ? 3 : 6);
     const int n_prod = (e_prod >= 1 && e_prod <= SR_MAX_PRODUCERS) ? e_prod : SR_DEFAULT_PRODUCERS;
     void *args[] = {(void *)&q, (void *)&nslot};
