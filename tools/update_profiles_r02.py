@@ -19,6 +19,7 @@ def row(e):
 
 names = {
     "r2_ncu_skinny_prefill": "single-utterance prefill chain (1.7B, M = 61): `gemm_tc_skinny_kernel<64,6>` - WO, gate/up, down, QKV of two layers",
+    "r2_ncu_skinny_encoder_final": "single-utterance encoder chain on the final build (1.7B encoder, T = 47): `gemm_tc_skinny_kernel<64,6>` - QKV, WO, fc1, fc2 of two layers (`ncu -k regex:gemm_tc_skinny_kernel -s 300 -c 8 python tools/profile_utt.py 1.7b 2`)",
     "r2_ncu_attn_prefill": "`attn_prefill_kernel` (P = 61)", "r2_ncu_attn_windowed": "`attn_windowed_kernel` (T = 47)",
     "r2_ncu_gemm_batched_prefill": "batched prefill (16 x 30 s, 1.7B, M = 6464), persistent one-CTA `gemm_tc_kernel<256,3>` (before the 2-CTA variant) - gate/up, down, QKV, WO",
     "r2_ncu_gemm_batched_encoder": "batched encoder (8 x 30 s per pass): `gemm_tc_kernel` - conv3, conv_out, QKV ...",
@@ -27,7 +28,7 @@ names = {
 tables = []
 for k, t in names.items():
     tables.append(f"\n{t}:\n\n| kernel | grid | us | DRAM MB | DRAM % | tensor pipe % | L2 % | warps active % | regs |\n|---|---:|---:|---:|---:|---:|---:|---:|---:|")
-    tables += [row(e) for e in ncu[k][:6]]
+    tables += [row(e) for e in ncu[k][:8]]
 
 s = f"""
 
