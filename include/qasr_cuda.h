@@ -14,6 +14,11 @@
  * decoder call takes `kv_len` = the number of valid cached positions BEFORE the call
  * (the reference's ctx->kv_cache_len, which callers reset to 0 per segment or roll back
  * for streaming prefix reuse).  Truncation moves no data.
+ *
+ * Threading and process-wide state (reference: single caller thread, global thread pool and scratch): one
+ * inference process per GPU is the supported mode.  Calls on ONE context must come from one thread at a time; contexts on
+ * different devices of one process are independent.  Process-wide, read once: the QASR_* environment switches,
+ * the split-K scratch per device, the cuTensorMapEncodeTiled entry point; per thread: the error text.
  */
 #ifndef QASR_CUDA_H
 #define QASR_CUDA_H
