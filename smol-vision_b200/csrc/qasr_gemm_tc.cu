@@ -1111,6 +1111,12 @@ bool gemm_tc_can_fuse_norm(int M, int K, int N) {
 
 bool gemm_tc_can_fuse_qk(int M, int K) { return gemm_tc_can_fuse_norm(M, K, 4096); }
 
+// host-only debug hook (tests/test_host_logic.py): bit 0 the consumer side (row scalars), bit 1 the producer side of a fused RMSNorm
+// (RESIDUAL GEMM of this shape), bit 2 q/k-norm + RoPE + KV store in a QKV GEMM with these M, K
+extern "C" int qasr_debug_gemm_fusion(int M, int K, int N) {
+    return (gemm_tc_can_scale_rows(M) ? 1 : 0) | (gemm_tc_can_fuse_norm(M, K, N) ? 2 : 0) | (gemm_tc_can_fuse_qk(M, K) ? 4 : 0);
+}
+
 int launch_gemm_tc(cudaStream_t s, const bf16_t *A_hi, const bf16_t *A_lo, int M, int K, const bf16_t *W, int N,
                    const GemmEpilogue &epi) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;

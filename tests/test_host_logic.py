@@ -193,6 +193,26 @@ def test_skinny_gemm_split_plan_invariants(pkg):
     assert [get(61, 2048, 4096)[4], get(61, 2048, 2048)[4], get(61, 2048, 12288)[4], get(61, 6144, 2048)[4], get(47, 4096, 1024)[4]] == [3, 5, 1, 5, 8]
 
 
+def test_fused_epilogue_decisions(pkg):
+    """Which GEMMs carry the fused RMSNorm / q-k-norm + RoPE epilogues (host logic of gemm_tc_can_fuse_*): the skinny split-K path only -
+    at most 256 rows, whole 128-column tiles, a split factor above 1 - so the production chains fuse exactly where DESIGN 3.2 says."""
+    import ctypes as C
+    lib = pkg.load_library()
+    f = lib.qasr_debug_gemm_fusion
+    f.argtypes = [C.c_int, C.c_int, C.c_int]
+    f.restype = C.c_int
+    for H, I in ((1024, 3072), (2048, 6144)):                       # 0.6B / 1.7B decoder dims
+        for M in (1, 23, 31, 61, 128, 157, 256):                    # batched decode groups, single-utterance prompts
+            assert f(M, 2048, H) & 3 == 3                           # WO -> post-attention norm
+            assert f(M, I, H) & 3 == 3                              # down -> next input norm
+            assert f(M, H, 4096) & 4                                # QKV: q/k-norm + RoPE + KV store
+            assert f(M, H, 2 * I) & 1 and f(M, H, 151936) & 1       # gate/up and lm_head scale their rows
+        for M in (257, 274, 404, 25856):                            # long prompts, batched prefill: large-tile kernels, stand-alone norms
+            assert f(M, 2048, H) == 0 and f(M, H, 4096) == 0
+    assert f(61, 2048, 1000) & 2 == 0                               # ragged N: no whole tiles
+    assert f(61, 64, 2048) & 2 == 0                                 # one k-block: no split-K reduction path
+
+
 def test_find_split_point_equals_scalar_restatement(pkg):
     """The vectorised split search must pick exactly the window the reference's scalar loop picks (qwen_asr.c:617-643:
     100 ms windows every 50 ms inside +-search_sec, strict '<' so the first minimum wins, centre of the window)."""
