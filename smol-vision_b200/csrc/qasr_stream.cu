@@ -812,9 +812,12 @@ int stream_init(void) {
         cudaGetLastError();
         return -1;
     }
-    int grid = sms;
-    // fewer CTAs = cheaper exchanges, less streaming headroom.  At least 16 CTAs per sequence: the attention roles are
-    // (sequence, head, split) CTAs and S = min(S, G / (16 * NSEQ)) must stay >= 1.
+    // Fewer CTAs = cheaper exchanges and fewer idle pollers, less streaming headroom.  From 128 CTAs up the busiest CTA of every phase has
+    // the same number of rounds for both models (256 QKV groups, 64 / 128 output groups, 384 / 768 gate-up groups: ceil(groups / G) does
+    // not change between 128 and 148), so the extra CTAs only add exchange traffic: measured on B200 (profiles/r02_decode_latency.txt)
+    // 1.7B 638.7 us per token at 148 CTAs, 616-618 at 130-134, 623 at 128, 713 at 126 (a seventh gate-up group); 0.6B 385 -> 383.
+    // At least 16 CTAs per sequence: the attention roles are (sequence, head, split) CTAs and S = min(S, G / (16 * NSEQ)) must stay >= 1.
+    int grid = sms >= 132 ? 132 : sms;
     { const char *e = getenv("QASR_SK_GRID"); if (e && atoi(e) >= 16 * QASR_STREAM_MAX_SEQS && atoi(e) <= sms) grid = atoi(e); }
     if (grid < 16 * QASR_STREAM_MAX_SEQS) {
         snprintf(g_sk_err, sizeof g_sk_err, "decode stream kernel needs at least %d SMs (device has %d)", 16 * QASR_STREAM_MAX_SEQS, sms);
