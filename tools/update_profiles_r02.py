@@ -5,11 +5,13 @@ import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 P = os.path.join(ROOT, "profiles")
 d = json.load(open(os.path.join(P, "r02_bench_default.json")))
+d148 = json.load(open(os.path.join(P, "r02_bench_default_148cta.json")))  # 1-GPU line of the build the 2- / 8-GPU lines were measured on (148-CTA decode grid)
 d2 = json.load(open(os.path.join(P, "r02_bench_default_2gpu.json")))
 d8 = json.load(open(os.path.join(P, "r02_bench_default_8gpu.json")))
 ref = json.load(open(os.path.join(P, "r02_bench_reference_arm.json")))
 ncu = json.load(open(os.path.join(P, "r02_ncu_summary.json")))
 st, st2, st8 = d["extra"]["strong"], d2["extra"]["strong"], d8["extra"]["strong"]
+st148 = d148["extra"]["strong"]
 
 
 def row(e):
@@ -37,7 +39,7 @@ s = f"""
 | file | what | how |
 |---|---|---|
 | `r02_bench_default.json` | **default bench line of round 2**: configs[1] headline + `roofline_0p6b` + `extra.strong` (configs[4] 256 x 30 s and configs[2] 3600 s / 180 segments on the ranks of the run) + `gemm_rooflines` (algorithmic and issued) + cpu_baseline | `python bench.py` (about 50 s on the box) |
-| `r02_bench_default_2gpu.json`, `r02_bench_default_8gpu.json` | the same line on 2 and 8 GPUs | `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps 10 --warmup 3` |
+| `r02_bench_default_148cta.json`, `r02_bench_default_2gpu.json`, `r02_bench_default_8gpu.json` | the line on 1, 2 and 8 GPUs of the build before the decode grid change (148 CTAs) | `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps 10 --warmup 3` |
 | `r02_bench_reference_arm.json` | reference arm: the reference's own CPU path (`oracle/_ref`, 16 host cores) | `python bench.py --impl reference --steps 3 --warmup 1` |
 | `r02_ncu_summary.json` | `ncu --set full` captures of the kernels VERDICT r1 asked evidence for: skinny GEMMs of the prefill chain at M = 61, `attn_prefill_kernel`, `attn_windowed_kernel`, the persistent large-tile GEMM in the batched prefill / encoder, conv stem kernels, `attn_decode_batch_kernel` | `bash tools/ncu_round2.sh` (each profiled command first exited 0 without ncu), summarised by `tools/ncu_summary.py` |
 | `r02_launches_batched_64x30s.csv.gz` | ncu launch list of the first version of the batched path: 64 x 30 s utterances, 1.7B, 3 decode steps | `ncu --metrics gpu__time_duration.sum --clock-control none --csv python tools/batch_profile.py 1.7b 64 30 3 1` |
@@ -64,7 +66,8 @@ tests pin what the bench times. 8 GPUs: {d8['value']:.0f} x (one replica per GPU
 | configs[4]: 256 x 30 s utterances, 1.7B, 128 tokens each | **{st['configs[4]']['value']:.0f} x** ({st['configs[4]']['ms_per_step'] / 1e3:.2f} s for 7680 s of audio, {st['configs[4]']['decoder_tok_s']:.0f} tokens/s; round 1: 405 x) | {st2['configs[4]']['value']:.0f} x | {st8['configs[4]']['value']:.0f} x | {st['configs[4]']['sequences_per_decode_step']} / {st2['configs[4]']['sequences_per_decode_step']} / {st8['configs[4]']['sequences_per_decode_step']} | {st['configs[4]']['roofline']['frac']:.2f} of the HBM peak (weights once + f32 KV rows of every sequence) |
 | configs[2]: 3600 s recording, -S 20 -W 3, 180 segments, 0.6B | **{st['configs[2]']['value']:.0f} x** ({st['configs[2]']['ms_per_step'] / 1e3:.2f} s, {st['configs[2]']['decoder_tok_s']:.0f} tokens/s; round 1: 770 x) | {st2['configs[2]']['value']:.0f} x | {st8['configs[2]']['value']:.0f} x | {st['configs[2]']['sequences_per_decode_step']} / {st2['configs[2]']['sequences_per_decode_step']} / {st8['configs[2]']['sequences_per_decode_step']} | {st['configs[2]']['roofline']['frac']:.2f} |
 
-2 GPUs: {st2['configs[4]']['value'] / st['configs[4]']['value']:.2f} x / {st2['configs[2]']['value'] / st['configs[2]']['value']:.2f} x of one GPU; 8 GPUs: {st8['configs[4]']['value'] / st['configs[4]']['value']:.2f} x / {st8['configs[2]']['value'] / st['configs[2]']['value']:.2f} x; configs[1] replicas (weak): {d2['value']:.0f} x and {d8['value']:.0f} x = {d8['value'] / d['value'] / 8:.2f} of linear at 8.
+2 GPUs: {st2['configs[4]']['value'] / st148['configs[4]']['value']:.2f} x / {st2['configs[2]']['value'] / st148['configs[2]']['value']:.2f} x of one GPU; 8 GPUs: {st8['configs[4]']['value'] / st148['configs[4]']['value']:.2f} x / {st8['configs[2]']['value'] / st148['configs[2]']['value']:.2f} x; configs[1] replicas (weak): {d2['value']:.0f} x and {d8['value']:.0f} x = {d8['value'] / d148['value'] / 8:.2f} of linear at 8.
+(The 2- and 8-GPU lines were measured before the decode grid went from 148 to 132 CTAs; ratios are against the 1-GPU line of that build, `r02_bench_default_148cta.json`: {d148['value']:.1f} x, configs[4] {st148['configs[4]']['value']:.0f} x, configs[2] {st148['configs[2]']['value']:.0f} x. The grid only changes the single-sequence decode kernel, i.e. the configs[1] replicas.)
 Strong scaling is bounded by the shard size, not by a collective (there is none): at 8 GPUs a rank holds 32 utterances / 22-23 segments, so
 32 / 23 sequences share each pass over the weights instead of 128 / 90 (one GPU, 1.7B: 24.2k / 17.5k / 12.2k tokens/s at 128 / 64 / 32 sequences per
 step) and the encoder / prefill GEMMs run at a quarter of the rows; slowest / mean rank {st8['configs[4]']['rank_ms']['imbalance']:.3f} (configs[4]) and {st8['configs[2]']['rank_ms']['imbalance']:.3f} (configs[2]).
