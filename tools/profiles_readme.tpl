@@ -1,8 +1,8 @@
-# profiles/ — measured evidence, named per round (all on B200, sm_100a, this pool)
+# profiles/ — measured evidence, named per round (all on B200, sm_100a, this pool). The round-1 section comes first; the CURRENT numbers are in "Round 2" further down.
 
 | file | what | how |
 |---|---|---|
-| `r01_bench_stream_cfg2.json` | **current headline bench line** (decode_stream_kernel default) incl. roofline, gemm_rooflines, cpu_baseline | `python bench.py` |
+| `r01_bench_stream_cfg2.json` | headline bench line of ROUND 1 (decode_stream_kernel; superseded by `r02_bench_default.json`, see "Round 2" below) incl. roofline, gemm_rooflines, cpu_baseline | `python bench.py` |
 | `r01_bench_reference_arm.json` | reference arm: the reference's own CPU path (oracle/_ref, 16 host cores) | `python bench.py --impl reference --steps 3 --warmup 1` |
 | `r01_bench_stream_cfg1_0p6b.json`, `r01_bench_stream_utt30.json` | the same bench on configs[0] (0.6B, 11 s) and one configs[4] unit (1.7B, 30 s, 128 tokens) | `python bench.py --workload cfg1|utt30` |
 | `r01_bench_stream_cfg3.json`, `_cfg4.json`, `_cfg5.json` | configs[2] (0.6B, -S 20 over a 3600 s recording = 180 segments, 4 sequences per decode step), configs[3] (0.6B stream, 2 s chunks over 60 s, per-chunk latency), configs[4] (1.7B, 64 x 30 s utterances, 2 sequences per decode step) | `python bench.py --workload cfg3|cfg4|cfg5 [--utterances 64]` |
